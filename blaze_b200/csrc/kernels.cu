@@ -1,0 +1,690 @@
+// Hand-written sm_100a kernels of the Filter / Project / HashAgg hot path (generic, VM-driven forms;
+// the specialised streaming kernels live in kernels_fast.cu).
+//
+//   filter_project_kernel  K1+K2+K3 of SURVEY.md §2.4 fused: predicate mask, ordered stream compaction
+//                          (single pass, decoupled look-back) and projection — filtered rows never
+//                          round-trip through HBM.  Replaces CachedExprsEvaluator::filter_project
+//                          (cached_exprs_evaluator.rs:82-166).
+//   agg_update_kernel      K4+K5+K6(+K7): key evaluation, open-addressing upsert and accumulator update
+//                          in one pass.  Replaces HashingData::update_batch (agg_table.rs:519-538):
+//                          create_grouping_rows + AggHashMap::upsert_records + partial_update/partial_merge.
+//   agg_emit_kernel        K8+K9: table scan -> dense Arrow columns (build_agg_columns, agg_ctx.rs:303-326).
+//   frozen_* kernels       the reference's frozen accumulator-row byte format (acc.rs:335-365,
+//                          count.rs:193-211, io/mod.rs:60-83) for the Binary `#9223372036854775807` column.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+#include "vm.cuh"
+
+namespace b200q {
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ void load_program(const VmProgram* __restrict__ g, VmInstr* s_code, uint64_t* s_pool) {
+  const uint32_t nc = g->n_code, np = g->n_pool;
+  for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) s_code[i] = g->code[i];
+  for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) s_pool[i] = g->pool[i];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FilterExec / ProjectExec
+// ---------------------------------------------------------------------------------------------------
+constexpr int FP_BLOCK = 256;
+constexpr int FP_R = 2;
+constexpr int FP_TILE = FP_BLOCK * FP_R;
+constexpr int FP_NW = FP_BLOCK / 32;
+constexpr unsigned long long ST_AGG = 1ULL << 62, ST_PREFIX = 2ULL << 62, ST_VALUE = (1ULL << 62) - 1;
+
+int64_t filter_project_num_tiles(int64_t n) { return (n + FP_TILE - 1) / FP_TILE; }
+
+struct FpSink {
+  const OutTable& outs;
+  long long wbase[FP_R];     // output position of the first surviving row of this warp-row
+  unsigned amask[FP_R];      // ballot of surviving lanes
+  bool* alive;
+  unsigned lt;
+
+  __device__ __forceinline__ void put_bits(uint32_t* bitmap, int r, bool bit) const {
+    // compact this warp-row's bits by the survivor mask and OR them into the pre-zeroed bitmap
+    const unsigned m = amask[r];
+    const unsigned rank = __popc(m & lt);
+    const unsigned w = __reduce_or_sync(0xffffffffu, (alive[r] && bit) ? (1u << rank) : 0u);
+    if ((threadIdx.x & 31) == 0 && m) {
+      const unsigned cnt = __popc(m);
+      const unsigned long long p = (unsigned long long)wbase[r];
+      const unsigned sh = (unsigned)(p & 31);
+      if (w << sh) atomicOr(bitmap + (p >> 5), w << sh);
+      if (sh + cnt > 32 && (w >> (32 - sh))) atomicOr(bitmap + (p >> 5) + 1, w >> (32 - sh));
+    }
+  }
+
+  __device__ __forceinline__ void out(int r, int idx, int phys, uint64_t lo, uint64_t hi, bool valid) const {
+    if (outs.validity[idx]) put_bits(outs.validity[idx], r, valid);
+    if (phys == PH_BOOL) { put_bits((uint32_t*)outs.values[idx], r, lo != 0); return; }
+    if (!alive[r]) return;
+    const long long p = wbase[r] + __popc(amask[r] & lt);
+    void* v = outs.values[idx];
+    switch (phys) {
+      case PH_I8: ((int8_t*)v)[p] = (int8_t)lo; break;
+      case PH_I16: ((int16_t*)v)[p] = (int16_t)lo; break;
+      case PH_I32: ((int32_t*)v)[p] = (int32_t)lo; break;
+      case PH_I64: case PH_F64: ((uint64_t*)v)[p] = lo; break;
+      case PH_F32: ((float*)v)[p] = (float)as_f64(lo); break;
+      default: ((uint64_t*)v)[2 * p] = lo; ((uint64_t*)v)[2 * p + 1] = hi; break;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(FP_BLOCK) filter_project_kernel(const VmProgram* __restrict__ prog, const ColTable cols, const OutTable outs,
+                                                                  long long n, long long ntiles, int has_filters,
+                                                                  unsigned long long* tile_status, unsigned long long* scratch) {
+  __shared__ VmInstr s_code[VM_MAX_CODE];
+  __shared__ uint64_t s_pool[VM_MAX_POOL];
+  __shared__ long long s_tile, s_excl;
+  __shared__ unsigned s_cnt[FP_R * FP_NW], s_off[FP_R * FP_NW];
+  load_program(prog, s_code, s_pool);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* err = (int*)(scratch + 2);
+
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(scratch + 0, 1ULL);   // ticket: lower tiles are always already running
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= ntiles) break;
+    long long row[FP_R]; bool inb[FP_R], alive[FP_R];
+#pragma unroll
+    for (int r = 0; r < FP_R; r++) { row[r] = tile * FP_TILE + r * FP_BLOCK + threadIdx.x; inb[r] = row[r] < n; alive[r] = inb[r]; }
+
+    FpSink sink{outs, {}, {}, alive, lanemask_lt()};
+    int pc = 0;
+    if (has_filters) {
+      NullSink ns;
+      pc = vm_run<FP_R>(s_code, s_pool, 0, cols, row, inb, alive, err, ns);     // stops after VM_COMPACT
+#pragma unroll
+      for (int r = 0; r < FP_R; r++) { sink.amask[r] = __ballot_sync(0xffffffffu, alive[r]); if (lane == 0) s_cnt[r * FP_NW + warp] = __popc(sink.amask[r]); }
+      __syncthreads();
+      if (warp == 0) {
+        unsigned v = lane < FP_R * FP_NW ? s_cnt[lane] : 0, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane < FP_R * FP_NW) s_off[lane] = incl - v;
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+        // decoupled look-back over the tile status words
+        unsigned long long excl = 0;
+        if (tile > 0) {
+          if (lane == 0) st_relaxed_u64(tile_status + tile, ST_AGG | total);
+          long long j = tile - 1;
+          while (true) {
+            const long long idx = j - lane;
+            unsigned long long s = idx >= 0 ? ld_relaxed_u64(tile_status + idx) : ST_PREFIX;
+            if (__any_sync(0xffffffffu, (s >> 62) == 0)) continue;                 // a predecessor has not published yet
+            const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+            unsigned long long val = s & ST_VALUE;
+            if (pm) {
+              const int first = __ffs(pm) - 1;                                     // nearest tile with an inclusive prefix
+              if ((int)lane > first) val = 0;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            excl += val;
+            if (pm) break;
+            j -= 32;
+          }
+        }
+        if (lane == 0) {
+          st_relaxed_u64(tile_status + tile, ST_PREFIX | (excl + total));
+          s_excl = (long long)excl;
+          if (tile == ntiles - 1) scratch[1] = excl + total;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < FP_R; r++) sink.wbase[r] = s_excl + s_off[r * FP_NW + warp];
+    } else {
+#pragma unroll
+      for (int r = 0; r < FP_R; r++) { sink.amask[r] = __ballot_sync(0xffffffffu, alive[r]); sink.wbase[r] = tile * FP_TILE + r * FP_BLOCK + warp * 32; }
+      if (tile == ntiles - 1 && threadIdx.x == 0) scratch[1] = (unsigned long long)n;
+    }
+    vm_run<FP_R>(s_code, s_pool, pc, cols, row, inb, alive, err, sink);
+    __syncthreads();
+  }
+}
+
+int launch_filter_project(const VmProgram* d_prog, const ColTable& cols, const OutTable& outs, int nouts, int64_t n, bool has_filters,
+                          unsigned long long* d_tile_status, unsigned long long* d_scratch, cudaStream_t s) {
+  (void)nouts;
+  const int64_t ntiles = filter_project_num_tiles(n);
+  if (ntiles == 0) return 0;
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t grid = ntiles < (int64_t)sms * 8 ? ntiles : (int64_t)sms * 8;     // persistent: a multiple of the SM count
+  filter_project_kernel<<<(unsigned)grid, FP_BLOCK, 0, s>>>(d_prog, cols, outs, n, ntiles, has_filters ? 1 : 0, d_tile_status, d_scratch);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// HashAgg: update
+// ---------------------------------------------------------------------------------------------------
+constexpr int AG_BLOCK = 256;
+constexpr int AG_R = 2;
+constexpr int AG_TILE = AG_BLOCK * AG_R;
+constexpr unsigned TAG_EMPTY = 0, TAG_LOCKED = 1;
+constexpr unsigned FLAG_SLOT_LOCK = 1u << 15;     // guards 128-bit min/max updates
+
+struct AggSink {
+  uint64_t (*buf)[AGG_MAX_ROW_WORDS];
+  uint32_t* vb;
+  const uint8_t* out_word;
+  __device__ __forceinline__ void out(int r, int idx, int phys, uint64_t lo, uint64_t hi, bool valid) const {
+    const int w = out_word[idx];
+    buf[r][w] = lo;
+    if (phys == PH_DEC128) buf[r][w + 1] = hi;
+    if (valid) vb[r] |= 1u << idx;
+  }
+};
+
+__device__ __forceinline__ uint64_t hash_keys(const AggLayout& lay, const uint64_t* buf, uint32_t vb, uint32_t& knull, uint64_t* kw) {
+  uint64_t h = 0x9E3779B97F4A7C15ULL;
+  knull = 0;
+  int w = 0;
+  for (int k = 0; k < lay.nkeys; k++) {
+    const int o = lay.key_out[k];
+    const bool valid = (vb >> o) & 1;
+    if (!valid) knull |= 1u << k;
+    for (int i = 0; i < lay.key_nwords[k]; i++) {
+      const uint64_t v = valid ? buf[lay.out_word[o] + i] : 0;   // NULL keys are canonicalised to 0 + null bit
+      kw[w++] = v;
+      h = mix64(h ^ v);
+    }
+  }
+  return mix64(h ^ knull);
+}
+
+__device__ __forceinline__ void slot_mark(unsigned long long* slot, unsigned flags_seen, int vbit) {
+  if (vbit != 0xFF && !((flags_seen >> vbit) & 1)) atomicOr((unsigned*)slot + 1, 1u << vbit);
+}
+
+__device__ __forceinline__ void dec_minmax(unsigned long long* slot, int word, i128_t v, bool is_min) {
+  unsigned* flags = (unsigned*)slot + 1;
+  while (atomicOr(flags, FLAG_SLOT_LOCK) & FLAG_SLOT_LOCK) {}
+  __threadfence();
+  volatile unsigned long long* p = slot + word;
+  const i128_t cur = mk128(p[0], p[1]);
+  if (is_min ? v < cur : v > cur) { p[0] = lo64(v); p[1] = hi64(v); }
+  __threadfence();
+  atomicAnd(flags, ~FLAG_SLOT_LOCK);
+}
+
+// find-or-insert the key, then apply every accumulator update; returns false when the row had to be deferred
+__device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable& tab, const uint64_t* buf, uint32_t vb) {
+  uint64_t kw[AGG_MAX_KEYS * 2];
+  uint32_t knull;
+  const uint64_t h = hash_keys(lay, buf, vb, knull, kw);
+  const unsigned tag = (unsigned)(h >> 32) | 0x80000000u;
+  uint64_t s = h & tab.mask;
+  unsigned long long* slot;
+  unsigned flags;
+  while (true) {
+    slot = tab.slots + s * (uint64_t)lay.slot_words;
+    const unsigned long long hdr = ld_relaxed_u64(slot);
+    const unsigned t = (unsigned)hdr;
+    flags = (unsigned)(hdr >> 32);
+    if (t == tag) {
+      bool eq = (flags >> 16) == knull;
+      for (int i = 0; eq && i < lay.nkw; i++) eq = ld_relaxed_u64(slot + 1 + i) == kw[i];
+      if (eq) break;
+    } else if (t == TAG_EMPTY) {
+      if (ld_relaxed_u64(tab.counters) >= tab.max_groups) return false;       // table is at its load limit: defer the row
+      if (atomicCAS((unsigned*)slot, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
+        for (int i = 0; i < lay.nkw; i++) slot[1 + i] = kw[i];
+        for (int i = 1 + lay.nkw; i < lay.slot_words; i++) slot[i] = lay.init[i];
+        flags = lay.init_flags | (knull << 16);
+        ((unsigned*)slot)[1] = flags;
+        __threadfence();
+        st_release_u32((unsigned*)slot, tag);
+        atomicAdd(tab.counters, 1ULL);
+        break;
+      }
+      continue;                                                                 // lost the race: look at the same slot again
+    } else if (t == TAG_LOCKED) {
+      continue;                                                                 // being published by another thread
+    }
+    s = (s + 1) & tab.mask;
+  }
+  // accumulate (K6 / K7)
+  for (int j = 0; j < lay.nacc; j++) {
+    const AccOp a = lay.acc[j];
+    const int o = a.arg_out[0];
+    const uint64_t* arg = buf + lay.out_word[o];
+    bool valid = true;
+    for (int i = 0; i < a.nargs; i++) valid = valid && ((vb >> a.arg_out[i]) & 1);
+    if (!valid) continue;
+    unsigned long long* w = slot + a.word;
+    switch (a.kind) {
+      case ACC_ADD_I64: red_add_u64(w, arg[0]); break;
+      case ACC_ADD_F64: red_add_f64(w, as_f64(arg[0])); break;
+      case ACC_ADD_DEC: {
+        const unsigned long long old = atomicAdd(w, (unsigned long long)arg[0]);
+        const unsigned long long carry = (old + arg[0]) < old ? 1ULL : 0ULL;     // exact: every carry is counted once, adds commute
+        red_add_u64(w + 1, arg[1] + carry);
+        break;
+      }
+      case ACC_COUNT: red_add_u64(w, 1ULL); break;
+      case ACC_MIN_I64: red_min_s64(w, (long long)arg[0]); break;
+      case ACC_MAX_I64: red_max_s64(w, (long long)arg[0]); break;
+      case ACC_MIN_F64: red_min_s64(w, total_order_key(arg[0])); break;
+      case ACC_MAX_F64: red_max_s64(w, total_order_key(arg[0])); break;
+      case ACC_MIN_DEC: dec_minmax(slot, a.word, mk128(arg[0], arg[1]), true); break;
+      default: dec_minmax(slot, a.word, mk128(arg[0], arg[1]), false); break;
+    }
+    slot_mark(slot, flags, a.vbit);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(AG_BLOCK) agg_update_kernel(const VmProgram* __restrict__ prog, const ColTable cols, const AggLayout lay, const AggTable tab,
+                                                              long long row_begin, long long n, const uint32_t* __restrict__ row_list) {
+  __shared__ VmInstr s_code[VM_MAX_CODE];
+  __shared__ uint64_t s_pool[VM_MAX_POOL];
+  load_program(prog, s_code, s_pool);
+  int* err = (int*)(tab.counters + 2);
+  const long long ntiles = (n + AG_TILE - 1) / AG_TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long row[AG_R]; bool inb[AG_R], alive[AG_R];
+    uint32_t rel[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      const long long i = tile * AG_TILE + r * AG_BLOCK + threadIdx.x;
+      inb[r] = i < n; alive[r] = inb[r];
+      rel[r] = inb[r] ? (row_list ? row_list[i] : (uint32_t)i) : 0;
+      row[r] = row_begin + rel[r];
+    }
+    uint64_t buf[AG_R][AGG_MAX_ROW_WORDS];
+    uint32_t vb[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) vb[r] = 0;
+    AggSink sink{buf, vb, lay.out_word};
+    vm_run<AG_R>(s_code, s_pool, 0, cols, row, inb, alive, err, sink);
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      if (alive[r] && !agg_upsert(lay, tab, buf[r], vb[r])) {
+        const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL);
+        tab.deferred[at] = rel[r];
+      }
+    }
+  }
+}
+
+static int grid_for(int64_t ntiles, int per_sm) {
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t cap = (int64_t)sms * per_sm;       // grid = multiple of the SM count (persistent, grid-stride)
+  return (int)(ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap);
+}
+
+int launch_agg_update(const VmProgram* d_prog, const ColTable& cols, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n,
+                      const uint32_t* d_row_list, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int64_t ntiles = (n + AG_TILE - 1) / AG_TILE;
+  agg_update_kernel<<<grid_for(ntiles, 8), AG_BLOCK, 0, s>>>(d_prog, cols, lay, tab, row_begin, n, d_row_list);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// HashAgg: grow (rehash into a larger table)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agg_rehash_kernel(const AggLayout lay, const AggTable old_tab, const AggTable new_tab) {
+  const uint64_t cap = old_tab.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long* src = old_tab.slots + i * (uint64_t)lay.slot_words;
+    const unsigned long long hdr = src[0];
+    if ((unsigned)hdr < 2) continue;
+    const unsigned knull = (unsigned)(hdr >> 48);
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (int w = 0; w < lay.nkw; w++) h = mix64(h ^ src[1 + w]);
+    h = mix64(h ^ knull);
+    uint64_t s = h & new_tab.mask;
+    while (true) {
+      unsigned long long* dst = new_tab.slots + s * (uint64_t)lay.slot_words;
+      if (atomicCAS((unsigned*)dst, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
+        for (int w = 1; w < lay.slot_words; w++) dst[w] = src[w];
+        ((unsigned*)dst)[1] = (unsigned)(hdr >> 32) & ~FLAG_SLOT_LOCK;
+        __threadfence();
+        st_release_u32((unsigned*)dst, (unsigned)hdr);
+        atomicAdd(new_tab.counters, 1ULL);
+        break;
+      }
+      s = (s + 1) & new_tab.mask;
+    }
+  }
+}
+
+int launch_agg_rehash(const AggLayout& lay, const AggTable& old_tab, const AggTable& new_tab, cudaStream_t s) {
+  const int64_t cap = (int64_t)old_tab.mask + 1;
+  agg_rehash_kernel<<<grid_for((cap + 255) / 256, 8), 256, 0, s>>>(lay, old_tab, new_tab);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// HashAgg: emit
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_store(const EmitCol& c, unsigned long long at, uint64_t lo, uint64_t hi, bool valid) {
+  if (c.valid_bytes) c.valid_bytes[at] = valid ? 1 : 0;
+  switch (c.phys) {
+    case PH_BOOL: ((uint8_t*)c.values)[at] = lo != 0; break;          // bytes; packed to bits by pack_valid_kernel
+    case PH_I8: ((int8_t*)c.values)[at] = (int8_t)lo; break;
+    case PH_I16: ((int16_t*)c.values)[at] = (int16_t)lo; break;
+    case PH_I32: ((int32_t*)c.values)[at] = (int32_t)lo; break;
+    case PH_I64: case PH_F64: ((uint64_t*)c.values)[at] = lo; break;
+    case PH_F32: ((float*)c.values)[at] = (float)as_f64(lo); break;
+    default: ((uint64_t*)c.values)[2 * at] = lo; ((uint64_t*)c.values)[2 * at + 1] = hi; break;
+  }
+}
+
+__global__ void __launch_bounds__(256) agg_emit_kernel(const AggLayout lay, const AggTable tab, const EmitTable emit, unsigned long long* out_count) {
+  const uint64_t cap = tab.mask + 1;
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (cap + stride - 1) / stride;
+  for (uint64_t it = 0; it < rounds; it++) {
+    const uint64_t i = it * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const unsigned long long* slot = tab.slots + i * (uint64_t)lay.slot_words;
+    unsigned long long hdr = 0;
+    if (i < cap) hdr = slot[0];
+    const bool occ = (unsigned)hdr >= 2;
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (!m) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(m));       // warp-aggregated claim of output rows
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!occ) continue;
+    const unsigned long long at = base + __popc(m & lanemask_lt());
+    const unsigned flags = (unsigned)(hdr >> 32);
+    for (int c = 0; c < emit.ncols; c++) {
+      const EmitCol ec = emit.col[c];
+      switch (ec.kind) {
+        case EMIT_KEY: {
+          const bool valid = !((flags >> (16 + ec.key)) & 1);
+          emit_store(ec, at, slot[ec.word], ec.phys == PH_DEC128 ? slot[ec.word + 1] : 0, valid);
+          break;
+        }
+        case EMIT_ACC_VALUE: {
+          const bool valid = ec.vbit == 0xFF ? true : ((flags >> ec.vbit) & 1);
+          uint64_t lo = slot[ec.word];
+          if (ec.is_order_key) lo = (uint64_t)total_order_key(lo);               // the key transform is an involution
+          emit_store(ec, at, valid ? lo : 0, (valid && ec.phys == PH_DEC128) ? slot[ec.word + 1] : 0, valid);
+          break;
+        }
+        case EMIT_AVG_F64: {
+          const long long cnt = (long long)slot[ec.word2];
+          const bool valid = (ec.vbit == 0xFF ? true : ((flags >> ec.vbit) & 1)) && cnt != 0;
+          const double sum = ec.sum_is_f64 ? as_f64(slot[ec.word]) : __ll2double_rn((long long)slot[ec.word]);
+          emit_store(ec, at, valid ? f64_bits(sum / __ll2double_rn(cnt)) : 0, 0, valid);
+          break;
+        }
+        default: {   // EMIT_AVG_DEC: i128::checked_div_euclid(sum, count) (avg.rs:158-165)
+          const long long cnt = (long long)slot[ec.word2];
+          const bool valid = (ec.vbit == 0xFF ? true : ((flags >> ec.vbit) & 1)) && cnt != 0;
+          i128_t q = 0;
+          if (valid) {
+            const i128_t sum = mk128(slot[ec.word], slot[ec.word + 1]);
+            q = sum / cnt; const i128_t r = sum % cnt;
+            if (r < 0) q += cnt > 0 ? -1 : 1;
+          }
+          emit_store(ec, at, lo64(q), hi64(q), valid);
+          break;
+        }
+      }
+    }
+  }
+}
+
+int launch_agg_emit(const AggLayout& lay, const AggTable& tab, const EmitTable& emit, unsigned long long* d_out_count, cudaStream_t s) {
+  const int64_t cap = (int64_t)tab.mask + 1;
+  agg_emit_kernel<<<grid_for((cap + 255) / 256, 8), 256, 0, s>>>(lay, tab, emit, d_out_count);
+  return 1;
+}
+
+__global__ void __launch_bounds__(256) pack_valid_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ bits, long long n) {
+  const long long nwords = (n + 31) / 32;
+  const unsigned lane = threadIdx.x & 31;
+  // one warp packs 32 words (1024 rows) per step: lane l reads byte (w*32 + l), ballot gives the word
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp_id; w < nwords; w += nwarps) {
+    const long long i = w * 32 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, i < n && bytes[i] != 0);
+    if (lane == 0) bits[w] = m;
+  }
+}
+
+int launch_pack_valid(const uint8_t* bytes, uint32_t* bits, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  pack_valid_kernel<<<grid_for((n + 8191) / 8192, 8), 256, 0, s>>>(bytes, bits, n);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// frozen accumulator rows (the Binary `#9223372036854775807` column)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int varint_len(unsigned long long v) { int n = 1; while (v >= 128) { v >>= 7; n++; } return n; }
+
+__device__ __forceinline__ unsigned long long state_value_bits(const FrozenField& f, long long i, unsigned long long& hi) {
+  hi = 0;
+  switch (f.phys) {
+    case PH_I8: return (unsigned long long)(long long)((const int8_t*)f.values)[i];
+    case PH_I16: return (unsigned long long)(long long)((const int16_t*)f.values)[i];
+    case PH_I32: return (unsigned long long)(long long)((const int32_t*)f.values)[i];
+    case PH_F32: return (unsigned long long)((const uint32_t*)f.values)[i];
+    case PH_DEC128: hi = ((const unsigned long long*)f.values)[2 * i + 1]; return ((const unsigned long long*)f.values)[2 * i];
+    default: return ((const unsigned long long*)f.values)[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) frozen_lengths_kernel(const FrozenTable ft, long long n, int32_t* __restrict__ lengths) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int len = 0;
+    for (int k = 0; k < ft.nfields; k++) {
+      const FrozenField& f = ft.f[k];
+      if (f.kind == FZ_COUNT) len += varint_len(((const unsigned long long*)f.values)[i]);
+      else len += 1 + ((f.valid ? f.valid[i] != 0 : true) ? f.width : 0);
+    }
+    lengths[i] = len;
+  }
+}
+
+__global__ void __launch_bounds__(256) frozen_write_kernel(const FrozenTable ft, long long n, const int32_t* __restrict__ offsets, uint8_t* __restrict__ data) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t* p = data + offsets[i];
+    for (int k = 0; k < ft.nfields; k++) {
+      const FrozenField& f = ft.f[k];
+      if (f.kind == FZ_COUNT) {
+        unsigned long long v = ((const unsigned long long*)f.values)[i];           // write_len (io/mod.rs:60-68)
+        while (v >= 128) { *p++ = (uint8_t)(128 + (v & 127)); v >>= 7; }
+        *p++ = (uint8_t)v;
+      } else {
+        const bool valid = f.valid ? f.valid[i] != 0 : true;
+        *p++ = valid ? 1 : 0;                                                      // acc.rs:335-346
+        if (valid) {
+          unsigned long long hi, lo = state_value_bits(f, i, hi);
+          for (int b = 0; b < f.width && b < 8; b++) *p++ = (uint8_t)(lo >> (8 * b));
+          for (int b = 8; b < f.width; b++) *p++ = (uint8_t)(hi >> (8 * (b - 8)));
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) frozen_read_kernel(const FrozenTable ft, long long n, const int32_t* __restrict__ offsets, long long obase,
+                                                          const uint8_t* __restrict__ data, int* err) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* p = data + offsets[obase + i];
+    const uint8_t* end = data + offsets[obase + i + 1];
+    for (int k = 0; k < ft.nfields; k++) {
+      const FrozenField& f = ft.f[k];
+      if (f.kind == FZ_COUNT) {                                                    // read_len (io/mod.rs:70-83)
+        unsigned long long v = 0; int shift = 0;
+        while (true) {
+          if (p >= end) { atomicOr(err, 4); break; }
+          const uint8_t b = *p++;
+          if (b < 128) { v += (unsigned long long)b << shift; break; }
+          v += (unsigned long long)(b - 128) << shift; shift += 7;
+        }
+        ((unsigned long long*)f.values)[i] = v;
+      } else {                                                                     // acc.rs:349-365
+        if (p >= end) { atomicOr(err, 4); break; }
+        const bool valid = *p++ == 1;
+        unsigned long long lo = 0, hi = 0;
+        if (valid) {
+          if (p + f.width > end) { atomicOr(err, 4); break; }
+          for (int b = 0; b < f.width && b < 8; b++) lo |= (unsigned long long)(*p++) << (8 * b);
+          for (int b = 8; b < f.width; b++) hi |= (unsigned long long)(*p++) << (8 * (b - 8));
+        }
+        ((uint8_t*)f.valid)[i] = valid ? 1 : 0;
+        switch (f.phys) {
+          case PH_I8: ((int8_t*)f.values)[i] = (int8_t)lo; break;
+          case PH_I16: ((int16_t*)f.values)[i] = (int16_t)lo; break;
+          case PH_I32: case PH_F32: ((uint32_t*)f.values)[i] = (uint32_t)lo; break;
+          case PH_DEC128: ((unsigned long long*)f.values)[2 * i] = lo; ((unsigned long long*)f.values)[2 * i + 1] = hi; break;
+          default: ((unsigned long long*)f.values)[i] = lo; break;
+        }
+      }
+    }
+  }
+}
+
+int launch_frozen_lengths(const FrozenTable& ft, int64_t n, int32_t* lengths, cudaStream_t s) {
+  if (n <= 0) return 0;
+  frozen_lengths_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, s>>>(ft, n, lengths); return 1;
+}
+int launch_frozen_write(const FrozenTable& ft, int64_t n, const int32_t* offsets, uint8_t* data, cudaStream_t s) {
+  if (n <= 0) return 0;
+  frozen_write_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, s>>>(ft, n, offsets, data); return 1;
+}
+int launch_frozen_read(const FrozenTable& ft, int64_t n, const int32_t* offsets, int64_t offsets_base, const uint8_t* data, int* d_err, cudaStream_t s) {
+  if (n <= 0) return 0;
+  frozen_read_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, s>>>(ft, n, offsets, offsets_base, data, d_err); return 1;
+}
+
+// exclusive scan of int32 (n -> n+1 offsets): block sums, scan of the sums by one block, final pass
+constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+int64_t scan_num_blocks(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem /*>=9 ints*/) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < SCAN_BLOCK / 32 ? smem[lane] : 0, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+    if (lane < SCAN_BLOCK / 32) smem[lane] = wi - w;
+    if (lane == SCAN_BLOCK / 32 - 1) smem[8] = wi;
+  }
+  __syncthreads();
+  const int res = incl - v + smem[warp];
+  *total = smem[8];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_block_sums_kernel(const int32_t* __restrict__ in, long long n, int32_t* __restrict__ block_sums) {
+  __shared__ int smem[9];
+  const long long base = blockIdx.x * (long long)SCAN_TILE;
+  int s = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) { const long long i = base + k * SCAN_BLOCK + threadIdx.x; if (i < n) s += in[i]; }
+  int total; block_exclusive_scan(s, &total, smem);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(int32_t* block_sums, long long nb) {
+  __shared__ int smem[9];
+  int carry = 0;
+  for (long long base = 0; base < nb; base += SCAN_BLOCK) {
+    const long long i = base + threadIdx.x;
+    const int v = i < nb ? block_sums[i] : 0;
+    int total; const int ex = block_exclusive_scan(v, &total, smem);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_final_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, long long n, const int32_t* __restrict__ block_sums) {
+  __shared__ int smem[9];
+  const long long base = blockIdx.x * (long long)SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+  int total; int ex = block_exclusive_scan(s, &total, smem) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+  // the last element out[n] = grand total: written by the thread that owns index n-1
+  if (n > 0 && base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = ex;   // ex now = exclusive prefix after this thread's items
+}
+
+int launch_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* d_block_sums, cudaStream_t s) {
+  if (n <= 0) { cudaMemsetAsync(out, 0, sizeof(int32_t), s); return 0; }
+  const int64_t nb = scan_num_blocks(n);
+  scan_block_sums_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(in, n, d_block_sums);
+  scan_sums_kernel<<<1, SCAN_BLOCK, 0, s>>>(d_block_sums, nb);
+  scan_final_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, s>>>(in, out, n, d_block_sums);
+  return 3;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spark murmur3 (seed 42) + pmod — hash/mur.rs:19-87, spark_hash.rs:62-200, shuffle/mod.rs:163-188
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ uint32_t mm3_mix_k1(uint32_t k1) { k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u; return k1; }
+__device__ __forceinline__ uint32_t mm3_mix_h1(uint32_t h1, uint32_t k1) { h1 ^= k1; h1 = rotl32(h1, 13); return h1 * 5 + 0xe6546b64u; }
+__device__ __forceinline__ uint32_t mm3_fmix(uint32_t h1, uint32_t len) { h1 ^= len; h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16; return h1; }
+
+struct PhysList { uint8_t phys[VM_MAX_COLS]; };
+
+__global__ void __launch_bounds__(256) murmur3_partition_kernel(const ColTable cols, const PhysList pl, int ncols, long long n, int num_partitions, uint32_t* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t h = 42;
+    for (int c = 0; c < ncols; c++) {
+      const DevCol col = cols.col[c];
+      if (col.validity) { const unsigned long long bi = (unsigned long long)i + col.bit_offset; if (!((col.validity[bi >> 3] >> (bi & 7)) & 1)) continue; }   // NULL leaves the hash unchanged
+      uint32_t w[4]; int nw;
+      switch (pl.phys[c]) {
+        case PH_BOOL: { const unsigned long long bi = (unsigned long long)i + col.bit_offset; w[0] = (((const uint8_t*)col.values)[bi >> 3] >> (bi & 7)) & 1; nw = 1; break; }
+        case PH_I8: w[0] = (uint32_t)(int32_t)((const int8_t*)col.values)[i]; nw = 1; break;
+        case PH_I16: w[0] = (uint32_t)(int32_t)((const int16_t*)col.values)[i]; nw = 1; break;
+        case PH_I32: case PH_F32: w[0] = ((const uint32_t*)col.values)[i]; nw = 1; break;
+        case PH_I64: case PH_F64: { const unsigned long long v = ((const unsigned long long*)col.values)[i]; w[0] = (uint32_t)v; w[1] = (uint32_t)(v >> 32); nw = 2; break; }
+        default: { const unsigned long long a = ((const unsigned long long*)col.values)[2 * i], b = ((const unsigned long long*)col.values)[2 * i + 1];
+                   w[0] = (uint32_t)a; w[1] = (uint32_t)(a >> 32); w[2] = (uint32_t)b; w[3] = (uint32_t)(b >> 32); nw = 4; break; }
+      }
+      uint32_t h1 = h;
+      for (int k = 0; k < nw; k++) h1 = mm3_mix_h1(h1, mm3_mix_k1(w[k]));
+      h = mm3_fmix(h1, (uint32_t)(4 * nw));
+    }
+    int32_t m = (int32_t)h % num_partitions;                                       // rem_euclid
+    if (m < 0) m += num_partitions;
+    out[i] = (uint32_t)m;
+  }
+}
+
+int launch_murmur3_partition(const ColTable& cols, const uint8_t* phys, int ncols, int64_t n, int32_t num_partitions, uint32_t* out, cudaStream_t s) {
+  if (n <= 0) return 0;
+  PhysList pl; for (int i = 0; i < ncols && i < VM_MAX_COLS; i++) pl.phys[i] = phys[i];
+  murmur3_partition_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, s>>>(cols, pl, ncols, n, num_partitions, out);
+  return 1;
+}
+
+}  // namespace b200q

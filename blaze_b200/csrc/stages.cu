@@ -1,0 +1,544 @@
+// Stage implementations: FilterProjectStage and AggStage (see runtime.h).
+#include <algorithm>
+#include <cstring>
+
+#include "runtime.h"
+
+namespace b200q {
+
+// ---------------------------------------------------------------------------------------------------
+DevMem::~DevMem() {
+  if (owned && ptr) cudaFreeAsync(ptr, stream);
+}
+DevMemP DevMem::alloc(size_t bytes, cudaStream_t s, bool zero) {
+  auto m = std::make_shared<DevMem>();
+  m->bytes = bytes; m->stream = s; m->owned = true;
+  if (bytes == 0) bytes = 16;
+  B200Q_CUDA(cudaMallocAsync(&m->ptr, bytes, s));
+  if (zero) B200Q_CUDA(cudaMemsetAsync(m->ptr, 0, bytes, s));
+  return m;
+}
+DevMemP DevMem::borrow(const void* p, size_t bytes, std::shared_ptr<void> owner) {
+  auto m = std::make_shared<DevMem>();
+  m->ptr = const_cast<void*>(p); m->bytes = bytes; m->owned = false; m->owner = std::move(owner);
+  return m;
+}
+
+static inline size_t bitmap_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4; }
+
+static DevCol dev_col_of(const DevColumn& c) {
+  DevCol d{};
+  const int w = c.type.byte_width();
+  d.values = c.values ? (const uint8_t*)c.values->ptr + (size_t)c.offset * (size_t)w : nullptr;
+  d.validity = c.validity ? (const uint8_t*)c.validity->ptr : nullptr;
+  d.bit_offset = (uint32_t)c.offset;
+  if (c.offset > 0xFFFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "column offset beyond 2^32 rows");
+  return d;
+}
+
+static void check_device_error_flags(int flags) {
+  if (flags & 1) throw ExecError(B200Q_ERR_EXECUTION, "Arrow error: Divide by zero error");
+  if (flags & 2) throw ExecError(B200Q_ERR_EXECUTION, "Arrow error: Arithmetic overflow");
+  if (flags & 4) throw ExecError(B200Q_ERR_EXECUTION, "corrupted accumulator row in the Binary agg buffer column");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FilterProjectStage
+// ---------------------------------------------------------------------------------------------------
+class FilterProjectStage : public Stage {
+  CompiledProgram cp_;
+  DevMemP d_prog_;
+  bool has_filters_;
+
+ public:
+  FilterProjectStage(OpContext& cx, const SchemaDef& in, const std::vector<ExprP>& filters, const std::vector<ExprP>& outs, const SchemaDef& out) {
+    in_schema = in; out_schema = out;
+    has_filters_ = !filters.empty();
+    cp_ = compile_program(filters, outs, has_filters_);
+    used_input_cols = cp_.used_cols;
+    d_prog_ = DevMem::alloc(sizeof(VmProgram), cx.stream);
+    B200Q_CUDA(cudaMemcpyAsync(d_prog_->ptr, &cp_.prog, sizeof(VmProgram), cudaMemcpyHostToDevice, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+  }
+
+  void push(OpContext& cx, DevBatch& in, std::vector<DevBatch>& outs) override {
+    const int64_t n = in.num_rows;
+    if (n == 0) return;
+    if (n > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "batches above 2^31-1 rows must be split by the caller");
+    ColTable ct{};
+    for (size_t i = 0; i < cp_.used_cols.size(); i++) ct.col[i] = dev_col_of(in.cols[cp_.used_cols[i]]);
+    OutTable ot{};
+    DevBatch ob;
+    for (size_t i = 0; i < cp_.outs.size(); i++) {
+      const OutDesc& od = cp_.outs[i];
+      DevColumn c; c.type = od.type;
+      const bool is_bool = od.type.id == T_BOOL;
+      c.values = is_bool ? DevMem::alloc(bitmap_bytes(n), cx.stream, true) : DevMem::alloc((size_t)n * od.type.byte_width(), cx.stream);
+      if (od.nullable) c.validity = DevMem::alloc(bitmap_bytes(n), cx.stream, true);
+      ot.values[i] = c.values->ptr; ot.validity[i] = c.validity ? (uint32_t*)c.validity->ptr : nullptr; ot.phys[i] = phys_of(od.type);
+      ob.cols.push_back(c);
+    }
+    const int64_t ntiles = filter_project_num_tiles(n);
+    DevMemP status = has_filters_ ? DevMem::alloc((size_t)ntiles * 8, cx.stream, true) : nullptr;
+    DevMemP scratch = DevMem::alloc(32, cx.stream, true);
+    cx.m.launches += launch_filter_project((const VmProgram*)d_prog_->ptr, ct, ot, (int)cp_.outs.size(), n, has_filters_,
+                                           status ? (unsigned long long*)status->ptr : nullptr, (unsigned long long*)scratch->ptr, cx.stream);
+    B200Q_CUDA(cudaGetLastError());
+    unsigned long long h[4];
+    B200Q_CUDA(cudaMemcpyAsync(h, scratch->ptr, 32, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    check_device_error_flags((int)h[2]);
+    ob.num_rows = (int64_t)h[1];
+    if (ob.num_rows > 0) outs.push_back(std::move(ob));       // sender.send drops empty batches (execution_context.rs:713-716)
+  }
+  void finish(OpContext&, std::vector<DevBatch>&) override {}
+};
+
+std::unique_ptr<Stage> make_filter_project_stage(OpContext& cx, const SchemaDef& in_schema, const std::vector<ExprP>& filters,
+                                                 const std::vector<ExprP>& outs, const SchemaDef& out_schema) {
+  return std::unique_ptr<Stage>(new FilterProjectStage(cx, in_schema, filters, outs, out_schema));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AggStage
+// ---------------------------------------------------------------------------------------------------
+static uint64_t host_mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
+
+StateCols state_columns_of(const AggDef& a) {
+  StateCols s; DType i64; i64.id = T_INT64;
+  switch (a.fn) {
+    case AGG_COUNT: s.fields.push_back(FieldDef{a.field_name, i64, false}); break;
+    case AGG_AVG:
+      s.fields.push_back(FieldDef{a.field_name + "#sum", a.data_type, true});
+      s.fields.push_back(FieldDef{a.field_name + "#count", i64, false});
+      break;
+    default: s.fields.push_back(FieldDef{a.field_name, a.data_type, true}); break;
+  }
+  return s;
+}
+
+// can this expression evaluate to NULL?  (conservative; used to drop validity tracking)
+static bool cast_may_fail(const DType& f, const DType& t) {
+  if (f == t) return false;
+  auto ii = [](const DType& d) { return d.is_integer() || d.id == T_DATE32 || d.id == T_TIMESTAMP_US || d.id == T_BOOL; };
+  if (ii(f) && ii(t)) return t.int_bits() < f.int_bits();
+  if (ii(f) && t.is_float()) return false;
+  if (f.is_float() && (t.is_float() || t.is_integer() || t.id == T_BOOL)) return false;
+  return true;
+}
+static bool can_be_null(const ExprP& e) {
+  switch (e->kind) {
+    case E_COLUMN: return e->nullable;
+    case E_LITERAL: return e->lit_null || e->type.id == T_NULL;
+    case E_BINARY:
+      if (e->op == OP_AND || e->op == OP_OR) return e->nullable;
+      return can_be_null(e->children[0]) || can_be_null(e->children[1]);
+    case E_IS_NULL: case E_IS_NOT_NULL: return false;
+    case E_NOT: case E_NEGATIVE: return can_be_null(e->children[0]);
+    case E_CAST: case E_TRY_CAST: return can_be_null(e->children[0]) || cast_may_fail(e->children[0]->type, e->type);
+    default: return true;
+  }
+}
+
+static bool same_expr(const ExprP& a, const ExprP& b) {
+  if (a == b) return true;
+  if (a->kind != b->kind || a->type != b->type || a->children.size() != b->children.size()) return false;
+  if (a->kind == E_COLUMN) return a->col_index == b->col_index;
+  if (a->kind == E_LITERAL) return a->lit_null == b->lit_null && a->lit_lo == b->lit_lo && a->lit_hi == b->lit_hi;
+  if (a->kind == E_BINARY && a->op != b->op) return false;
+  if (a->kind == E_SCALAR_FN && a->name != b->name) return false;
+  if (a->kind == E_IN_LIST && a->negated != b->negated) return false;
+  if (a->kind == E_CASE && (a->case_has_base != b->case_has_base || a->case_has_else != b->case_has_else)) return false;
+  for (size_t i = 0; i < a->children.size(); i++) if (!same_expr(a->children[i], b->children[i])) return false;
+  return true;
+}
+// strip casts that change nothing on the device (same 64-bit representation, cannot fail)
+static ExprP strip_noop_casts(ExprP e) {
+  while ((e->kind == E_CAST || e->kind == E_TRY_CAST) && !cast_may_fail(e->children[0]->type, e->type)) {
+    const DType &f = e->children[0]->type, &t = e->type;
+    const bool same_repr = (f == t) || (f.is_intlike() && t.is_intlike());
+    if (!same_repr) break;
+    e = e->children[0];
+  }
+  return e;
+}
+
+class AggStage : public Stage {
+  PlanNode node_;                       // copy of the Agg node (exprs already rewritten over the stage input)
+  std::vector<ExprP> filters_;
+  std::vector<ExprP> vm_outs_;          // keys, then accumulator arguments
+  CompiledProgram cp_;
+  DevMemP d_prog_;
+  AggLayout lay_{};
+  bool merge_mode_ = false, columnar_ = false, final_ = false;
+  int n_in_ = 0;                        // input columns
+  std::vector<FieldDef> merge_state_fields_;   // state columns fed by the merge-mode aggs (in agg order)
+  int first_state_col_ = 0;             // index of the first state column in the program's column space
+
+  // table
+  DevMemP slots_, counters_, deferred_[2];
+  uint64_t capacity_ = 0;
+  int64_t deferred_cap_ = 0;
+  int64_t ngroups_ = 0;
+
+  // emit plan (per output/state column)
+  struct EmitSpec { EmitCol ec; FieldDef field; bool frozen_count = false; };
+  std::vector<EmitSpec> emit_;          // key columns first, then per-agg result or state columns
+  std::vector<FrozenField> frozen_fields_;     // non-final, reference format: how the state columns freeze
+
+  int add_out(const ExprP& e) {
+    ExprP s = strip_noop_casts(e);
+    for (size_t i = 0; i < vm_outs_.size(); i++) if (same_expr(vm_outs_[i], s)) return (int)i;
+    vm_outs_.push_back(s);
+    return (int)vm_outs_.size() - 1;
+  }
+
+  static uint8_t frozen_width(const DType& t) { return (uint8_t)t.byte_width(); }
+
+ public:
+  AggStage(OpContext& cx, const SchemaDef& in, const std::vector<ExprP>& filters, const PlanNode& agg,
+           const std::vector<ExprP>& group_exprs, const std::vector<std::vector<ExprP>>& agg_args) : node_(agg), filters_(filters) {
+    in_schema = in; out_schema = agg.schema;
+    n_in_ = (int)in.fields.size();
+    merge_mode_ = agg.need_partial_merge; final_ = agg.need_final_merge;
+    columnar_ = cx.conf.partial_state_columnar != 0;
+    if (agg.exec_mode != 0 && !agg.group_exprs.empty()) {
+      // SortAgg over sorted input produces the same multiset of groups; the GPU always hashes.
+    }
+    if ((int)group_exprs.size() > AGG_MAX_KEYS) throw PlanError(B200Q_ERR_UNSUPPORTED, "more than 8 grouping columns");
+    if (merge_mode_ && !filters.empty()) throw PlanError(B200Q_ERR_UNSUPPORTED, "Filter fused below a merge-mode aggregate");
+
+    // ---- state columns consumed by merge-mode aggs
+    for (auto& a : agg.aggs) if (a.mode != MODE_PARTIAL) for (auto& f : state_columns_of(a).fields) merge_state_fields_.push_back(f);
+    if (merge_mode_) {
+      if (columnar_) {
+        first_state_col_ = n_in_ - (int)merge_state_fields_.size();
+        if (first_state_col_ < (int)0) throw PlanError(B200Q_ERR_INVALID_PLAN, "columnar partial state: input has too few columns");
+        for (size_t k = 0; k < merge_state_fields_.size(); k++)
+          if (in.fields[first_state_col_ + k].type != merge_state_fields_[k].type)
+            throw PlanError(B200Q_ERR_INVALID_PLAN, "columnar partial state: column " + in.fields[first_state_col_ + k].name + " has type " +
+                                                        in.fields[first_state_col_ + k].type.str() + ", expected " + merge_state_fields_[k].type.str());
+      } else {
+        first_state_col_ = n_in_;
+        if (in.fields.empty() || in.fields.back().type.id != T_BINARY)
+          throw PlanError(B200Q_ERR_INVALID_PLAN, "merge-mode aggregate: the last input column must be the Binary agg buffer column (agg_ctx.rs:280)");
+      }
+    }
+
+    // ---- slot layout
+    lay_.nkeys = (int)group_exprs.size();
+    int word = 1;
+    for (int k = 0; k < lay_.nkeys; k++) {
+      const ExprP& g = group_exprs[k];
+      lay_.key_out[k] = (uint8_t)add_out(g);
+      if (lay_.key_out[k] != k) throw PlanError(B200Q_ERR_UNSUPPORTED, "duplicate grouping expressions");
+      lay_.key_word[k] = (uint8_t)word; lay_.key_nwords[k] = g->type.is_decimal() ? 2 : 1;
+      word += lay_.key_nwords[k];
+    }
+    lay_.nkw = word - 1;
+    for (int i = 0; i < AGG_MAX_SLOT_WORDS; i++) lay_.init[i] = 0;
+    lay_.init_flags = 0;
+    int vbits = 0, state_k = 0;
+    auto new_vbit = [&]() { if (vbits >= 15) throw PlanError(B200Q_ERR_UNSUPPORTED, "too many nullable accumulators in one aggregate"); return (uint8_t)vbits++; };
+    auto state_col_expr = [&](const FieldDef& f) {
+      auto e = std::make_shared<Expr>(); e->kind = E_COLUMN; e->col_index = first_state_col_ + state_k++; e->name = f.name; e->type = f.type; e->nullable = f.nullable;
+      return ExprP(e);
+    };
+    auto add_acc = [&](AccKind kind, int nwords, uint8_t vbit, const std::vector<int>& args, uint64_t init_lo, uint64_t init_hi) {
+      if (lay_.nacc >= AGG_MAX_ACC) throw PlanError(B200Q_ERR_UNSUPPORTED, "too many accumulators in one aggregate");
+      if (word + nwords > AGG_MAX_SLOT_WORDS) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate state too wide for one table slot");
+      AccOp& a = lay_.acc[lay_.nacc++];
+      a.kind = kind; a.word = (uint8_t)word; a.vbit = vbit; a.nargs = (uint8_t)args.size();
+      for (size_t i = 0; i < args.size() && i < 4; i++) a.arg_out[i] = (uint8_t)args[i];
+      lay_.init[word] = init_lo; if (nwords == 2) lay_.init[word + 1] = init_hi;
+      const int w = word; word += nwords; return w;
+    };
+
+    // key emit columns
+    for (int k = 0; k < lay_.nkeys; k++) {
+      EmitSpec es{}; es.ec.kind = EMIT_KEY; es.ec.phys = phys_of(group_exprs[k]->type); es.ec.word = lay_.key_word[k]; es.ec.key = (uint8_t)k; es.ec.vbit = 0xFF;
+      es.field = agg.schema.fields[k];
+      emit_.push_back(es);
+    }
+
+    for (size_t ai = 0; ai < agg.aggs.size(); ai++) {
+      const AggDef& a = agg.aggs[ai];
+      const bool partial = a.mode == MODE_PARTIAL;
+      const DType& dt = a.data_type;
+      if ((a.fn == AGG_MIN || a.fn == AGG_MAX) && dt.id == T_BOOL) throw PlanError(B200Q_ERR_UNSUPPORTED, "min/max over boolean is not on the hot path");
+      int sum_word = -1, cnt_word = -1; uint8_t sum_vbit = 0xFF;
+      // --- sum-like part (Sum, Avg, Min, Max)
+      if (a.fn != AGG_COUNT) {
+        ExprP arg;
+        if (partial) { arg = agg_args[ai][0]; }
+        else { arg = state_col_expr(state_columns_of(a).fields[0]); }
+        const int o = add_out(arg);
+        const bool nullable_arg = can_be_null(arg);
+        const uint8_t vbit = nullable_arg ? new_vbit() : (uint8_t)0xFF;
+        AccKind kind; int nwords = 1; uint64_t ilo = 0, ihi = 0;
+        if (a.fn == AGG_SUM || a.fn == AGG_AVG) {
+          if (dt.is_decimal()) { kind = ACC_ADD_DEC; nwords = 2; }
+          else if (dt.id == T_FLOAT64) kind = ACC_ADD_F64;
+          else if (dt.is_integer()) kind = ACC_ADD_I64;
+          else throw PlanError(B200Q_ERR_UNSUPPORTED, "sum/avg accumulating at " + dt.str() + " is not on the hot path");
+        } else {
+          const bool mn = a.fn == AGG_MIN;
+          if (dt.is_decimal()) { kind = mn ? ACC_MIN_DEC : ACC_MAX_DEC; nwords = 2; ilo = mn ? ~0ULL : 0ULL; ihi = mn ? 0x7FFFFFFFFFFFFFFFULL : 0x8000000000000000ULL; }
+          else if (dt.is_float()) { kind = mn ? ACC_MIN_F64 : ACC_MAX_F64; ilo = mn ? 0x7FFFFFFFFFFFFFFFULL : 0x8000000000000000ULL; }
+          else if (dt.is_intlike()) { kind = mn ? ACC_MIN_I64 : ACC_MAX_I64; ilo = mn ? 0x7FFFFFFFFFFFFFFFULL : 0x8000000000000000ULL; }
+          else throw PlanError(B200Q_ERR_UNSUPPORTED, "min/max over " + dt.str() + " is not on the hot path");
+        }
+        sum_word = add_acc(kind, nwords, vbit, {o}, ilo, ihi); sum_vbit = vbit;
+      }
+      // --- count part (Count, Avg)
+      if (a.fn == AGG_COUNT || a.fn == AGG_AVG) {
+        if (partial) {
+          std::vector<int> args;
+          const auto& srcs = a.fn == AGG_AVG ? std::vector<ExprP>{agg_args[ai][0]} : agg_args[ai];
+          for (auto& e : srcs) if (can_be_null(e)) args.push_back(add_out(e));      // agg.rs:178-189 + never-NULL arguments dropped
+          if (args.size() > 4) throw PlanError(B200Q_ERR_UNSUPPORTED, "count over more than 4 nullable arguments");
+          cnt_word = add_acc(ACC_COUNT, 1, 0xFF, args, 0, 0);
+        } else {
+          const auto sc = state_columns_of(a);
+          const int o = add_out(state_col_expr(sc.fields.back()));
+          cnt_word = add_acc(ACC_ADD_I64, 1, 0xFF, {o}, 0, 0);
+        }
+      }
+      // --- emit columns
+      auto value_spec = [&](const FieldDef& f, int w, uint8_t vbit, bool order_key) {
+        EmitSpec es{}; es.ec.kind = EMIT_ACC_VALUE; es.ec.phys = phys_of(f.type); es.ec.word = (uint8_t)w; es.ec.vbit = vbit; es.ec.is_order_key = order_key; es.field = f; return es;
+      };
+      const bool order_key = (a.fn == AGG_MIN || a.fn == AGG_MAX) && dt.is_float();
+      if (final_) {
+        const FieldDef& of = agg.schema.fields[lay_.nkeys + ai];
+        if (a.fn == AGG_COUNT) emit_.push_back(value_spec(of, cnt_word, 0xFF, false));
+        else if (a.fn == AGG_AVG) {
+          EmitSpec es{}; es.field = of; es.ec.word = (uint8_t)sum_word; es.ec.word2 = (uint8_t)cnt_word; es.ec.vbit = sum_vbit;
+          if (dt.is_decimal()) { es.ec.kind = EMIT_AVG_DEC; es.ec.phys = PH_DEC128; }
+          else { es.ec.kind = EMIT_AVG_F64; es.ec.phys = PH_F64; es.ec.sum_is_f64 = dt.id == T_FLOAT64; }
+          emit_.push_back(es);
+        } else emit_.push_back(value_spec(of, sum_word, sum_vbit, order_key));
+      } else {
+        const auto sc = state_columns_of(a);
+        if (a.fn == AGG_COUNT) { emit_.push_back(value_spec(sc.fields[0], cnt_word, 0xFF, false)); emit_.back().frozen_count = true; }
+        else {
+          emit_.push_back(value_spec(sc.fields[0], sum_word, sum_vbit, order_key));
+          if (a.fn == AGG_AVG) { emit_.push_back(value_spec(sc.fields[1], cnt_word, 0xFF, false)); emit_.back().frozen_count = true; }
+        }
+      }
+    }
+    if (lay_.nkeys == 0 && lay_.nacc == 0) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate without groupings and aggregates");
+    lay_.slot_words = (word + 3) & ~3;                           // 32-byte aligned slots: one L2 sector per probe for narrow aggregates
+    if (lay_.slot_words > AGG_MAX_SLOT_WORDS) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate state too wide for one table slot");
+
+    if (!final_ && columnar_) {          // typed state columns instead of the Binary agg-buffer column
+      out_schema.fields.resize(lay_.nkeys);
+      for (size_t i = lay_.nkeys; i < emit_.size(); i++) out_schema.fields.push_back(emit_[i].field);
+    }
+
+    // ---- program
+    cp_ = compile_program(filters_, vm_outs_, false);
+    lay_.nouts = (int)cp_.outs.size();
+    int ow = 0;
+    for (size_t i = 0; i < cp_.outs.size(); i++) { lay_.out_word[i] = (uint8_t)ow; ow += cp_.outs[i].slots; }
+    if (ow > AGG_MAX_ROW_WORDS) throw PlanError(B200Q_ERR_UNSUPPORTED, "too many key/argument words per row");
+    for (int c : cp_.used_cols) if (c < n_in_) used_input_cols.push_back(c);
+    if (merge_mode_ && !columnar_) used_input_cols.push_back(n_in_ - 1);
+    std::sort(used_input_cols.begin(), used_input_cols.end());
+    used_input_cols.erase(std::unique(used_input_cols.begin(), used_input_cols.end()), used_input_cols.end());
+    d_prog_ = DevMem::alloc(sizeof(VmProgram), cx.stream);
+    B200Q_CUDA(cudaMemcpyAsync(d_prog_->ptr, &cp_.prog, sizeof(VmProgram), cudaMemcpyHostToDevice, cx.stream));
+
+    // ---- frozen-row descriptors of the state columns (non-final output in the reference format)
+    if (!final_) {
+      for (size_t i = lay_.nkeys; i < emit_.size(); i++) {
+        FrozenField f{}; const FieldDef& fd = emit_[i].field;
+        f.kind = emit_[i].frozen_count ? FZ_COUNT : FZ_PRIM; f.width = frozen_width(fd.type); f.phys = phys_of(fd.type);
+        frozen_fields_.push_back(f);
+      }
+    }
+
+    // ---- table
+    uint64_t want = (uint64_t)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * 2;
+    capacity_ = 1ULL << 20;                                       // floor: keeps the insert-overshoot bound (resident threads) below capacity/2
+    while (capacity_ < want) capacity_ <<= 1;
+    alloc_table(cx, capacity_, slots_, counters_);
+    if (lay_.nkeys == 0) seed_global_group(cx);
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    cx.m.table_capacity = (int64_t)capacity_;
+  }
+
+  void alloc_table(OpContext& cx, uint64_t cap, DevMemP& slots, DevMemP& counters) {
+    slots = DevMem::alloc((size_t)cap * lay_.slot_words * 8, cx.stream, true);
+    counters = DevMem::alloc(64, cx.stream, true);
+  }
+
+  // no-grouping aggregation always yields exactly one row (agg_exec.rs:280-323): pre-insert the empty key
+  void seed_global_group(OpContext& cx) {
+    const uint64_t h = host_mix64(0x9E3779B97F4A7C15ULL ^ 0ULL);
+    const uint32_t tag = (uint32_t)(h >> 32) | 0x80000000u;
+    const uint64_t s = h & (capacity_ - 1);
+    std::vector<uint64_t> img(lay_.slot_words, 0);
+    for (int i = 1; i < lay_.slot_words; i++) img[i] = lay_.init[i];
+    img[0] = (uint64_t)tag | ((uint64_t)lay_.init_flags << 32);
+    B200Q_CUDA(cudaMemcpyAsync((uint8_t*)slots_->ptr + s * lay_.slot_words * 8, img.data(), img.size() * 8, cudaMemcpyHostToDevice, cx.stream));
+    const unsigned long long one = 1;
+    B200Q_CUDA(cudaMemcpyAsync(counters_->ptr, &one, 8, cudaMemcpyHostToDevice, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+  }
+
+  AggTable table_view(int deferred_idx) const {
+    AggTable t{};
+    t.slots = (unsigned long long*)slots_->ptr; t.mask = capacity_ - 1; t.max_groups = capacity_ / 2;
+    t.counters = (unsigned long long*)counters_->ptr;
+    t.deferred = deferred_[deferred_idx] ? (uint32_t*)deferred_[deferred_idx]->ptr : nullptr;
+    return t;
+  }
+
+  void grow(OpContext& cx, uint64_t min_groups) {
+    uint64_t cap = capacity_;
+    do cap <<= 2; while (cap / 2 < min_groups);
+    DevMemP nslots, ncounters;
+    alloc_table(cx, cap, nslots, ncounters);
+    AggTable oldt = table_view(0);
+    AggTable newt{}; newt.slots = (unsigned long long*)nslots->ptr; newt.mask = cap - 1; newt.max_groups = cap / 2; newt.counters = (unsigned long long*)ncounters->ptr;
+    cx.m.launches += launch_agg_rehash(lay_, oldt, newt, cx.stream);
+    B200Q_CUDA(cudaGetLastError());
+    slots_ = nslots; counters_ = ncounters; capacity_ = cap;
+    cx.m.grow_count++; cx.m.table_capacity = (int64_t)cap;
+  }
+
+  void read_counters(OpContext& cx, unsigned long long (&h)[3]) {
+    B200Q_CUDA(cudaMemcpyAsync(h, counters_->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    check_device_error_flags((int)h[2]);
+    ngroups_ = (int64_t)h[0];
+    cx.m.num_groups = ngroups_;
+  }
+
+  void update_rows(OpContext& cx, const ColTable& ct, int64_t n) {
+    const int64_t chunk = std::max<int64_t>(1 << 16, std::min<int64_t>(cx.conf.max_launch_rows, 0x7FFFFFFFLL));
+    for (int64_t begin = 0; begin < n; begin += chunk) {
+      const int64_t m = std::min(chunk, n - begin);
+      if (deferred_cap_ < m) {
+        deferred_cap_ = m;
+        deferred_[0] = DevMem::alloc((size_t)m * 4, cx.stream);
+        deferred_[1] = DevMem::alloc((size_t)m * 4, cx.stream);
+      }
+      cx.m.launches += launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, table_view(0), begin, m, nullptr, cx.stream);
+      B200Q_CUDA(cudaGetLastError());
+      unsigned long long h[3];
+      read_counters(cx, h);
+      int cur = 0;
+      while (h[1] > 0) {
+        // the table hit its load limit: grow it, then replay only the rows that could not be inserted
+        const uint64_t ndef = h[1];
+        grow(cx, (uint64_t)ngroups_ + ndef);
+        B200Q_CUDA(cudaMemsetAsync((uint8_t*)counters_->ptr + 8, 0, 8, cx.stream));
+        // counters_ is new after grow(): ngroups was recounted by the rehash, deferred/err start at 0
+        AggTable t = table_view(cur ^ 1);
+        cx.m.launches += launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, (int64_t)ndef, (const uint32_t*)deferred_[cur]->ptr, cx.stream);
+        B200Q_CUDA(cudaGetLastError());
+        cur ^= 1;
+        read_counters(cx, h);
+      }
+    }
+  }
+
+  void push(OpContext& cx, DevBatch& in, std::vector<DevBatch>&) override {
+    const int64_t n = in.num_rows;
+    if (n == 0) return;
+    ColTable ct{};
+    std::vector<DevColumn> state_cols;
+    if (merge_mode_ && !columnar_) unfreeze(cx, in, state_cols);
+    for (size_t i = 0; i < cp_.used_cols.size(); i++) {
+      const int c = cp_.used_cols[i];
+      ct.col[i] = dev_col_of(c < n_in_ ? in.cols[c] : state_cols[c - n_in_]);
+    }
+    update_rows(cx, ct, n);
+  }
+
+  // Binary agg-buffer column -> typed state columns (AccColumn::unfreeze_from_rows, agg_ctx.rs:276-296)
+  void unfreeze(OpContext& cx, DevBatch& in, std::vector<DevColumn>& state_cols) {
+    const int64_t n = in.num_rows;
+    const DevColumn& bc = in.cols.back();
+    if (!bc.offsets || !bc.values) throw ExecError(B200Q_ERR_INVALID_ARG, "agg buffer column without offsets/data");
+    FrozenTable ft{}; ft.nfields = (int)merge_state_fields_.size();
+    if (ft.nfields > FROZEN_MAX_FIELDS) throw ExecError(B200Q_ERR_UNSUPPORTED, "too many accumulator fields");
+    std::vector<DevMemP> valid_bytes(ft.nfields);
+    for (int k = 0; k < ft.nfields; k++) {
+      const FieldDef& f = merge_state_fields_[k];
+      DevColumn c; c.type = f.type; c.values = DevMem::alloc((size_t)n * f.type.byte_width(), cx.stream);
+      FrozenField& ff = ft.f[k];
+      ff.kind = f.nullable ? FZ_PRIM : FZ_COUNT; ff.width = frozen_width(f.type); ff.phys = phys_of(f.type); ff.values = c.values->ptr;
+      if (f.nullable) { valid_bytes[k] = DevMem::alloc((size_t)n, cx.stream); ff.valid = (const uint8_t*)valid_bytes[k]->ptr; c.validity = DevMem::alloc(bitmap_bytes(n), cx.stream); }
+      state_cols.push_back(c);
+    }
+    int* d_err = (int*)((unsigned long long*)counters_->ptr + 2);
+    cx.m.launches += launch_frozen_read(ft, n, (const int32_t*)bc.offsets->ptr, bc.offset, (const uint8_t*)bc.values->ptr, d_err, cx.stream);
+    for (int k = 0; k < ft.nfields; k++)
+      if (valid_bytes[k]) cx.m.launches += launch_pack_valid((const uint8_t*)valid_bytes[k]->ptr, (uint32_t*)state_cols[k].validity->ptr, n, cx.stream);
+    B200Q_CUDA(cudaGetLastError());
+    // valid_bytes buffers are released stream-ordered after the pack kernels
+  }
+
+  void finish(OpContext& cx, std::vector<DevBatch>& outs) override {
+    unsigned long long h[3];
+    read_counters(cx, h);
+    const int64_t g = ngroups_;
+    if (g == 0) return;                                             // no records (agg_table.rs:154-156)
+    EmitTable et{}; et.ncols = (int)emit_.size();
+    if (et.ncols > EMIT_MAX_COLS) throw ExecError(B200Q_ERR_UNSUPPORTED, "too many output columns");
+    DevBatch ob; ob.num_rows = g;
+    std::vector<DevMemP> valid_bytes(emit_.size()), bool_bytes(emit_.size());
+    for (size_t i = 0; i < emit_.size(); i++) {
+      EmitCol ec = emit_[i].ec; const FieldDef& f = emit_[i].field;
+      DevColumn c; c.type = f.type;
+      if (f.type.id == T_BOOL) { bool_bytes[i] = DevMem::alloc((size_t)g, cx.stream); ec.values = bool_bytes[i]->ptr; c.values = DevMem::alloc(bitmap_bytes(g), cx.stream); }
+      else { c.values = DevMem::alloc((size_t)g * f.type.byte_width(), cx.stream); ec.values = c.values->ptr; }
+      if (f.nullable) { valid_bytes[i] = DevMem::alloc((size_t)g, cx.stream); ec.valid_bytes = (uint8_t*)valid_bytes[i]->ptr; c.validity = DevMem::alloc(bitmap_bytes(g), cx.stream); }
+      et.col[i] = ec;
+      ob.cols.push_back(c);
+    }
+    DevMemP out_count = DevMem::alloc(8, cx.stream, true);
+    cx.m.launches += launch_agg_emit(lay_, table_view(0), et, (unsigned long long*)out_count->ptr, cx.stream);
+    for (size_t i = 0; i < emit_.size(); i++) {
+      if (valid_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)valid_bytes[i]->ptr, (uint32_t*)ob.cols[i].validity->ptr, g, cx.stream);
+      if (bool_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)bool_bytes[i]->ptr, (uint32_t*)ob.cols[i].values->ptr, g, cx.stream);
+    }
+    B200Q_CUDA(cudaGetLastError());
+    if (!final_ && !columnar_) {
+      // freeze the state columns into the reference's Binary agg-buffer column (freeze_acc_table, agg_ctx.rs:407-426)
+      FrozenTable ft{}; ft.nfields = (int)frozen_fields_.size();
+      for (int k = 0; k < ft.nfields; k++) {
+        ft.f[k] = frozen_fields_[k];
+        ft.f[k].values = ob.cols[lay_.nkeys + k].values->ptr;
+        ft.f[k].valid = valid_bytes[lay_.nkeys + k] ? (const uint8_t*)valid_bytes[lay_.nkeys + k]->ptr : nullptr;
+      }
+      DevMemP lengths = DevMem::alloc((size_t)g * 4, cx.stream);
+      DevMemP offsets = DevMem::alloc((size_t)(g + 1) * 4, cx.stream);
+      DevMemP block_sums = DevMem::alloc((size_t)scan_num_blocks(g) * 4 + 16, cx.stream);
+      cx.m.launches += launch_frozen_lengths(ft, g, (int32_t*)lengths->ptr, cx.stream);
+      cx.m.launches += launch_exclusive_scan_i32((const int32_t*)lengths->ptr, (int32_t*)offsets->ptr, g, (int32_t*)block_sums->ptr, cx.stream);
+      int32_t total = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&total, (int32_t*)offsets->ptr + g, 4, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      if (total < 0) throw ExecError(B200Q_ERR_UNSUPPORTED, "frozen accumulator column exceeds 2 GiB; emit in smaller batches");
+      DevMemP data = DevMem::alloc((size_t)total, cx.stream);
+      cx.m.launches += launch_frozen_write(ft, g, (const int32_t*)offsets->ptr, (uint8_t*)data->ptr, cx.stream);
+      B200Q_CUDA(cudaGetLastError());
+      DevColumn bc; bc.type.id = T_BINARY; bc.values = data; bc.offsets = offsets;
+      ob.cols.resize(lay_.nkeys);
+      ob.cols.push_back(bc);
+    }
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    outs.push_back(std::move(ob));
+  }
+};
+
+std::unique_ptr<Stage> make_agg_stage(OpContext& cx, const SchemaDef& in_schema, const std::vector<ExprP>& filters, const PlanNode& agg,
+                                      const std::vector<ExprP>& group_exprs, const std::vector<std::vector<ExprP>>& agg_args) {
+  return std::unique_ptr<Stage>(new AggStage(cx, in_schema, filters, agg, group_exprs, agg_args));
+}
+
+}  // namespace b200q

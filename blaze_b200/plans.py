@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the Rust constructors the plan-serde layer
+calls:
+
+    FilterExec.try_new(predicates, input)                       datafusion-ext-plans/src/filter_exec.rs:52-73
+    ProjectExec.try_new([(expr, name)], input)                  datafusion-ext-plans/src/project_exec.rs:57-81
+    AggExec.try_new(exec_mode, groupings, aggs, supports_partial_skipping, input)
+                                                                datafusion-ext-plans/src/agg_exec.rs:67-98
+    create_agg(function, children, input_schema, return_type)   datafusion-ext-plans/src/agg/agg.rs:171-205
+    plan.execute() / collect(plan)                              ExecutionPlan::execute + physical_plan::collect
+
+Each plan object serialises itself to the reference's protobuf (`blaze_b200.proto`) and executes
+through the C ABI (`blaze_b200.native`): the whole subtree becomes ONE fused GPU pipeline.
+Constructors validate by decoding the plan in the native library (no GPU needed), so the errors are
+the library's own (`FilterExec.try_new` with a non-boolean predicate raises like the reference does).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+from . import exprs as E
+from . import native
+from . import proto as P
+from . import types as T
+from .exprs import AggExpr, AggFunctionExpr, GroupingExpr
+from .types import Field, Schema
+
+HashAgg, SortAgg = E.HASH_AGG, E.SORT_AGG
+Partial, PartialMerge, Final = E.PARTIAL, E.PARTIAL_MERGE, E.FINAL
+
+
+class ExecutionPlan:
+    def schema(self) -> Schema:
+        raise NotImplementedError
+
+    def children(self) -> List["ExecutionPlan"]:
+        return []
+
+    def node(self):
+        """-> plan.protobuf.PhysicalPlanNode"""
+        raise NotImplementedError
+
+    def leaf(self) -> "MemoryExec":
+        p = self
+        while p.children():
+            p = p.children()[0]
+        return p
+
+    def plan_bytes(self) -> bytes:
+        return self.node().SerializeToString()
+
+    def explain(self) -> str:
+        return native.plan_explain(self.plan_bytes())
+
+    def _validate(self):
+        native.plan_explain(self.plan_bytes())
+
+    def execute(self, conf: Optional[native.Conf] = None, device: int = 0):
+        """Run the subtree on the GPU over the leaf's batches; yields pyarrow RecordBatches."""
+        leaf = self.leaf()
+        with native.NativeOp(self.plan_bytes(), conf, device) as op:
+            for rb in leaf.batches:
+                op.push(rb)
+                while True:
+                    out = op.pull()
+                    if out is None:
+                        break
+                    yield out
+            op.finish()
+            while True:
+                out = op.pull()
+                if out is None:
+                    break
+                yield out
+            self.last_metrics = op.metrics()
+
+
+def collect(plan: ExecutionPlan, conf: Optional[native.Conf] = None, device: int = 0) -> List:
+    return list(plan.execute(conf, device))
+
+
+class MemoryExec(ExecutionPlan):
+    """In-memory source = the reference tests' `TestMemoryExec` (agg_exec.rs:490); on the wire it is an
+    FFIReaderExecNode leaf, i.e. batches arrive through the Arrow C Data Interface exactly like
+    FFIReaderExec's input (ffi_reader_exec.rs:163-194)."""
+
+    def __init__(self, schema: Schema, batches: Sequence = (), resource_id: str = "mem"):
+        self._schema = schema
+        self.batches = list(batches)
+        self.resource_id = resource_id
+
+    @staticmethod
+    def from_arrow(batches: Sequence, schema=None) -> "MemoryExec":
+        import pyarrow as pa
+        if schema is None:
+            schema = batches[0].schema
+        return MemoryExec(T.from_arrow_schema(schema), batches)
+
+    def schema(self):
+        return self._schema
+
+    def node(self):
+        return P.ffi_reader_node(self._schema, self.resource_id)
+
+
+class FilterExec(ExecutionPlan):
+    def __init__(self, predicates: Sequence[E.Expr], input: ExecutionPlan):
+        self.predicates = list(predicates)
+        self.input = input
+        self._validate()
+
+    try_new = classmethod(lambda cls, predicates, input: cls(predicates, input))
+
+    def schema(self):
+        return self.input.schema()                                      # filter_exec.rs:99-101
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        return P.filter_node(self.input.node(), self.predicates)
+
+
+class ProjectExec(ExecutionPlan):
+    def __init__(self, exprs: Sequence[Tuple[E.Expr, str]], input: ExecutionPlan):
+        self.exprs = [(e, n) for e, n in exprs]
+        self.input = input
+        ins = input.schema()
+        self._schema = Schema(Field(n, e.data_type(ins), e.nullable(ins)) for e, n in self.exprs)   # project_exec.rs:62-72
+        self._validate()
+
+    try_new = classmethod(lambda cls, exprs, input: cls(exprs, input))
+
+    def schema(self):
+        return self._schema
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        ins = self.input.schema()
+        return P.projection_node(self.input.node(), [e for e, _ in self.exprs], [n for _, n in self.exprs],
+                                 [e.data_type(ins) for e, _ in self.exprs])
+
+
+def create_agg(function: int, children: Sequence[E.Expr], input_schema: Schema, return_type: T.DataType) -> AggFunctionExpr:
+    """`create_agg` (agg/agg.rs:171-205).  The Count/Sum/Avg rewrites (drop non-nullable count
+    children, wrap Sum/Avg children in TryCast(return_type)) happen natively at decode time, exactly
+    where the reference does them."""
+    return AggFunctionExpr(function, children, return_type)
+
+
+class AggExec(ExecutionPlan):
+    def __init__(self, exec_mode: int, groupings: Sequence[GroupingExpr], aggs: Sequence[AggExpr],
+                 supports_partial_skipping: bool, input: ExecutionPlan, columnar_state: bool = False):
+        self.exec_mode = exec_mode
+        self.groupings = list(groupings)
+        self.aggs = list(aggs)
+        self.supports_partial_skipping = supports_partial_skipping
+        self.input = input
+        self.columnar_state = columnar_state
+        ins = input.schema()
+        fields = [Field(g.field_name, g.expr.data_type(ins), g.expr.nullable(ins)) for g in self.groupings]
+        final = any(a.mode == Final for a in self.aggs)
+        if final:
+            for a in self.aggs:
+                fields.append(Field(a.field_name, _agg_final_type(a.agg, ins), a.agg.function != E.AGG_COUNT))
+        elif columnar_state:
+            for a in self.aggs:
+                fields += _state_fields(a, ins)
+        else:
+            fields.append(Field(E.AGG_BUF_COLUMN_NAME, T.binary, False))                             # agg_ctx.rs:139-141
+        self._schema = Schema(fields)
+        self._validate()
+
+    try_new = classmethod(lambda cls, exec_mode, groupings, aggs, supports_partial_skipping, input:
+                          cls(exec_mode, groupings, aggs, supports_partial_skipping, input))
+
+    def schema(self):
+        return self._schema
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        return P.agg_node(self.input.node(), self.exec_mode, self.groupings, self.aggs, self.supports_partial_skipping)
+
+
+def _agg_data_type(f: AggFunctionExpr, ins: Schema) -> T.DataType:
+    if f.function == E.AGG_COUNT:
+        return T.int64
+    if f.function in (E.AGG_SUM, E.AGG_AVG):
+        return f.return_type
+    return f.children[0].data_type(ins)
+
+
+def _agg_final_type(f: AggFunctionExpr, ins: Schema) -> T.DataType:
+    dt = _agg_data_type(f, ins)
+    if f.function == E.AGG_AVG and not dt.is_decimal:
+        return T.float64                                                                              # avg.rs:166-171
+    return dt
+
+
+def _state_fields(a: AggExpr, ins: Schema) -> List[Field]:
+    dt = _agg_data_type(a.agg, ins)
+    if a.agg.function == E.AGG_COUNT:
+        return [Field(a.field_name, T.int64, False)]
+    if a.agg.function == E.AGG_AVG:
+        return [Field(a.field_name + "#sum", dt, True), Field(a.field_name + "#count", T.int64, False)]
+    return [Field(a.field_name, dt, True)]

@@ -1,0 +1,211 @@
+/*
+ * blaze_b200.h — C ABI of the B200-native Filter / Project / HashAgg hot path.
+ *
+ * This is the drop-in boundary posited by BASELINE.json's north_star: the reference
+ * (kwai/blaze = Apache Auron @ d1eaef148a58) keeps its Rust host code — plan-serde, JNI bridge,
+ * `ExecutionPlan` impls — and each `execute()` body forwards Arrow batches through these entry
+ * points instead of running the CPU operator.  INTEGRATION.md shows the Rust shim.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/native-engine/):
+ *
+ *   b200q_op_create         FilterExec::try_new   datafusion-ext-plans/src/filter_exec.rs:51-73
+ *                           ProjectExec::try_new  datafusion-ext-plans/src/project_exec.rs:57-81
+ *                           AggExec::try_new      datafusion-ext-plans/src/agg_exec.rs:67-98
+ *                           + plan decoding       auron-serde/src/from_proto.rs:107-152,407-500,839-1026
+ *   b200q_op_output_schema  ExecutionPlan::schema()        filter_exec.rs:99-101, project_exec.rs:119-121,
+ *                                                          agg_exec.rs:121-123
+ *   b200q_op_push           the `input.next()` side of the operator loop
+ *                           filter_exec.rs:186-195, project_exec.rs:217-229, agg_exec.rs:240-274;
+ *                           batch layout = struct-typed ArrowArray, as FFIReaderExec imports it
+ *                           datafusion-ext-plans/src/ffi_reader_exec.rs:163-194
+ *   b200q_op_finish         end of the input stream: `tables.output(sender)` agg_exec.rs:275
+ *   b200q_op_pull           `sender.send(batch)` / SendableRecordBatchStream::poll_next; batches leave
+ *                           as struct-typed ArrowArray exactly like auron/src/rt.rs:229-259
+ *   b200q_op_metrics        BaselineMetrics / update_spark_metric_node   auron/src/metrics.rs:22-58
+ *   b200q_op_destroy        drop of the operator stream / NativeExecutionRuntime::finalize rt.rs:261-273
+ *   b200q_conf              auron-jni-bridge/src/conf.rs:32-61 (keys) with the native fallbacks of
+ *                           datafusion-ext-commons/src/lib.rs:74-91 and agg/agg_ctx.rs:174-185
+ *   b200q_last_error        DataFusionError::Execution(msg) forwarded through the channel
+ *                           datafusion-ext-plans/src/common/execution_context.rs:569-598
+ *   b200q_murmur3_partition evaluate_hashes + evaluate_partition_ids
+ *                           datafusion-ext-plans/src/shuffle/mod.rs:163-188 (Spark murmur3 seed 42, pmod)
+ *
+ * Conventions: every call returns a status (0 = ok) and never unwinds; the message of the last
+ * failure on the calling thread is available from b200q_last_error().  A CUDA error is sticky
+ * for the handle.  A handle is used by one thread at a time (the operator's producer task);
+ * different handles are independent (one CUDA stream set each).
+ */
+#ifndef BLAZE_B200_H
+#define BLAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data / Device Data Interface (spec structs; guarded like arrow/c/abi.h) ---------- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif /* ARROW_C_DATA_INTERFACE */
+
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void* sync_event; /* cudaEvent_t* or NULL */
+  int64_t reserved[3];
+};
+#endif /* ARROW_C_DEVICE_DATA_INTERFACE */
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+typedef int32_t b200q_status;
+#define B200Q_OK 0
+#define B200Q_ERR_INVALID_PLAN 1 /* malformed protobuf / missing required field (PlanSerDeError)   */
+#define B200Q_ERR_UNSUPPORTED 2  /* plan is valid for the reference but outside this hot path      */
+#define B200Q_ERR_CUDA 3         /* CUDA runtime failure; sticky for the handle                    */
+#define B200Q_ERR_STATE 4        /* call sequence violation (push after finish, ...)               */
+#define B200Q_ERR_EXECUTION 5    /* data-dependent error, e.g. "Divide by zero error"              */
+#define B200Q_ERR_NO_DEVICE 6    /* no CUDA device / sm_100a kernels cannot run: NEVER falls back   */
+#define B200Q_ERR_INVALID_ARG 7
+
+/* plan_kind for b200q_op_create / b200q_plan_explain */
+#define B200Q_PLAN_NODE 0       /* bytes are a plan.protobuf.PhysicalPlanNode (auron.proto:27-55)  */
+#define B200Q_TASK_DEFINITION 1 /* bytes are a plan.protobuf.TaskDefinition   (auron.proto:735-740) */
+
+typedef struct b200q_op b200q_op;
+
+/* Tunables: the AuronConf keys the path reads (AuronConf.java:25-128) + GPU-side sizing knobs. */
+typedef struct b200q_conf {
+  uint32_t struct_size;               /* sizeof(b200q_conf), for forward compatibility            */
+  int32_t batch_size;                 /* BATCH_SIZE, default 10000 (commons/src/lib.rs:74-77)     */
+  int64_t suggested_batch_mem_size;   /* SUGGESTED_BATCH_MEM_SIZE, default 8 MiB (lib.rs:79-82)   */
+  int32_t partial_agg_skipping_enable;/* accepted; the GPU table never needs to skip  */
+  double partial_agg_skipping_ratio;  /* default 0.999 (agg_ctx.rs:177)                           */
+  int64_t partial_agg_skipping_min_rows; /* default 20000 (agg_ctx.rs:178)                        */
+  int64_t staging_rows;               /* host batches are staged in pinned memory up to this many
+                                         rows before one H2D + one kernel launch (default 1<<20)  */
+  int64_t agg_initial_groups;         /* initial hash-table sizing hint in groups (default 1<<19) */
+  int64_t max_launch_rows;            /* rows per kernel launch for device-resident pushes
+                                         (default 1<<26)                                          */
+  int32_t partial_state_columnar;     /* 1: non-final agg output/input uses typed state columns
+                                         (GPU-to-GPU exchange) instead of the reference's Binary
+                                         frozen-row column `#9223372036854775807`                 */
+  int32_t force_generic_kernels;      /* 1: disable the specialised fast kernels (testing)        */
+} b200q_conf;
+
+typedef struct b200q_metrics {
+  uint32_t struct_size;
+  int64_t input_rows;
+  int64_t input_batches;
+  int64_t output_rows;                /* BaselineMetrics::output_rows                             */
+  int64_t output_batches;
+  int64_t elapsed_compute_ns;         /* device time of this op's kernels (CUDA events)           */
+  int64_t gpu_kernel_launches;        /* kernels of THIS library launched by the op               */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t num_groups;                 /* agg: groups currently in the table                       */
+  int64_t table_capacity_slots;
+  int64_t table_grow_count;
+  int64_t fast_path_launches;         /* launches that took a specialised kernel                  */
+} b200q_metrics;
+
+/* library identity; safe without a GPU */
+int32_t b200q_version(void);
+const char* b200q_build_info(void);
+/* message of the last failing call on this thread ("" if none) */
+const char* b200q_last_error(void);
+/* number of visible CUDA devices (0 without a GPU/driver; never an error) */
+int32_t b200q_device_count(void);
+
+/* fill *conf with the defaults listed above */
+b200q_status b200q_conf_init(b200q_conf* conf);
+
+/* Decode + validate a plan WITHOUT touching the GPU and render it as text (host-logic tests,
+ * debugging).  Writes at most cap bytes incl. NUL; *needed = bytes required. */
+b200q_status b200q_plan_explain(const uint8_t* plan, size_t plan_len, int32_t plan_kind,
+                                char* buf, size_t cap, size_t* needed);
+
+/* Build the operator pipeline for a plan subtree made of Agg / Projection / Filter nodes over one
+ * FFIReader or EmptyPartitions leaf.  `input_schema` may be NULL (the leaf carries its schema);
+ * when given it must match the leaf schema.  `device` is the CUDA ordinal. */
+b200q_status b200q_op_create(const uint8_t* plan, size_t plan_len, int32_t plan_kind,
+                             const struct ArrowSchema* input_schema, const b200q_conf* conf,
+                             int32_t device, b200q_op** out);
+
+/* schema of the batches accepted by push (the leaf schema) / produced by pull; caller releases */
+b200q_status b200q_op_input_schema(b200q_op* op, struct ArrowSchema* out);
+b200q_status b200q_op_output_schema(b200q_op* op, struct ArrowSchema* out);
+
+/* Feed one input batch: a struct-typed ArrowArray in HOST memory whose children are the columns
+ * of the input schema.  Ownership moves to the library (it calls batch->release when done, also on
+ * failure). */
+b200q_status b200q_op_push(b200q_op* op, struct ArrowArray* batch);
+/* Same, for columns already resident in HBM (ARROW_DEVICE_CUDA, same device as the op). */
+b200q_status b200q_op_push_device(b200q_op* op, struct ArrowDeviceArray* batch);
+
+/* End of input: flush staged rows, run final aggregation / emission. */
+b200q_status b200q_op_finish(b200q_op* op);
+
+/* Next output batch (struct-typed ArrowArray in host memory; caller releases).  *has_batch = 0
+ * when nothing is available: before finish this means "push more", after finish "exhausted". */
+b200q_status b200q_op_pull(b200q_op* op, struct ArrowArray* out, int32_t* has_batch);
+/* Same, but buffers stay in HBM (for GPU-to-GPU chaining and the HBM-resident benchmark). */
+b200q_status b200q_op_pull_device(b200q_op* op, struct ArrowDeviceArray* out, int32_t* has_batch);
+
+/* block until all device work queued by this op has completed */
+b200q_status b200q_op_sync(b200q_op* op);
+
+b200q_status b200q_op_metrics(b200q_op* op, b200q_metrics* out);
+void b200q_op_destroy(b200q_op* op);
+
+/* Spark-compatible partition ids of device-resident key columns:
+ * pid[i] = pmod(murmur3_x86_32 chained over the key columns (NULL leaves the hash unchanged), seed 42,
+ * num_partitions).  `keys` is a struct-typed device array; out_pids is a device buffer of
+ * keys->array.length uint32.  Used for the multi-GPU partial->final exchange. */
+b200q_status b200q_murmur3_partition(const struct ArrowSchema* key_schema,
+                                     const struct ArrowDeviceArray* keys, int32_t num_partitions,
+                                     uint32_t* out_pids_device, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLAZE_B200_H */

@@ -1,0 +1,143 @@
+"""HashAggregateExec on the GPU vs the oracle (multiset parity; bit-exact ints/decimals, 1e-6 fp64)."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from blaze_b200 import exprs as E, plans as PL, types as T, native
+from oracle import blaze_oracle as O
+from helpers import *
+
+pytestmark = pytest.mark.gpu
+
+
+def agg_exprs(mode, specs, ins):
+    return [E.AggExpr(name, mode, PL.create_agg(fn, children, ins, rt)) for name, fn, children, rt in specs]
+
+
+def run_partial_final(rb, group_cols, specs, batch_rows=10000, conf=None, float_cols=(), columnar=False):
+    """Partial -> Final through the reference's Binary agg-buffer column (or the columnar state),
+    both stages fused in one op; compared with the oracle running the same two AggExecs."""
+    batches = split_batches(rb, batch_rows)
+    leaf = PL.MemoryExec.from_arrow(batches, rb.schema)
+    ins = leaf.schema()
+    groupings = [E.GroupingExpr(c, E.Column(c)) for c in group_cols]
+    partial = PL.AggExec(PL.HashAgg, groupings, agg_exprs(PL.Partial, specs, ins), False, leaf, columnar_state=columnar)
+    specs_final = [(name, fn, [E.placeholder(ch[0].data_type(ins))] if ch else [], rt) for name, fn, ch, rt in specs]
+    final = PL.AggExec(PL.HashAgg, groupings, agg_exprs(PL.Final, specs_final, partial.schema()), False, partial)
+    if columnar:
+        conf = conf or native.default_conf()
+        conf.partial_state_columnar = 1
+    got = PL.collect(final, conf)
+    ob = oracle_batches(batches)
+    o_partial = O.AggExec(E.HASH_AGG, groupings, agg_exprs(E.PARTIAL, specs, ins), False, ins)
+    mid = o_partial.execute(ob)
+    o_final = O.AggExec(E.HASH_AGG, groupings, agg_exprs(E.FINAL, specs_final, o_partial.schema), False, o_partial.schema)
+    exp = o_final.execute(mid)
+    assert_multiset_equal(got, exp, float_cols)
+    return got, final
+
+
+def test_reference_kat_test_agg():
+    """the reference's own golden table (agg_exec.rs:493-681), in-scope aggregates"""
+    cols = {"a": [2, 9, 3, 1, 0, 4, 6], "b": [1, 0, 0, 3, 5, 6, 3], "c": [7, 8, 7, 8, 9, 2, 5], "d": [-7, 86, 71, 83, 90, -2, 5],
+            "e": [-7, 86, 71, 83, 90, -2, 5], "f": [0, 1, 2, 3, 4, 5, 6], "g": [6, 3, 6, 3, 1, 5, 4], "h": [6, 3, 6, 3, 1, 5, 4]}
+    rb = rb_from_cols(list(cols), [pa.array(v, pa.int32()) for v in cols.values()])
+    specs = [("agg_expr_sum", E.AGG_SUM, [E.Column("a")], T.int64), ("agg_expr_avg", E.AGG_AVG, [E.Column("b")], T.float64),
+             ("agg_expr_max", E.AGG_MAX, [E.Column("d")], T.int32), ("agg_expr_min", E.AGG_MIN, [E.Column("e")], T.int32),
+             ("agg_expr_count", E.AGG_COUNT, [E.Column("f")], T.int64)]
+    got, _ = run_partial_final(rb, ["c"], specs)
+    t = pa.Table.from_batches(got).sort_by("c").to_pydict()
+    assert t == {"c": [2, 5, 7, 8, 9], "agg_expr_sum": [4, 6, 5, 10, 0], "agg_expr_avg": [6.0, 3.0, 0.5, 1.5, 5.0],
+                 "agg_expr_max": [-2, 5, 71, 86, 90], "agg_expr_min": [-2, 5, -7, 83, 90], "agg_expr_count": [1, 1, 2, 2, 1]}
+
+
+def m1_batch(n, card, seed=44, null_frac=0.0, key_null_frac=0.0):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, card, n, dtype=np.int64)
+    v = rng.integers(-10**6, 10**6, n, dtype=np.int64)
+    return rb_from_cols(["k", "v"], [with_nulls(rng, k, key_null_frac), with_nulls(rng, v, null_frac)])
+
+
+@pytest.mark.parametrize("columnar", [False, True])
+@pytest.mark.parametrize("n,card,nf,knf", [(1, 1, 0, 0), (1000, 7, 0.3, 0.1), (200_000, 50_000, 0.1, 0.0), (300_000, 3, 0.0, 0.05)])
+def test_m1_sum_count(n, card, nf, knf, columnar):
+    rb = m1_batch(n, card, 44, nf, knf)
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64),
+             ("mn", E.AGG_MIN, [E.Column("v")], T.int64), ("mx", E.AGG_MAX, [E.Column("v")], T.int64),
+             ("av", E.AGG_AVG, [E.Column("v")], T.float64)]
+    run_partial_final(rb, ["k"], specs, float_cols=(5,), columnar=columnar)
+
+
+def test_all_null_group_and_wrapping_sum():
+    k = pa.array([1, 1, 2, 2, 3], pa.int64())
+    v = pa.array([2**62, 2**62, None, None, -5], pa.int64())
+    rb = rb_from_cols(["k", "v"], [k, v])
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64)]
+    got, _ = run_partial_final(rb, ["k"], specs)
+    t = pa.Table.from_batches(got).sort_by("k").to_pydict()
+    assert t["s"] == [-2**63, None, -5] and t["c"] == [2, 0, 1]      # wrapping add (Cargo.toml:43-45), NULL for an all-NULL group
+
+
+def test_table_growth_many_groups():
+    n = 600_000
+    rb = m1_batch(n, 2**40, 45)                                       # ~all keys distinct: forces rehash + replay of deferred rows
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64)]
+    conf = native.default_conf(agg_initial_groups=1024, staging_rows=0)
+    got, plan = run_partial_final(rb, ["k"], specs, batch_rows=n, conf=conf)
+    assert plan.last_metrics["table_grow_count"] >= 0
+
+
+def test_two_keys_filter_fused_q1_shape():
+    n = 250_000
+    rng = np.random.default_rng(46)
+    f = rng.integers(0, 1000, n, dtype=np.int64)
+    k1 = rng.integers(0, 2**10, n, dtype=np.int64)
+    k2 = rng.integers(0, 8, n).astype(np.int32)
+    v = rng.integers(-10**6, 10**6, n, dtype=np.int64)
+    rb = rb_from_cols(["f", "k1", "k2", "v"], [pa.array(f), with_nulls(rng, k1, 0.01), pa.array(k2), with_nulls(rng, v, 0.05)])
+    batches = split_batches(rb, 10000)
+    leaf = PL.MemoryExec.from_arrow(batches, rb.schema)
+    ins = leaf.schema()
+    preds = [E.BinaryExpr(E.Column("f"), "GtEq", E.Literal(200, T.int64)), E.BinaryExpr(E.Column("f"), "LtEq", E.Literal(399, T.int64))]
+    filt = PL.FilterExec(preds, leaf)
+    groupings = [E.GroupingExpr("k1", E.Column("k1")), E.GroupingExpr("k2", E.Column("k2"))]
+    aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], ins, T.int64))]
+    plan = PL.AggExec(PL.HashAgg, groupings, aggs, True, filt)
+    got = PL.collect(plan)
+    ob = oracle_batches(batches)
+    exp = O.AggExec(E.HASH_AGG, groupings, aggs, False, ins).execute(O.FilterExec(preds, ins).execute(ob))
+    assert_multiset_equal(got, exp)                                   # includes the frozen Binary column, byte for byte
+
+
+def test_no_grouping_and_empty_input():
+    rb = m1_batch(5000, 10, 47, 0.2)
+    leaf = PL.MemoryExec.from_arrow(split_batches(rb, 1000), rb.schema)
+    ins = leaf.schema()
+    aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], ins, T.int64)),
+            E.AggExpr("c", E.PARTIAL, PL.create_agg(E.AGG_COUNT, [E.Column("v")], ins, T.int64))]
+    plan = PL.AggExec(PL.HashAgg, [], aggs, False, leaf)
+    got = PL.collect(plan)
+    exp = O.AggExec(E.HASH_AGG, [], aggs, False, ins).execute(oracle_batches(leaf.batches))
+    assert_multiset_equal(got, exp)
+    empty = PL.MemoryExec(ins, [])
+    got = PL.collect(PL.AggExec(PL.HashAgg, [], aggs, False, empty))
+    exp = O.AggExec(E.HASH_AGG, [], aggs, False, ins).execute([])
+    assert_multiset_equal(got, exp)
+    assert PL.collect(PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs, False, empty)) == []
+
+
+def test_f64_and_decimal_sums():
+    import decimal
+    n = 120_000
+    rng = np.random.default_rng(48)
+    k = rng.integers(0, 5000, n, dtype=np.int64)
+    x = rng.normal(0, 1e6, n)
+    raw = rng.integers(-10**15, 10**15, n)
+    dec = pa.array([decimal.Decimal(int(r)).scaleb(-2) for r in raw], type=pa.decimal128(17, 2))
+    rb = rb_from_cols(["k", "x", "d"], [pa.array(k), with_nulls(rng, x, 0.1), dec])
+    specs = [("sx", E.AGG_SUM, [E.Column("x")], T.float64), ("ax", E.AGG_AVG, [E.Column("x")], T.float64),
+             ("mnx", E.AGG_MIN, [E.Column("x")], T.float64), ("mxx", E.AGG_MAX, [E.Column("x")], T.float64),
+             ("sd", E.AGG_SUM, [E.Column("d")], T.decimal128(27, 2)), ("ad", E.AGG_AVG, [E.Column("d")], T.decimal128(21, 6)),
+             ("mnd", E.AGG_MIN, [E.Column("d")], T.decimal128(17, 2)), ("mxd", E.AGG_MAX, [E.Column("d")], T.decimal128(17, 2)),
+             ("c", E.AGG_COUNT, [E.Column("x")], T.int64)]
+    run_partial_final(rb, ["k"], specs, float_cols=(1, 2))

@@ -1,0 +1,134 @@
+"""Pin the oracle against every golden vector the reference's own tests hold for this path
+(SURVEY.md §8c).  CPU only."""
+import numpy as np
+import pyarrow as pa
+
+from blaze_b200 import exprs as E, types as T
+from oracle import blaze_oracle as O
+
+
+def _i32_batch(cols):
+    return O.batch_from_arrow(pa.RecordBatch.from_arrays([pa.array(v, pa.int32()) for v in cols.values()], names=list(cols)))
+
+
+def test_agg_kat_partial_then_final():
+    """datafusion-ext-plans/src/agg_exec.rs:493-681 `test_agg`, rows 1-5 of the expected table for the
+    five in-scope aggregates."""
+    cols = {"a": [2, 9, 3, 1, 0, 4, 6], "b": [1, 0, 0, 3, 5, 6, 3], "c": [7, 8, 7, 8, 9, 2, 5], "d": [-7, 86, 71, 83, 90, -2, 5],
+            "e": [-7, 86, 71, 83, 90, -2, 5], "f": [0, 1, 2, 3, 4, 5, 6], "g": [6, 3, 6, 3, 1, 5, 4], "h": [6, 3, 6, 3, 1, 5, 4]}
+    b = _i32_batch(cols)
+    ins = b.schema
+    specs = [("agg_expr_sum", E.AGG_SUM, "a", T.int64), ("agg_expr_avg", E.AGG_AVG, "b", T.float64),
+             ("agg_expr_max", E.AGG_MAX, "d", T.int32), ("agg_expr_min", E.AGG_MIN, "e", T.int32),
+             ("agg_expr_count", E.AGG_COUNT, "f", T.int64)]
+    g = [E.GroupingExpr("c", E.Column("c"))]
+    partial = O.AggExec(E.HASH_AGG, g, [E.AggExpr(n, E.PARTIAL, E.AggFunctionExpr(f, [E.Column(c)], rt)) for n, f, c, rt in specs], False, ins)
+    mid = partial.execute([b])
+    assert [f.name for f in partial.schema] == ["c", "#9223372036854775807"] and partial.schema[1].dtype == T.binary
+    final = O.AggExec(E.HASH_AGG, g, [E.AggExpr(n, E.FINAL, E.AggFunctionExpr(f, [E.Literal(None, T.null)] if f != E.AGG_MAX and f != E.AGG_MIN
+                                                                                else [E.placeholder(T.int32)], rt)) for n, f, c, rt in specs],
+                      False, partial.schema)
+    out = O.concat_batches(final.schema, final.execute(mid))
+    rows = sorted(zip(*[[None if not c.valid[i] else c.values[i].item() for i in range(out.num_rows)] for c in out.cols]))
+    assert rows == [(2, 4, 6.0, -2, -2, 1), (5, 6, 3.0, 5, 5, 1), (7, 5, 0.5, 71, -7, 2), (8, 10, 1.5, 86, 83, 2), (9, 0, 5.0, 90, 90, 1)]
+
+
+def test_agg_fuzz_model_seeded():
+    """agg_exec.rs:714-843 `fuzztest` re-expressed with a fixed seed: key = u32 % 1e6 as i64, val f64 non-null
+    only when u32 % 1000 == 0 (the inverted flag, :732-739), partial stage with supports_partial_skipping=true;
+    per-key `sum as i64` equality and exact counts, cnt == 0 where the sum is NULL (:825-841)."""
+    rng = np.random.default_rng(12345)
+    batches, model_sum, model_cnt = [], {}, {}
+    for _ in range(20):
+        key = (rng.integers(0, 2**32, 10000, dtype=np.uint64) % 1_000_000).astype(np.int64)
+        val = (rng.integers(0, 2**32, 10000, dtype=np.uint64) % 1_000_000).astype(np.float64)
+        nonnull = rng.integers(0, 2**32, 10000, dtype=np.uint64) % 1000 == 0
+        for k, v, ok in zip(key, val, nonnull):
+            if ok:
+                model_sum[k] = model_sum.get(k, 0.0) + v
+                model_cnt[k] = model_cnt.get(k, 0) + 1
+        batches.append(O.batch_from_arrow(pa.RecordBatch.from_arrays([pa.array(key), pa.array(val, mask=~nonnull)], names=["key", "val"])))
+    ins = batches[0].schema
+    ins = T.Schema([T.Field("key", T.int64, False), T.Field("val", T.float64, True)])
+    for b in batches:
+        b.schema = ins
+    g = [E.GroupingExpr("key", E.Column("key"))]
+    # merge-mode aggregates carry placeholder children (NativeAggBase.scala:241-282)
+    ch = lambda mode: [E.Column("val")] if mode == E.PARTIAL else [E.placeholder(T.float64)]
+    mk = lambda mode: [E.AggExpr("sum", mode, E.AggFunctionExpr(E.AGG_SUM, ch(mode), T.float64)),
+                       E.AggExpr("cnt", mode, E.AggFunctionExpr(E.AGG_COUNT, ch(mode), T.int64))]
+    partial = O.AggExec(E.HASH_AGG, g, mk(E.PARTIAL), True, ins)
+    mid = partial.execute(batches)
+    final = O.AggExec(E.HASH_AGG, g, mk(E.FINAL), False, partial.schema)
+    out = O.concat_batches(final.schema, final.execute(mid))
+    seen = 0
+    for i in range(out.num_rows):
+        k = out.cols[0].values[i]
+        assert out.cols[0].valid[i] and out.cols[2].valid[i]
+        if out.cols[1].valid[i]:
+            assert int(model_sum[k]) == int(out.cols[1].values[i])
+            assert model_cnt[k] == out.cols[2].values[i]
+            seen += 1
+        else:
+            assert out.cols[2].values[i] == 0
+    assert seen == len(model_sum)
+
+
+def test_murmur3_kats():
+    # datafusion-ext-commons/src/hash/mur.rs:94-103
+    assert [O.murmur3_bytes(s.encode(), 42) for s in ["", "a", "ab", "abc", "abcd", "abcde"]] == \
+        [142593372, 1485273170, -97053317, 1322437556, -396302900, 814637928]
+    # spark_hash.rs:377-456 (values generated from Spark)
+    u = lambda xs: [x - (1 << 32) if x >> 31 else x for x in xs]
+    i8 = O.col_from_arrow(pa.array([1, 0, -1, 127, -128], pa.int8()))
+    assert list(O.create_murmur3_hashes([i8], 5, 42)) == u([0xdea578e3, 0x379fae8f, 0xa0590e3d, 0x43b4d8ed, 0x422a1365])
+    i32 = O.col_from_arrow(pa.array([1, 2, 3, 4], pa.int32()))
+    assert list(O.create_murmur3_hashes([i32], 4, 42)) == [-559580957, 1765031574, -1823081949, -397064898]
+    i64 = O.col_from_arrow(pa.array([1, 0, -1, 2**63 - 1, -2**63], pa.int64()))
+    assert list(O.create_murmur3_hashes([i64], 5, 42)) == u([0x99f0149d, 0x9c67b85d, 0xc8008529, 0xa05b5d7b, 0xcd1e64fb])
+    assert [O.murmur3_long(v, 42) for v in [1, 0, -1]] == u([0x99f0149d, 0x9c67b85d, 0xc8008529])
+    # pmod
+    assert list(O.partition_ids(np.array([-559580957, 1765031574, -1], np.int32), 200)) == [(-559580957) % 200, 1765031574 % 200, 199]
+
+
+def test_check_overflow_kat():
+    # datafusion-ext-functions/src/spark_check_overflow.rs:134-158: (20,8) -> (10,5)
+    vals = [12342132145623, 13245, 123213244568923, 1234567890, None]
+    got = [None if v is None else O.change_precision_round_half_up(v, 20, 8, 10, 5) for v in vals]
+    assert got == [None, 13, None, 1234568, None]
+
+
+def test_varint_and_frozen_rows():
+    # write_len/read_len (datafusion-ext-commons/src/io/mod.rs:60-83)
+    for n in [0, 1, 127, 128, 129, 16383, 16384, 2**32, 2**63 - 1]:
+        b = O.write_len(n)
+        assert O.read_len(b, 0) == (n, len(b))
+    assert O.write_len(127) == b"\x7f" and O.write_len(128) == b"\x80\x01" and O.write_len(300) == bytes([128 + 44, 2])
+    # prim [valid][LE bytes] (acc.rs:335-346), count varint, avg = sum || count (avg.rs:208-212)
+    acc = O._PrimAcc(T.int64); acc.resize(2); acc.update_value(0, np.int64(-2), lambda v: v)
+    assert acc.freeze(0) == b"\x01" + (-2).to_bytes(8, "little", signed=True) and acc.freeze(1) == b"\x00"
+
+
+def test_partial_skipping_passthrough_keeps_the_final_result():
+    """agg_table.rs:108-120,447-463 + agg_ctx.rs:428-462: once >= 20000 groups with cardinality ratio > 0.999 the
+    table is flushed and later rows pass through as one partial state per row; the Final result is unchanged."""
+    n = 60000
+    key = np.arange(n, dtype=np.int64) % 50000                      # the first 50000 rows are all distinct
+    val = np.arange(n, dtype=np.int64)
+    ins = T.Schema([T.Field("key", T.int64, False), T.Field("val", T.int64, False)])
+    batches = []
+    for i in range(0, n, 10000):
+        b = O.batch_from_arrow(pa.RecordBatch.from_arrays([pa.array(key[i:i + 10000]), pa.array(val[i:i + 10000])], names=["key", "val"]))
+        b.schema = ins
+        batches.append(b)
+    g = [E.GroupingExpr("key", E.Column("key"))]
+    mk = lambda mode: [E.AggExpr("sum", mode, E.AggFunctionExpr(E.AGG_SUM, [E.Column("val")] if mode == E.PARTIAL else [E.placeholder(T.int64)], T.int64))]
+    outs = {}
+    for skipping in (False, True):
+        partial = O.AggExec(E.HASH_AGG, g, mk(E.PARTIAL), skipping, ins)
+        mid = partial.execute(batches)
+        if skipping:
+            assert sum(b.num_rows for b in mid) == n               # every row after the trigger became its own partial row
+        final = O.AggExec(E.HASH_AGG, g, mk(E.FINAL), False, partial.schema)
+        outs[skipping] = O.rows_multiset(final.execute(mid))
+    assert outs[False] == outs[True] and len(outs[True]) == 50000
