@@ -496,6 +496,7 @@ b200q_status b200q_op_create(const uint8_t* plan, size_t plan_len, int32_t plan_
     if (op->cx.conf.agg_initial_groups <= 0) op->cx.conf.agg_initial_groups = 1 << 19;
     B200Q_CUDA(cudaSetDevice(device));
     B200Q_CUDA(cudaStreamCreateWithFlags(&op->cx.stream, cudaStreamNonBlocking));
+    B200Q_CUDA(cudaEventCreate(&op->cx.ev0)); B200Q_CUDA(cudaEventCreate(&op->cx.ev1));
     build_pipeline(op);
     if (input_schema) {
       if (input_schema->n_children != (int64_t)op->in_schema.fields.size()) throw PlanError(B200Q_ERR_INVALID_ARG, "input_schema does not match the plan leaf: column count");
@@ -643,6 +644,7 @@ b200q_status b200q_op_metrics(b200q_op* op, b200q_metrics* out) {
   b200q_metrics r; memset(&r, 0, sizeof(r)); r.struct_size = sizeof(r);
   r.input_rows = m.input_rows; r.input_batches = m.input_batches; r.output_rows = m.output_rows; r.output_batches = m.output_batches;
   r.elapsed_compute_ns = (int64_t)(m.gpu_ms * 1e6); r.gpu_kernel_launches = m.launches; r.h2d_bytes = m.h2d_bytes; r.d2h_bytes = m.d2h_bytes;
+  r.hot_kernel_ns = (int64_t)(m.hot_ms * 1e6); r.hot_kernel_rows = m.hot_rows; r.hot_kernel_launches = m.hot_launches;
   r.num_groups = m.num_groups; r.table_capacity_slots = m.table_capacity; r.table_grow_count = m.grow_count; r.fast_path_launches = m.fast_launches;
   const size_t n = std::min<size_t>(out->struct_size ? out->struct_size : sizeof(r), sizeof(r));
   memcpy(out, &r, n);
@@ -657,6 +659,8 @@ void b200q_op_destroy(b200q_op* op) {
   op->out_queue.clear(); op->has_cur_host = false; op->cur_host = HostBatch();
   op->stages.clear();
   staging_free(op);
+  if (op->cx.ev0) cudaEventDestroy(op->cx.ev0);
+  if (op->cx.ev1) cudaEventDestroy(op->cx.ev1);
   if (op->cx.stream) { cudaStreamSynchronize(op->cx.stream); cudaStreamDestroy(op->cx.stream); }
   delete op;
 }

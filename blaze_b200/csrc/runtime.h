@@ -64,6 +64,7 @@ struct Metrics {
   int64_t launches = 0, fast_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   int64_t num_groups = 0, table_capacity = 0, grow_count = 0;
   double gpu_ms = 0;
+  double hot_ms = 0; int64_t hot_rows = 0, hot_launches = 0;
 };
 
 struct OpContext {
@@ -71,6 +72,7 @@ struct OpContext {
   cudaStream_t stream = nullptr;
   b200q_conf conf;
   Metrics m;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // timing of the dominant kernel on `stream`
 };
 
 class Stage {

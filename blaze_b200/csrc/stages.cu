@@ -81,12 +81,15 @@ class FilterProjectStage : public Stage {
     const int64_t ntiles = filter_project_num_tiles(n);
     DevMemP status = has_filters_ ? DevMem::alloc((size_t)ntiles * 8, cx.stream, true) : nullptr;
     DevMemP scratch = DevMem::alloc(32, cx.stream, true);
+    B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
     cx.m.launches += launch_filter_project((const VmProgram*)d_prog_->ptr, ct, ot, (int)cp_.outs.size(), n, has_filters_,
                                            status ? (unsigned long long*)status->ptr : nullptr, (unsigned long long*)scratch->ptr, cx.stream);
+    B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
     B200Q_CUDA(cudaGetLastError());
     unsigned long long h[4];
     B200Q_CUDA(cudaMemcpyAsync(h, scratch->ptr, 32, cudaMemcpyDeviceToHost, cx.stream));
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.hot_ms += ms; cx.m.gpu_ms += ms; cx.m.hot_rows += n; cx.m.hot_launches++; }
     check_device_error_flags((int)h[2]);
     ob.num_rows = (int64_t)h[1];
     if (ob.num_rows > 0) outs.push_back(std::move(ob));       // sender.send drops empty batches (execution_context.rs:713-716)
@@ -425,10 +428,13 @@ class AggStage : public Stage {
         deferred_[0] = DevMem::alloc((size_t)m * 4, cx.stream);
         deferred_[1] = DevMem::alloc((size_t)m * 4, cx.stream);
       }
+      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
       cx.m.launches += launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, table_view(0), begin, m, nullptr, cx.stream);
+      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
       B200Q_CUDA(cudaGetLastError());
       unsigned long long h[3];
       read_counters(cx, h);
+      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.hot_ms += ms; cx.m.gpu_ms += ms; cx.m.hot_rows += m; cx.m.hot_launches++; }
       int cur = 0;
       while (h[1] > 0) {
         // the table hit its load limit: grow it, then replay only the rows that could not be inserted

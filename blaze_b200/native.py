@@ -61,7 +61,8 @@ class Conf(C.Structure):
 class Metrics(C.Structure):
     _fields_ = [("struct_size", C.c_uint32)] + [(n, C.c_int64) for n in (
         "input_rows", "input_batches", "output_rows", "output_batches", "elapsed_compute_ns", "gpu_kernel_launches",
-        "h2d_bytes", "d2h_bytes", "num_groups", "table_capacity_slots", "table_grow_count", "fast_path_launches")]
+        "h2d_bytes", "d2h_bytes", "num_groups", "table_capacity_slots", "table_grow_count", "fast_path_launches",
+        "hot_kernel_ns", "hot_kernel_rows", "hot_kernel_launches")]
 
 
 # every symbol include/blaze_b200.h declares (tests/test_capi_symbols.py checks the .so exports them all)

@@ -146,6 +146,10 @@ typedef struct b200q_metrics {
   int64_t table_capacity_slots;
   int64_t table_grow_count;
   int64_t fast_path_launches;         /* launches that took a specialised kernel                  */
+  int64_t hot_kernel_ns;              /* CUDA-event time of the dominant kernel only: the HashAgg
+                                         update kernel, or the fused filter/project kernel        */
+  int64_t hot_kernel_rows;            /* input rows those launches covered                        */
+  int64_t hot_kernel_launches;
 } b200q_metrics;
 
 /* library identity; safe without a GPU */
