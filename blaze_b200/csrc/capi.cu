@@ -446,6 +446,7 @@ static void conf_defaults(b200q_conf* c) {
   c->max_launch_rows = 1 << 26;
   c->partial_state_columnar = 0;
   c->force_generic_kernels = 0;
+  c->agg_dense_keys = 1;
 }
 
 }  // namespace b200q

@@ -14,26 +14,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "agg_device.cuh"
 #include "kernels.cuh"
 #include "vm.cuh"
 
 namespace b200q {
 
 // ---------------------------------------------------------------------------------------------------
-// small device helpers
+// small device helpers (atomics, hash, find-or-insert: agg_device.cuh)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-__device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
-__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-
 __device__ __forceinline__ void load_program(const VmProgram* __restrict__ g, VmInstr* s_code, uint64_t* s_pool) {
   const uint32_t nc = g->n_code, np = g->n_pool;
   for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) s_code[i] = g->code[i];
@@ -182,8 +171,6 @@ int launch_filter_project(const VmProgram* d_prog, const ColTable& cols, const O
 constexpr int AG_BLOCK = 256;
 constexpr int AG_R = 2;
 constexpr int AG_TILE = AG_BLOCK * AG_R;
-constexpr unsigned TAG_EMPTY = 0, TAG_LOCKED = 1;
-constexpr unsigned FLAG_SLOT_LOCK = 1u << 15;     // guards 128-bit min/max updates
 
 struct AggSink {
   uint64_t (*buf)[AGG_MAX_ROW_WORDS];
@@ -198,24 +185,15 @@ struct AggSink {
 };
 
 __device__ __forceinline__ uint64_t hash_keys(const AggLayout& lay, const uint64_t* buf, uint32_t vb, uint32_t& knull, uint64_t* kw) {
-  uint64_t h = 0x9E3779B97F4A7C15ULL;
   knull = 0;
   int w = 0;
   for (int k = 0; k < lay.nkeys; k++) {
     const int o = lay.key_out[k];
     const bool valid = (vb >> o) & 1;
     if (!valid) knull |= 1u << k;
-    for (int i = 0; i < lay.key_nwords[k]; i++) {
-      const uint64_t v = valid ? buf[lay.out_word[o] + i] : 0;   // NULL keys are canonicalised to 0 + null bit
-      kw[w++] = v;
-      h = mix64(h ^ v);
-    }
+    for (int i = 0; i < lay.key_nwords[k]; i++) kw[w++] = valid ? buf[lay.out_word[o] + i] : 0;   // NULL keys are canonicalised to 0 + null bit
   }
-  return mix64(h ^ knull);
-}
-
-__device__ __forceinline__ void slot_mark(unsigned long long* slot, unsigned flags_seen, int vbit) {
-  if (vbit != 0xFF && !((flags_seen >> vbit) & 1)) atomicOr((unsigned*)slot + 1, 1u << vbit);
+  return agg_hash_words(kw, w, knull);
 }
 
 __device__ __forceinline__ void dec_minmax(unsigned long long* slot, int word, i128_t v, bool is_min) {
@@ -234,37 +212,9 @@ __device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable&
   uint64_t kw[AGG_MAX_KEYS * 2];
   uint32_t knull;
   const uint64_t h = hash_keys(lay, buf, vb, knull, kw);
-  const unsigned tag = (unsigned)(h >> 32) | 0x80000000u;
-  uint64_t s = h & tab.mask;
-  unsigned long long* slot;
   unsigned flags;
-  while (true) {
-    slot = tab.slots + s * (uint64_t)lay.slot_words;
-    const unsigned long long hdr = ld_relaxed_u64(slot);
-    const unsigned t = (unsigned)hdr;
-    flags = (unsigned)(hdr >> 32);
-    if (t == tag) {
-      bool eq = (flags >> 16) == knull;
-      for (int i = 0; eq && i < lay.nkw; i++) eq = ld_relaxed_u64(slot + 1 + i) == kw[i];
-      if (eq) break;
-    } else if (t == TAG_EMPTY) {
-      if (ld_relaxed_u64(tab.counters) >= tab.max_groups) return false;       // table is at its load limit: defer the row
-      if (atomicCAS((unsigned*)slot, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
-        for (int i = 0; i < lay.nkw; i++) slot[1 + i] = kw[i];
-        for (int i = 1 + lay.nkw; i < lay.slot_words; i++) slot[i] = lay.init[i];
-        flags = lay.init_flags | (knull << 16);
-        ((unsigned*)slot)[1] = flags;
-        __threadfence();
-        st_release_u32((unsigned*)slot, tag);
-        atomicAdd(tab.counters, 1ULL);
-        break;
-      }
-      continue;                                                                 // lost the race: look at the same slot again
-    } else if (t == TAG_LOCKED) {
-      continue;                                                                 // being published by another thread
-    }
-    s = (s + 1) & tab.mask;
-  }
+  unsigned long long* slot = agg_find_or_insert(lay, tab, kw, knull, h, &flags);
+  if (!slot) return false;
   // accumulate (K6 / K7)
   for (int j = 0; j < lay.nacc; j++) {
     const AccOp a = lay.acc[j];
@@ -353,9 +303,7 @@ __global__ void __launch_bounds__(256) agg_rehash_kernel(const AggLayout lay, co
     const unsigned long long hdr = src[0];
     if ((unsigned)hdr < 2) continue;
     const unsigned knull = (unsigned)(hdr >> 48);
-    uint64_t h = 0x9E3779B97F4A7C15ULL;
-    for (int w = 0; w < lay.nkw; w++) h = mix64(h ^ src[1 + w]);
-    h = mix64(h ^ knull);
+    const uint64_t h = agg_hash_words((const uint64_t*)src + 1, lay.nkw, knull);
     uint64_t s = h & new_tab.mask;
     while (true) {
       unsigned long long* dst = new_tab.slots + s * (uint64_t)lay.slot_words;

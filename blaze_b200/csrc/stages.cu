@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "runtime.h"
+#include "kernels_fast.cuh"
 
 namespace b200q {
 
@@ -184,6 +185,12 @@ class AggStage : public Stage {
   int64_t deferred_cap_ = 0;
   int64_t ngroups_ = 0;
 
+  // specialised kernels (kernels_fast.cu)
+  bool fast_ok_ = false, dense_possible_ = false, dense_decided_ = false;
+  FastSpec fs_{};
+  DenseEmitMap dmap_{};
+  DevMemP dense_tab_;
+
   // emit plan (per output/state column)
   struct EmitSpec { EmitCol ec; FieldDef field; bool frozen_count = false; };
   std::vector<EmitSpec> emit_;          // key columns first, then per-agg result or state columns
@@ -242,6 +249,14 @@ class AggStage : public Stage {
     for (int i = 0; i < AGG_MAX_SLOT_WORDS; i++) lay_.init[i] = 0;
     lay_.init_flags = 0;
     int vbits = 0, state_k = 0;
+    {   // keep narrow accumulator sets inside one 32-byte sector (one L2 sector operation per row)
+      int total_acc_words = 0;
+      for (auto& a : agg.aggs) {
+        if (a.fn != AGG_COUNT) total_acc_words += a.data_type.is_decimal() ? 2 : 1;
+        if (a.fn == AGG_COUNT || a.fn == AGG_AVG) total_acc_words += 1;
+      }
+      if (total_acc_words <= 4 && (word % 4) + total_acc_words > 4) word = (word + 3) & ~3;
+    }
     auto new_vbit = [&]() { if (vbits >= 15) throw PlanError(B200Q_ERR_UNSUPPORTED, "too many nullable accumulators in one aggregate"); return (uint8_t)vbits++; };
     auto state_col_expr = [&](const FieldDef& f) {
       auto e = std::make_shared<Expr>(); e->kind = E_COLUMN; e->col_index = first_state_col_ + state_k++; e->name = f.name; e->type = f.type; e->nullable = f.nullable;
@@ -352,6 +367,8 @@ class AggStage : public Stage {
     d_prog_ = DevMem::alloc(sizeof(VmProgram), cx.stream);
     B200Q_CUDA(cudaMemcpyAsync(d_prog_->ptr, &cp_.prog, sizeof(VmProgram), cudaMemcpyHostToDevice, cx.stream));
 
+    detect_fast(cx);
+
     // ---- frozen-row descriptors of the state columns (non-final output in the reference format)
     if (!final_) {
       for (size_t i = lay_.nkeys; i < emit_.size(); i++) {
@@ -369,6 +386,108 @@ class AggStage : public Stage {
     if (lay_.nkeys == 0) seed_global_group(cx);
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
     cx.m.table_capacity = (int64_t)capacity_;
+  }
+
+
+  // ---- specialised-kernel eligibility -------------------------------------------------------------------
+  int prog_col_slot(int col_index) const {
+    for (size_t i = 0; i < cp_.used_cols.size(); i++) if (cp_.used_cols[i] == col_index) return (int)i;
+    return -1;
+  }
+  static bool int_phys(const DType& t) { return t.is_intlike(); }
+
+  void detect_fast(OpContext& cx) {
+    fast_ok_ = false;
+    if (cx.conf.force_generic_kernels) return;
+    if (lay_.nkeys < 1 || lay_.nkeys > 2 || lay_.nacc < 1 || lay_.nacc > 2 || filters_.size() > 4) return;
+    FastSpec fs{};
+    fs.nkeys = lay_.nkeys; fs.nacc = lay_.nacc; fs.nfilt = (int)filters_.size();
+    for (int k = 0; k < lay_.nkeys; k++) {
+      const ExprP& e = vm_outs_[lay_.key_out[k]];
+      if (e->kind != E_COLUMN || !int_phys(e->type) || lay_.key_nwords[k] != 1) return;
+      const int s = prog_col_slot(e->col_index); if (s < 0 || s > 127) return;
+      fs.key_col[k] = (int8_t)s; fs.key_phys[k] = phys_of(e->type);
+    }
+    for (int j = 0; j < lay_.nacc; j++) {
+      const AccOp& a = lay_.acc[j];
+      fs.acc[j].vbit = a.vbit; fs.acc[j].word = a.word; fs.acc[j].col = -1; fs.acc[j].phys = PH_I64;
+      if (a.kind == ACC_ADD_I64) {
+        const ExprP& e = vm_outs_[a.arg_out[0]];
+        if (e->kind != E_COLUMN || !int_phys(e->type)) return;
+        const int s = prog_col_slot(e->col_index); if (s < 0 || s > 127) return;
+        fs.acc[j].kind = FAST_ACC_ADD; fs.acc[j].col = (int8_t)s; fs.acc[j].phys = phys_of(e->type);
+      } else if (a.kind == ACC_COUNT && a.nargs <= 1) {
+        fs.acc[j].kind = FAST_ACC_COUNT;
+        if (a.nargs == 1) {
+          const ExprP& e = vm_outs_[a.arg_out[0]];
+          if (e->kind != E_COLUMN || !(e->type.is_intlike() || e->type.is_float() || e->type.is_decimal())) return;
+          const int s = prog_col_slot(e->col_index); if (s < 0 || s > 127) return;
+          fs.acc[j].col = (int8_t)s; fs.acc[j].phys = phys_of(e->type);
+        }
+      } else return;
+    }
+    if (lay_.nacc == 2 && lay_.acc[0].word / 4 != lay_.acc[1].word / 4) return;
+    for (size_t f = 0; f < filters_.size(); f++) {
+      const ExprP& p = filters_[f];
+      if (p->kind != E_BINARY || p->op < OP_EQ || p->op > OP_GE) return;
+      ExprP l = strip_noop_casts(p->children[0]), r = strip_noop_casts(p->children[1]);
+      int op = p->op - OP_EQ;
+      if (l->kind == E_LITERAL && r->kind == E_COLUMN) { std::swap(l, r); static const int flip[] = {CMP_EQ, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE}; op = flip[op]; }
+      if (l->kind != E_COLUMN || r->kind != E_LITERAL || r->lit_null || !int_phys(l->type) || !int_phys(r->type)) return;
+      const int s = prog_col_slot(l->col_index); if (s < 0 || s > 127) return;
+      fs.filt[f].col = (int8_t)s; fs.filt[f].phys = phys_of(l->type); fs.filt[f].op = (uint8_t)op; fs.filt[f].lit = (long long)r->lit_lo;
+    }
+    fs_ = fs; fast_ok_ = true;
+    // DENSE mode needs: one key; every SUM either never NULL or validated by a COUNT over the same column
+    dense_possible_ = lay_.nkeys == 1 && cx.conf.agg_dense_keys != 0;
+    for (int j = 0; j < lay_.nacc && dense_possible_; j++) {
+      if (fs_.acc[j].kind == FAST_ACC_ADD && fs_.acc[j].vbit != 0xFF) {
+        bool ok = false;
+        for (int i = 0; i < lay_.nacc; i++) ok |= i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col;
+        dense_possible_ = ok;
+      }
+    }
+    if (dense_possible_) {
+      for (size_t c = 0; c < emit_.size(); c++) {
+        dmap_.word[c] = 0; dmap_.valid_word[c] = 0xFF;
+        const EmitCol& ec = emit_[c].ec;
+        if (ec.kind == EMIT_KEY) continue;
+        if (ec.kind != EMIT_ACC_VALUE || ec.is_order_key) { dense_possible_ = false; break; }
+        int j = -1; for (int i = 0; i < lay_.nacc; i++) if (fs_.acc[i].word == ec.word) j = i;
+        if (j < 0) { dense_possible_ = false; break; }
+        dmap_.word[c] = (uint8_t)(1 + j);
+        if (ec.vbit != 0xFF) for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) dmap_.valid_word[c] = (uint8_t)(1 + i);
+      }
+    }
+  }
+
+  // decide DENSE mode from the key range of (a sample of) the first batch
+  void decide_dense(OpContext& cx, const ColTable& ct, int64_t n) {
+    dense_decided_ = true;
+    if (!fast_ok_ || !dense_possible_ || n == 0) return;
+    const int64_t sample = std::min<int64_t>(n, 1 << 22);
+    DevMemP d = DevMem::alloc(24, cx.stream);
+    const long long init[3] = {INT64_MAX, INT64_MIN, 0};
+    B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 24, cudaMemcpyHostToDevice, cx.stream));
+    cx.m.launches += launch_key_range(ct.col[fs_.key_col[0]], fs_.key_phys[0], sample, (long long*)d->ptr, cx.stream);
+    long long h[3];
+    B200Q_CUDA(cudaMemcpyAsync(h, d->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    if (h[2] <= 0 || h[1] < h[0]) return;
+    const unsigned __int128 range = (unsigned __int128)((__int128)h[1] - (__int128)h[0]) + 1;
+    const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(h[2], cx.conf.agg_initial_groups), 1 << 16);
+    if (range > budget || range > ((uint64_t)1 << 26)) return;          // sparse keys: stay on the hash table
+    const uint64_t r = (uint64_t)range, margin = r / 8 + 64;
+    fs_.dense_base = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
+    fs_.dense_cap = r + 2 * margin;
+    dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * 32, cx.stream, true);
+    fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;
+    fs_.dense = 1;
+  }
+
+  int launch_update(OpContext& cx, const ColTable& ct, const AggTable& t, int64_t begin, int64_t m, const uint32_t* list) {
+    if (fast_ok_) { cx.m.fast_launches++; return launch_agg_fast_update(ct, fs_, lay_, t, begin, m, list, cx.stream); }
+    return launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, m, list, cx.stream);
   }
 
   void alloc_table(OpContext& cx, uint64_t cap, DevMemP& slots, DevMemP& counters) {
@@ -429,7 +548,7 @@ class AggStage : public Stage {
         deferred_[1] = DevMem::alloc((size_t)m * 4, cx.stream);
       }
       B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-      cx.m.launches += launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, table_view(0), begin, m, nullptr, cx.stream);
+      cx.m.launches += launch_update(cx, ct, table_view(0), begin, m, nullptr);
       B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
       B200Q_CUDA(cudaGetLastError());
       unsigned long long h[3];
@@ -443,7 +562,7 @@ class AggStage : public Stage {
         B200Q_CUDA(cudaMemsetAsync((uint8_t*)counters_->ptr + 8, 0, 8, cx.stream));
         // counters_ is new after grow(): ngroups was recounted by the rehash, deferred/err start at 0
         AggTable t = table_view(cur ^ 1);
-        cx.m.launches += launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, (int64_t)ndef, (const uint32_t*)deferred_[cur]->ptr, cx.stream);
+        cx.m.launches += launch_update(cx, ct, t, begin, (int64_t)ndef, (const uint32_t*)deferred_[cur]->ptr);
         B200Q_CUDA(cudaGetLastError());
         cur ^= 1;
         read_counters(cx, h);
@@ -461,6 +580,7 @@ class AggStage : public Stage {
       const int c = cp_.used_cols[i];
       ct.col[i] = dev_col_of(c < n_in_ ? in.cols[c] : state_cols[c - n_in_]);
     }
+    if (!dense_decided_) decide_dense(cx, ct, n);
     update_rows(cx, ct, n);
   }
 
@@ -491,7 +611,16 @@ class AggStage : public Stage {
   void finish(OpContext& cx, std::vector<DevBatch>& outs) override {
     unsigned long long h[3];
     read_counters(cx, h);
-    const int64_t g = ngroups_;
+    int64_t g = ngroups_;
+    if (fs_.dense) {
+      DevMemP dc = DevMem::alloc(8, cx.stream, true);
+      cx.m.launches += launch_dense_count(fs_.dense_tab, fs_.dense_cap, (unsigned long long*)dc->ptr, cx.stream);
+      unsigned long long hc = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&hc, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      g += (int64_t)hc;
+      cx.m.num_groups = g;
+    }
     if (g == 0) return;                                             // no records (agg_table.rs:154-156)
     EmitTable et{}; et.ncols = (int)emit_.size();
     if (et.ncols > EMIT_MAX_COLS) throw ExecError(B200Q_ERR_UNSUPPORTED, "too many output columns");
@@ -508,6 +637,7 @@ class AggStage : public Stage {
     }
     DevMemP out_count = DevMem::alloc(8, cx.stream, true);
     cx.m.launches += launch_agg_emit(lay_, table_view(0), et, (unsigned long long*)out_count->ptr, cx.stream);
+    if (fs_.dense) cx.m.launches += launch_agg_emit_dense(fs_, et, dmap_, (unsigned long long*)out_count->ptr, cx.stream);
     for (size_t i = 0; i < emit_.size(); i++) {
       if (valid_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)valid_bytes[i]->ptr, (uint32_t*)ob.cols[i].validity->ptr, g, cx.stream);
       if (bool_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)bool_bytes[i]->ptr, (uint32_t*)ob.cols[i].values->ptr, g, cx.stream);

@@ -130,6 +130,8 @@ typedef struct b200q_conf {
                                          (GPU-to-GPU exchange) instead of the reference's Binary
                                          frozen-row column `#9223372036854775807`                 */
   int32_t force_generic_kernels;      /* 1: disable the specialised fast kernels (testing)        */
+  int32_t agg_dense_keys;             /* 1 (default): single integer keys spanning a small range
+                                         are direct-indexed (no probe); 0: always hash           */
 } b200q_conf;
 
 typedef struct b200q_metrics {

@@ -141,3 +141,70 @@ def test_f64_and_decimal_sums():
              ("mnd", E.AGG_MIN, [E.Column("d")], T.decimal128(17, 2)), ("mxd", E.AGG_MAX, [E.Column("d")], T.decimal128(17, 2)),
              ("c", E.AGG_COUNT, [E.Column("x")], T.int64)]
     run_partial_final(rb, ["k"], specs, float_cols=(1, 2))
+
+
+MODES = {"fast+dense": {}, "fast-hash": {"agg_dense_keys": 0}, "generic": {"force_generic_kernels": 1}}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("n,card,nf,knf,lo", [(1, 1, 0, 0, 0), (4099, 17, 0.3, 0.2, -5), (400_000, 100_000, 0.0, 0.0, 10**12), (300_000, 2**45, 0.1, 0.01, 0)])
+def test_fast_paths_sum_count(mode, n, card, nf, knf, lo):
+    """the specialised kernels (lane-paired REDs, dense direct indexing) vs the generic VM kernel vs the oracle"""
+    rng = np.random.default_rng(50)
+    k = rng.integers(lo, lo + card, n, dtype=np.int64)
+    v = rng.integers(-10**6, 10**6, n, dtype=np.int64)
+    rb = rb_from_cols(["k", "v"], [with_nulls(rng, k, knf), with_nulls(rng, v, nf)])
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64)]
+    conf = native.default_conf(staging_rows=0, **MODES[mode])
+    got, plan = run_partial_final(rb, ["k"], specs, batch_rows=150_000, conf=conf)
+    m = plan.last_metrics
+    if mode == "generic":
+        assert m["fast_path_launches"] == 0
+    else:
+        assert m["fast_path_launches"] > 0
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_fast_paths_filters_two_keys_small_ints(mode):
+    n = 200_000
+    rng = np.random.default_rng(51)
+    d = pa.array(rng.integers(0, 3000, n, dtype=np.int32), pa.int32()).cast(pa.date32())
+    k1 = rng.integers(0, 300, n).astype(np.int16)
+    k2 = rng.integers(-3, 3, n).astype(np.int8)
+    v = rng.integers(-1000, 1000, n).astype(np.int32)
+    rb = rb_from_cols(["d", "k1", "k2", "v"], [d, with_nulls(rng, k1, 0.02, pa.int16()), pa.array(k2), with_nulls(rng, v, 0.1, pa.int32())])
+    batches = split_batches(rb, 10000)
+    leaf = PL.MemoryExec.from_arrow(batches, rb.schema)
+    ins = leaf.schema()
+    preds = [E.BinaryExpr(E.Column("d"), "GtEq", E.Literal(1000, T.date32)), E.BinaryExpr(E.Literal(2000, T.date32), "Gt", E.Column("d")),
+             E.BinaryExpr(E.Column("k2"), "NotEq", E.Literal(0, T.int8))]
+    groupings = [E.GroupingExpr("k1", E.Column("k1")), E.GroupingExpr("k2", E.Column("k2"))]
+    aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], ins, T.int64)),
+            E.AggExpr("n", E.PARTIAL, PL.create_agg(E.AGG_COUNT, [E.Literal(1, T.int64)], ins, T.int64))]
+    plan = PL.AggExec(PL.HashAgg, groupings, aggs, True, PL.FilterExec(preds, leaf))
+    got = PL.collect(plan, native.default_conf(**MODES[mode]))
+    exp = O.AggExec(E.HASH_AGG, groupings, aggs, False, ins).execute(O.FilterExec(preds, ins).execute(oracle_batches(batches)))
+    assert_multiset_equal(got, exp)
+    assert (plan.last_metrics["fast_path_launches"] > 0) == (mode != "generic")
+
+
+def test_large_batch_against_c_port():
+    """64M rows (BASELINE M1 shape, one device-sized host batch): compared with the C restatement of the reference
+    algorithm (oracle/cpu_ref.c) + a checksum-of-checksums property independent of any oracle"""
+    from oracle import cpu_ref
+    n = 1 << 26
+    rng = np.random.default_rng(52)
+    k = rng.integers(0, 1 << 20, n, dtype=np.int64)
+    v = rng.integers(-10**6, 10**6, n, dtype=np.int64)
+    rb = rb_from_cols(["k", "v"], [pa.array(k), pa.array(v)])
+    leaf = PL.MemoryExec.from_arrow([rb], rb.schema)
+    ins = leaf.schema()
+    g = [E.GroupingExpr("k", E.Column("k"))]
+    mk = lambda mode, ch: [E.AggExpr("s", mode, PL.create_agg(E.AGG_SUM, ch, ins, T.int64)), E.AggExpr("c", mode, PL.create_agg(E.AGG_COUNT, ch, ins, T.int64))]
+    final = PL.AggExec(PL.HashAgg, g, mk(E.FINAL, [E.placeholder(T.int64)]), False, PL.AggExec(PL.HashAgg, g, mk(E.PARTIAL, [E.Column("v")]), False, leaf))
+    t = pa.Table.from_batches(PL.collect(final, native.default_conf(staging_rows=0, batch_size=1 << 20)))
+    gk, gs, gc = t["k"].to_numpy(), t["s"].to_numpy(), t["c"].to_numpy()
+    assert int(gc.sum()) == n and int(gs.sum()) == int(v.sum()) and len(np.unique(gk)) == len(gk)
+    ref = cpu_ref.hashagg_sum_count(k, v, nthreads=8, max_groups=1 << 21)
+    order_g, order_r = np.argsort(gk), np.argsort(ref["k"])
+    assert np.array_equal(gk[order_g], ref["k"][order_r]) and np.array_equal(gs[order_g], ref["sum"][order_r]) and np.array_equal(gc[order_g], ref["count"][order_r])
