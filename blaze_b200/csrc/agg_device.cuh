@@ -24,10 +24,10 @@ __device__ __forceinline__ ulonglong2 ld_relaxed_v2u64(const unsigned long long*
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-__device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.relaxed.gpu.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ void slot_mark(unsigned long long* slot, unsigned fla
 // the row must be deferred.  *flags = the slot's flags word as last seen (may be stale: only used to skip
 // redundant validity marking).  `s` = first slot index to probe.
 __device__ __forceinline__ unsigned long long* agg_find_or_insert(const AggLayout& lay, const AggTable& tab, const uint64_t* kw, uint32_t knull,
-                                                                   uint64_t h, unsigned* flags_out) {
+                                                                   uint64_t h, unsigned* flags_out, bool* inserted) {
   const unsigned tag = (unsigned)(h >> 32) | 0x80000000u;
   uint64_t s = h & tab.mask;
   while (true) {
@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned long long* agg_find_or_insert(const AggLayou
         ((unsigned*)slot)[1] = flags;
         __threadfence();
         st_release_u32((unsigned*)slot, tag);
-        atomicAdd(tab.counters, 1ULL);
+        *inserted = true;            // the caller adds to tab.counters[0] (warp-aggregated where it can)
         *flags_out = flags;
         return slot;
       }

@@ -213,8 +213,10 @@ __device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable&
   uint32_t knull;
   const uint64_t h = hash_keys(lay, buf, vb, knull, kw);
   unsigned flags;
-  unsigned long long* slot = agg_find_or_insert(lay, tab, kw, knull, h, &flags);
+  bool inserted = false;
+  unsigned long long* slot = agg_find_or_insert(lay, tab, kw, knull, h, &flags, &inserted);
   if (!slot) return false;
+  if (inserted) atomicAdd(tab.counters, 1ULL);
   // accumulate (K6 / K7)
   for (int j = 0; j < lay.nacc; j++) {
     const AccOp a = lay.acc[j];

@@ -52,125 +52,224 @@ __device__ __forceinline__ bool cmp_apply(int op, long long a, long long b) {
   switch (op) { case CMP_EQ: return a == b; case CMP_NE: return a != b; case CMP_LT: return a < b; case CMP_LE: return a <= b; case CMP_GT: return a > b; default: return a >= b; }
 }
 
-template <int NACC, bool DENSE>
-__global__ void __launch_bounds__(FA_BLOCK) agg_fast_update_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
-                                                                   long long row_begin, long long n, const uint32_t* __restrict__ row_list) {
-  const unsigned lane = threadIdx.x & 31;
+// One warp handles 32 consecutive rows per unit.  A gang of G adjacent lanes owns G consecutive rows; EVERY lane of
+// the gang loads the gang's G keys itself (the G lanes read the same addresses, which the LSU serves as one
+// access), computes the G slot addresses redundantly, and then in step s = 0..G-1 the gang's lanes update
+// the different accumulator words of row s with ONE red.add.u64 instruction => one 32-byte sector operation
+// per row, no shuffles, no per-thread arrays with dynamic indices.
+//   DENSE : G = 4, lane m updates word m of {rows, acc0, acc1} of the direct-indexed entry
+//   hashed: G = 2 (two accumulators: lane 0 -> acc0, lane 1 -> acc1) or G = 1 (one accumulator)
+template <int NK, int NACC, bool DENSE>
+__global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                   long long row_begin, long long n) {
+  constexpr int G = DENSE ? 4 : (NACC == 2 ? 2 : 1);
+  constexpr int UNITS = FA_R;                                   // units of 32 rows per warp per tile
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = lane % G, gl = lane - m;                   // my word index inside the gang, first lane of my gang
   const long long ntiles = (n + FA_TILE - 1) / FA_TILE;
+  // which accumulator (if any) this lane updates, and through which column
+  const int my_acc = DENSE ? (int)m - 1 : (int)m;               // DENSE: lane 0 counts rows
+  const bool has_acc = my_acc >= 0 && my_acc < NACC;
+  const int acc_col = has_acc ? fs.acc[my_acc].col : -1;
+  const int acc_kind = has_acc ? fs.acc[my_acc].kind : FAST_ACC_COUNT;
+  const int acc_phys = has_acc ? fs.acc[my_acc].phys : PH_I64;
+  const int acc_word = has_acc ? fs.acc[my_acc].word : 0;
+  const int acc_vbit = has_acc ? fs.acc[my_acc].vbit : 0xFF;
+
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    bool alive[FA_R]; uint32_t rel[FA_R]; long long row[FA_R];
-    long long key[2][FA_R]; uint32_t knull[FA_R];
-    unsigned long long aval[2][FA_R]; bool aact[2][FA_R];
-    // ---- stream the columns: all loads of the tile are issued before any dependent work
 #pragma unroll
-    for (int r = 0; r < FA_R; r++) {
-      const long long i = tile * FA_TILE + r * FA_BLOCK + threadIdx.x;
-      alive[r] = i < n;
-      rel[r] = alive[r] ? (row_list ? row_list[i] : (uint32_t)i) : 0;
-      row[r] = row_begin + rel[r];
-    }
+    for (int u = 0; u < UNITS; u++) {
+      const long long rel0 = tile * FA_TILE + (long long)(u * (FA_BLOCK / 32) + warp) * 32 + gl;   // first row of my gang (relative)
+      long long key0[G], key1[G]; bool alive[G]; unsigned knull[G];
+      unsigned long long val[G]; bool act[G];
+      // ---- loads (independent, issued back to back)
 #pragma unroll
-    for (int r = 0; r < FA_R; r++) {
-      knull[r] = 0;
-      for (int k = 0; k < fs.nkeys; k++) {
-        key[k][r] = 0;
-        if (alive[r]) {
-          const DevCol& c = cols.col[fs.key_col[k]];
-          if (col_valid(c, row[r])) key[k][r] = col_load_int(c, fs.key_phys[k], row[r]); else knull[r] |= 1u << k;
+      for (int s = 0; s < G; s++) {
+        const long long rel = rel0 + s, row = row_begin + rel;
+        alive[s] = rel < n; knull[s] = 0; key0[s] = 0; key1[s] = 0; val[s] = (DENSE && m == 3) ? 0 : 1; act[s] = alive[s];
+        if (!alive[s]) continue;
+        { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) key0[s] = col_load_int(c, fs.key_phys[0], row); else knull[s] |= 1u; }
+        if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) key1[s] = col_load_int(c, fs.key_phys[1], row); else knull[s] |= 2u; }
+        if (has_acc && acc_col >= 0) {
+          const DevCol& c = cols.col[acc_col];
+          act[s] = col_valid(c, row);
+          if (acc_kind == FAST_ACC_ADD) val[s] = act[s] ? (unsigned long long)col_load_int(c, acc_phys, row) : 0ULL;
+        }
+      }
+      // ---- fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
+      for (int f = 0; f < fs.nfilt; f++) {
+        const DevCol& c = cols.col[fs.filt[f].col];
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+          const long long row = row_begin + rel0 + s;
+          if (alive[s]) alive[s] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
+        }
+      }
+      // ---- slot of every row of the gang (computed redundantly by each lane of the gang)
+      unsigned long long* ptr[G];          // word this lane updates for row s (nullptr: nothing to do)
+      unsigned long long* slot[G]; unsigned flags[G]; bool miss[G]; uint64_t h[G];
+      ulonglong2 hk[G];
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; miss[s] = false; h[s] = 0;
+        if (!alive[s]) continue;
+        if (DENSE) {
+          const unsigned long long idx = (unsigned long long)(key0[s] - fs.dense_base);
+          if (knull[s] == 0 && idx < fs.dense_cap) { ptr[s] = fs.dense_tab + idx * 4 + m; continue; }
+        }
+        uint64_t hh = mix64(AGG_HASH_SEED ^ (uint64_t)key0[s]);
+        if (NK == 2) hh = mix64(hh ^ (uint64_t)key1[s]);
+        h[s] = mix64(hh ^ knull[s]);
+        slot[s] = tab.slots + (h[s] & tab.mask) * (uint64_t)lay.slot_words;
+        hk[s] = ld_relaxed_v2u64(slot[s]);                                     // {hdr, key0}: one 16-byte probe per row
+        miss[s] = true;
+      }
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        if (!miss[s]) continue;
+        const unsigned tag = (unsigned)(h[s] >> 32) | 0x80000000u;
+        flags[s] = (unsigned)(hk[s].x >> 32);
+        bool hit = (unsigned)hk[s].x == tag && (flags[s] >> 16) == knull[s] && hk[s].y == (uint64_t)key0[s];
+        if (hit && NK == 2) hit = ld_relaxed_u64(slot[s] + 2) == (uint64_t)key1[s];
+        miss[s] = !hit;
+      }
+      // ---- first probe missed somewhere in the warp: lane 0 of the gang runs the full protocol, then broadcasts
+      bool any_miss = false;
+#pragma unroll
+      for (int s = 0; s < G; s++) any_miss |= miss[s];
+      if (__any_sync(0xffffffffu, any_miss)) {
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+          unsigned long long sp = (unsigned long long)slot[s]; unsigned fl = flags[s]; bool ins = false;
+          if (miss[s] && m == 0) {
+            uint64_t kw[2] = {(uint64_t)key0[s], (uint64_t)key1[s]};
+            unsigned long long* p = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &ins);
+            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + s); }
+            sp = (unsigned long long)p;
+          }
+          { const unsigned b = __ballot_sync(0xffffffffu, ins); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }   // one counter update per warp step
+          if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
+          if (miss[s]) { slot[s] = (unsigned long long*)sp; flags[s] = fl; if (!sp) alive[s] = false; }
         }
       }
 #pragma unroll
-      for (int j = 0; j < NACC; j++) {
-        aval[j][r] = 1; aact[j][r] = alive[r];
-        if (alive[r] && fs.acc[j].col >= 0) {
-          const DevCol& c = cols.col[fs.acc[j].col];
-          const bool v = col_valid(c, row[r]);
-          aact[j][r] = v;
-          if (fs.acc[j].kind == FAST_ACC_ADD) aval[j][r] = v ? (unsigned long long)col_load_int(c, fs.acc[j].phys, row[r]) : 0ULL;
-        }
+      for (int s = 0; s < G; s++)
+        if (alive[s] && slot[s] && has_acc) ptr[s] = slot[s] + acc_word;        // hashed row: this lane's accumulator word
+      // ---- accumulate: step s updates row s; the gang's lanes hit adjacent words of ONE sector in ONE instruction.
+      // The RED is issued UNCONDITIONALLY: a predicated red is if-converted by ptxas into `@P ATOMG ... RZ`
+      // (an atomic WITH a return path, measured 4.5x slower per sector than REDG); lanes with nothing to add
+      // target this warp's private sink sector with the value 0 instead.
+      unsigned long long* const sink = fs.sink + (((blockIdx.x * (FA_BLOCK / 32) + warp) & (FAST_SINK_WARPS - 1)) << 2) + (m & 3);
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        const bool pred = alive[s] && ptr[s] != nullptr;
+        red_add_u64(pred ? ptr[s] : sink, (pred && act[s]) ? val[s] : 0ULL);
+        if (pred && act[s] && slot[s]) slot_mark(slot[s], flags[s], acc_vbit);
       }
     }
-    // ---- fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
-    for (int f = 0; f < fs.nfilt; f++) {
-      const DevCol& c = cols.col[fs.filt[f].col];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LEAN dense kernel: the hot loop of the M1 shape with everything resolved at compile time.
+// Preconditions (checked on the host per launch): one int64 key column, accumulator/filter columns int64,
+// none of them carries a validity bitmap, all base pointers 32-byte aligned, row_begin % 4 == 0.
+// Per 32 rows a warp issues: 1 (+1) 256-bit streaming loads and 4 REDG — about 2 instructions per row.
+// ---------------------------------------------------------------------------------------------------
+struct i64x4 { long long v[4]; };
+__device__ __forceinline__ i64x4 ld_stream_v4(const long long* p) {
+  i64x4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ i64x4 ld_guarded4(const long long* p, long long rel0, long long n, long long fill) {
+  i64x4 r;
 #pragma unroll
-      for (int r = 0; r < FA_R; r++)
-        if (alive[r]) alive[r] = col_valid(c, row[r]) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row[r]), fs.filt[f].lit);
-    }
-    // ---- locate the slot of every row
-    unsigned long long* slot[FA_R]; unsigned flags[FA_R]; bool dense[FA_R];
-    unsigned long long* cand[FA_R]; ulonglong2 hk[FA_R]; uint64_t h[FA_R];
+  for (int s = 0; s < 4; s++) r.v[s] = rel0 + s < n ? __ldg(p + rel0 + s) : fill;
+  return r;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                  long long row_begin, long long n) {
+  constexpr int U = 2;                                          // units (32 rows) in flight per warp
+  const unsigned lane = threadIdx.x & 31, m = lane & 3, gl = lane & ~3u;
+  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const long long nunits = (n + 31) / 32;
+  const long long* kcol = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
+  // operand of the word this lane owns: word 0 = row counter (+1), word 1/2 = acc0/acc1, word 3 = padding (+0)
+  const int my_acc = (int)m - 1;
+  const bool has_acc = my_acc >= 0 && my_acc < NACC;
+  const bool is_add = has_acc && fs.acc[has_acc ? my_acc : 0].kind == FAST_ACC_ADD;
+  const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[my_acc].col].values + row_begin : nullptr;
+  const long long cst = (m == 0 || has_acc) ? 1 : 0;
+  unsigned long long* const sink = fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + m;
+  const long long base = fs.dense_base; const unsigned long long cap = fs.dense_cap;
+  unsigned long long* const dtab = fs.dense_tab + m;
+
+  for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
+    i64x4 k[U], v[U]; bool alive[U][4];
 #pragma unroll
-    for (int r = 0; r < FA_R; r++) {
-      slot[r] = nullptr; flags[r] = 0; dense[r] = false; cand[r] = nullptr;
-      if (!alive[r]) continue;
-      if (DENSE) {
-        const unsigned long long idx = (unsigned long long)(key[0][r] - fs.dense_base);
-        if (knull[r] == 0 && idx < fs.dense_cap) { dense[r] = true; slot[r] = fs.dense_tab + idx * 4; continue; }
+    for (int u = 0; u < U; u++) {
+      const long long rel0 = (unit0 + u) * 32 + gl;
+      if (rel0 + 4 <= n) {
+        k[u] = ld_stream_v4(kcol + rel0);
+        if (is_add) v[u] = ld_stream_v4(vcol + rel0); else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = cst; }
+      } else {
+        k[u] = ld_guarded4(kcol, rel0, n, 0);
+        if (is_add) v[u] = ld_guarded4(vcol, rel0, n, 0); else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = cst; }
       }
-      uint64_t kw[2] = {(uint64_t)key[0][r], (uint64_t)key[1][r]};
-      h[r] = agg_hash_words(kw, fs.nkeys, knull[r]);
-      cand[r] = tab.slots + (h[r] & tab.mask) * (uint64_t)lay.slot_words;
-      hk[r] = ld_relaxed_v2u64(cand[r]);                                         // {hdr, key0}: one 16-byte probe
-    }
 #pragma unroll
-    for (int r = 0; r < FA_R; r++) {
-      if (!alive[r] || dense[r]) continue;
-      const unsigned tag = (unsigned)(h[r] >> 32) | 0x80000000u;
-      const unsigned fl = (unsigned)(hk[r].x >> 32);
-      bool hit = (unsigned)hk[r].x == tag && (fl >> 16) == knull[r] && hk[r].y == (uint64_t)key[0][r];
-      if (hit && fs.nkeys == 2) hit = ld_relaxed_u64(cand[r] + 2) == (uint64_t)key[1][r];
-      if (hit) { slot[r] = cand[r]; flags[r] = fl; continue; }
-      uint64_t kw[2] = {(uint64_t)key[0][r], (uint64_t)key[1][r]};               // first probe missed: full protocol (insert / walk)
-      slot[r] = agg_find_or_insert(lay, tab, kw, knull[r], h[r], &flags[r]);
-      if (!slot[r]) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = rel[r]; alive[r] = false; }
+      for (int s = 0; s < 4; s++) alive[u][s] = rel0 + s < n;
     }
-    // ---- accumulate: every lane reaches this point (warp-converged) so lanes can update each other's rows
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
+      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
 #pragma unroll
-    for (int r = 0; r < FA_R; r++) {
-      const bool live = alive[r] && slot[r] != nullptr;
-      if (DENSE) {
-        // gang of 4 lanes: in step s the 4 lanes update words {rows, acc0, acc1} of the row owned by gang lane s
-        const unsigned m = lane & 3, gbase = lane & ~3u;
+      for (int u = 0; u < U; u++) {
+        const long long rel0 = (unit0 + u) * 32 + gl;
+        const i64x4 x = rel0 + 4 <= n ? ld_stream_v4(fcol + rel0) : ld_guarded4(fcol, rel0, n, 0);
+#pragma unroll
+        for (int s = 0; s < 4; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
+      }
+    }
+    bool oor = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
+        const bool in = alive[u][s] && idx < cap;
+        oor |= alive[u][s] && !in;
+        red_add_u64(in ? dtab + idx * 4 : sink, in ? (unsigned long long)v[u].v[s] : 0ULL);    // 4 lanes -> 1 sector
+      }
+    }
+    // keys outside the dense range (rare): lane 0 of the gang routes the row through the hash table
+    if (__any_sync(0xffffffffu, oor)) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-          const unsigned src = gbase + s;
-          const unsigned long long ps = __shfl_sync(0xffffffffu, (unsigned long long)slot[r], src);
-          const bool pd = __shfl_sync(0xffffffffu, (int)(live && dense[r]), src);
-          const unsigned long long v0 = __shfl_sync(0xffffffffu, aval[0][r], src);
-          const bool a0 = __shfl_sync(0xffffffffu, (int)aact[0][r], src);
-          unsigned long long v1 = 1; bool a1 = false;
-          if (NACC == 2) { v1 = __shfl_sync(0xffffffffu, aval[1][r], src); a1 = __shfl_sync(0xffffffffu, (int)aact[1][r], src); }
-          // one predicated RED instruction for the whole gang: the 3 words of a row share a 32-byte sector
-          const unsigned long long val = m == 0 ? 1ULL : (m == 1 ? v0 : v1);
-          const bool pred = pd && (m == 0 || (m == 1 && a0) || (m == 2 && NACC == 2 && a1));
-          if (pred) red_add_u64((unsigned long long*)ps + m, val);
+          const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
+          bool inserted = false;
+          if (alive[u][s] && idx >= cap && m == 0) {
+            const long long rel = (unit0 + u) * 32 + gl + s;
+            uint64_t kw[2] = {(uint64_t)k[u].v[s], 0};
+            unsigned fl;
+            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, agg_hash_words(kw, 1, 0), &fl, &inserted);
+            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
+            else {
+#pragma unroll
+              for (int j = 0; j < NACC; j++) {
+                const unsigned long long x = fs.acc[j].kind == FAST_ACC_ADD ? (unsigned long long)__ldg((const long long*)cols.col[fs.acc[j].col].values + row_begin + rel) : 1ULL;
+                atomicAdd(p + fs.acc[j].word, x);
+                slot_mark(p, fl, fs.acc[j].vbit);
+              }
+            }
+          }
+          const unsigned b = __ballot_sync(0xffffffffu, inserted);
+          if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
         }
-      }
-      const bool hashed = live && !dense[r];
-      if (NACC == 2) {
-        // lane pairing: the owner updates acc0, its neighbour updates acc1 of the same row in the same instruction
-        const int w0 = fs.acc[0].word, w1 = fs.acc[1].word;
-        const unsigned long long ps = __shfl_xor_sync(0xffffffffu, (unsigned long long)slot[r], 1);
-        const bool ph = __shfl_xor_sync(0xffffffffu, (int)hashed, 1);
-        const unsigned long long pv1 = __shfl_xor_sync(0xffffffffu, aval[1][r], 1);
-        const bool pa1 = __shfl_xor_sync(0xffffffffu, (int)aact[1][r], 1);
-        const bool odd = lane & 1;
-        {   // step 1: rows owned by even lanes (one predicated RED: both words sit in the same 32-byte sector)
-          unsigned long long* ptr = odd ? (unsigned long long*)ps + w1 : slot[r] + w0;
-          const unsigned long long val = odd ? pv1 : aval[0][r];
-          const bool pred = odd ? (ph && pa1) : (hashed && aact[0][r]);
-          if (pred) red_add_u64(ptr, val);
-        }
-        {   // step 2: rows owned by odd lanes
-          unsigned long long* ptr = odd ? slot[r] + w0 : (unsigned long long*)ps + w1;
-          const unsigned long long val = odd ? aval[0][r] : pv1;
-          const bool pred = odd ? (hashed && aact[0][r]) : (ph && pa1);
-          if (pred) red_add_u64(ptr, val);
-        }
-        if (hashed) { if (aact[0][r]) slot_mark(slot[r], flags[r], fs.acc[0].vbit); if (aact[1][r]) slot_mark(slot[r], flags[r], fs.acc[1].vbit); }
-      } else {
-        if (hashed && aact[0][r]) { red_add_u64(slot[r] + fs.acc[0].word, aval[0][r]); slot_mark(slot[r], flags[r], fs.acc[0].vbit); }
       }
     }
   }
@@ -182,16 +281,25 @@ static int fast_grid(int64_t ntiles) {
   return (int)(ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap);
 }
 
-int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n,
-                           const uint32_t* d_row_list, cudaStream_t s) {
+template <int NK, int NACC>
+static void launch_gang(bool dense, int grid, cudaStream_t s, const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n) {
+  if (dense) agg_gang_update_kernel<NK, NACC, true><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+  else agg_gang_update_kernel<NK, NACC, false><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+}
+
+int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
   const int64_t ntiles = (n + FA_TILE - 1) / FA_TILE;
   const int grid = fast_grid(ntiles);
   const bool dense = fs.dense != 0;
-  if (fs.nacc == 2) { if (dense) agg_fast_update_kernel<2, true><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n, d_row_list);
-                      else agg_fast_update_kernel<2, false><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n, d_row_list); }
-  else { if (dense) agg_fast_update_kernel<1, true><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n, d_row_list);
-         else agg_fast_update_kernel<1, false><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n, d_row_list); }
+  if (dense && fs.lean) {
+    const int g = fast_grid((n + 32 * 8 * 2 - 1) / (32 * 8 * 2));
+    if (fs.nacc == 2) agg_lean_dense_kernel<2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+    else agg_lean_dense_kernel<1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+    return 1;
+  }
+  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dense, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dense, grid, s, cols, fs, lay, tab, row_begin, n); }
+  else { if (fs.nacc == 2) launch_gang<2, 2>(false, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(false, grid, s, cols, fs, lay, tab, row_begin, n); }
   return 1;
 }
 

@@ -8,19 +8,21 @@ enum FastAccKind : uint8_t { FAST_ACC_ADD = 0, FAST_ACC_COUNT = 1 };   // COUNT 
 
 struct FastSpec {
   int32_t nkeys, nacc, nfilt, dense;
+  int32_t lean, _pad0;                                    // lean: all referenced columns are aligned non-null int64 (set per launch)
   int8_t key_col[2]; uint8_t key_phys[2];                 // program column slots / physical kinds of the key columns
   struct { uint8_t kind; int8_t col; uint8_t phys; uint8_t vbit; uint8_t word; uint8_t _pad[3]; } acc[2];
   struct { int8_t col; uint8_t phys; uint8_t op; uint8_t _pad[5]; long long lit; } filt[4];
   long long dense_base;                                   // DENSE: slot index = key - dense_base
   unsigned long long dense_cap;                           // entries of 4 words {rows, acc0, acc1, -}
   unsigned long long* dense_tab;
+  unsigned long long* sink;                               // FAST_SINK_WARPS x 4 words: per-warp scratch sector for no-op REDs
 };
+constexpr int FAST_SINK_WARPS = 4096;
 
 // per emit column: which dense word holds the value and which (count) word validates it
 struct DenseEmitMap { uint8_t word[EMIT_MAX_COLS]; uint8_t valid_word[EMIT_MAX_COLS]; };
 
-int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n,
-                           const uint32_t* d_row_list, cudaStream_t s);
+int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
 int launch_key_range(const DevCol& col, int phys, int64_t n, long long* d_out, cudaStream_t s);
 int launch_agg_emit_dense(const FastSpec& fs, const EmitTable& emit, const DenseEmitMap& map, unsigned long long* d_out_count, cudaStream_t s);
 int launch_dense_count(const unsigned long long* tab, uint64_t cap, unsigned long long* d_out, cudaStream_t s);

@@ -189,7 +189,7 @@ class AggStage : public Stage {
   bool fast_ok_ = false, dense_possible_ = false, dense_decided_ = false;
   FastSpec fs_{};
   DenseEmitMap dmap_{};
-  DevMemP dense_tab_;
+  DevMemP dense_tab_, sink_;
 
   // emit plan (per output/state column)
   struct EmitSpec { EmitCol ec; FieldDef field; bool frozen_count = false; };
@@ -437,6 +437,8 @@ class AggStage : public Stage {
       const int s = prog_col_slot(l->col_index); if (s < 0 || s > 127) return;
       fs.filt[f].col = (int8_t)s; fs.filt[f].phys = phys_of(l->type); fs.filt[f].op = (uint8_t)op; fs.filt[f].lit = (long long)r->lit_lo;
     }
+    sink_ = DevMem::alloc((size_t)FAST_SINK_WARPS * 32, cx.stream, true);
+    fs.sink = (unsigned long long*)sink_->ptr;
     fs_ = fs; fast_ok_ = true;
     // DENSE mode needs: one key; every SUM either never NULL or validated by a COUNT over the same column
     dense_possible_ = lay_.nkeys == 1 && cx.conf.agg_dense_keys != 0;
@@ -485,8 +487,31 @@ class AggStage : public Stage {
     fs_.dense = 1;
   }
 
+  // LEAN kernels: every referenced column is a non-null, 32-byte aligned int64 column
+  bool lean_ok(const ColTable& ct, int64_t begin) const {
+    if (begin % 4) return false;
+    auto ok = [&](int slot, uint8_t phys) {
+      const DevCol& c = ct.col[slot];
+      return phys == PH_I64 && c.validity == nullptr && ((uintptr_t)c.values & 31) == 0;
+    };
+    for (int k = 0; k < fs_.nkeys; k++) if (!ok(fs_.key_col[k], fs_.key_phys[k])) return false;
+    for (int j = 0; j < fs_.nacc; j++) {
+      if (fs_.acc[j].col < 0) continue;
+      if (fs_.acc[j].kind == FAST_ACC_ADD) { if (!ok(fs_.acc[j].col, fs_.acc[j].phys)) return false; }
+      else if (ct.col[fs_.acc[j].col].validity != nullptr) return false;       // COUNT(col): needs no data, only "no NULLs"
+    }
+    for (int f = 0; f < fs_.nfilt; f++) if (!ok(fs_.filt[f].col, fs_.filt[f].phys)) return false;
+    return true;
+  }
+
   int launch_update(OpContext& cx, const ColTable& ct, const AggTable& t, int64_t begin, int64_t m, const uint32_t* list) {
-    if (fast_ok_) { cx.m.fast_launches++; return launch_agg_fast_update(ct, fs_, lay_, t, begin, m, list, cx.stream); }
+    // deferred-row replays (arbitrary row lists, rare) always take the generic kernel: same table, same semantics
+    if (fast_ok_ && !list) {
+      cx.m.fast_launches++;
+      FastSpec fs = fs_;
+      fs.lean = lean_ok(ct, begin) ? 1 : 0;
+      return launch_agg_fast_update(ct, fs, lay_, t, begin, m, cx.stream);
+    }
     return launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, m, list, cx.stream);
   }
 
