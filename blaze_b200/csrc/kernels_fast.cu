@@ -7,12 +7,21 @@
 // HBM speed (6.5 TB/s) but every row also needs a random read-modify-write into the L2-resident group
 // table, and the chip retires ~1.55e11 scattered 32-byte sector operations per second.  So the design
 // goal is ONE sector operation per row:
-//   - slot = one 32-byte sector {hdr, key, acc0, acc1}: the probe is a single 16-byte load;
-//   - the two accumulators of a row are updated by the SAME `red.add.u64` instruction from two adjacent
-//     lanes (lane pairing), which the memory system coalesces into one sector operation;
-//   - DENSE mode (single integer key whose values span a small range, e.g. TPC-DS surrogate keys):
-//     the slot index is key - base, no probe at all: {rows, acc0, acc1} updated by a gang of 4 lanes in
-//     one instruction.  Keys outside the range (and NULL keys) take the hash path.
+//   - hashed: slot = one 32-byte sector {hdr, key, acc0, acc1}: the probe is a single 16-byte load and the
+//     two accumulators of a row are updated by the SAME red.add.u64 instruction from two adjacent lanes,
+//     which the memory system coalesces into one sector operation;
+//   - DENSE (single integer key whose values span a small range, e.g. TPC-DS surrogate keys): the entry
+//     index is key - base, no probe at all; an entry is 2 or 4 words ({sum,count} / {rows,acc0,acc1,-})
+//     updated by a gang of 2 or 4 lanes in one instruction.  Keys outside the range and NULL keys take
+//     the hash table.
+//
+// Lane organisation ("gang"): G adjacent lanes own G consecutive rows; EVERY lane of the gang loads the
+// gang's G rows itself (the lanes read the same addresses: one access for the LSU), computes the G entry
+// addresses redundantly, and in step s = 0..G-1 the gang's lanes update word 0..G-1 of row s.  No shuffles,
+// no per-thread arrays with dynamic indices.
+//
+// REDs are issued UNCONDITIONALLY: ptxas if-converts a predicated `red` into `@P ATOMG ... RZ` (an atomic
+// with a return path); lanes with nothing to add send +0 to their warp's private sink sector instead.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,8 +31,8 @@
 namespace b200q {
 
 constexpr int FA_BLOCK = 256;
-constexpr int FA_R = 4;                       // rows per thread per tile (independent loads in flight)
-constexpr int FA_TILE = FA_BLOCK * FA_R;
+constexpr int FA_UNITS = 4;                   // 32-row units per warp per tile (generic gang kernel)
+constexpr int FA_TILE = FA_BLOCK * FA_UNITS;
 
 // streaming load: bypass L1 and mark the line evict-first in L2 so the input stream does not push the
 // group table out of L2
@@ -51,42 +60,41 @@ __device__ __forceinline__ long long col_load_int(const DevCol& c, int phys, lon
 __device__ __forceinline__ bool cmp_apply(int op, long long a, long long b) {
   switch (op) { case CMP_EQ: return a == b; case CMP_NE: return a != b; case CMP_LT: return a < b; case CMP_LE: return a <= b; case CMP_GT: return a > b; default: return a >= b; }
 }
+__device__ __forceinline__ unsigned long long* warp_sink(const FastSpec& fs, long long gwarp, unsigned m) {
+  return fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + (m & 3);
+}
 
-// One warp handles 32 consecutive rows per unit.  A gang of G adjacent lanes owns G consecutive rows; EVERY lane of
-// the gang loads the gang's G keys itself (the G lanes read the same addresses, which the LSU serves as one
-// access), computes the G slot addresses redundantly, and then in step s = 0..G-1 the gang's lanes update
-// the different accumulator words of row s with ONE red.add.u64 instruction => one 32-byte sector operation
-// per row, no shuffles, no per-thread arrays with dynamic indices.
-//   DENSE : G = 4, lane m updates word m of {rows, acc0, acc1} of the direct-indexed entry
-//   hashed: G = 2 (two accumulators: lane 0 -> acc0, lane 1 -> acc1) or G = 1 (one accumulator)
-template <int NK, int NACC, bool DENSE>
+// ---------------------------------------------------------------------------------------------------
+// generic gang kernel: any integer widths, validity bitmaps, 1-2 keys; DG = dense gang width (0: no dense table)
+// ---------------------------------------------------------------------------------------------------
+template <int NK, int NACC, int DG>
 __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                    long long row_begin, long long n) {
-  constexpr int G = DENSE ? 4 : (NACC == 2 ? 2 : 1);
-  constexpr int UNITS = FA_R;                                   // units of 32 rows per warp per tile
+  constexpr bool DENSE = DG != 0;
+  constexpr int G = DENSE ? DG : (NACC == 2 ? 2 : 1);
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned m = lane % G, gl = lane - m;                   // my word index inside the gang, first lane of my gang
   const long long ntiles = (n + FA_TILE - 1) / FA_TILE;
-  // which accumulator (if any) this lane updates, and through which column
-  const int my_acc = DENSE ? (int)m - 1 : (int)m;               // DENSE: lane 0 counts rows
-  const bool has_acc = my_acc >= 0 && my_acc < NACC;
-  const int acc_col = has_acc ? fs.acc[my_acc].col : -1;
-  const int acc_kind = has_acc ? fs.acc[my_acc].kind : FAST_ACC_COUNT;
-  const int acc_phys = has_acc ? fs.acc[my_acc].phys : PH_I64;
-  const int acc_word = has_acc ? fs.acc[my_acc].word : 0;
-  const int acc_vbit = has_acc ? fs.acc[my_acc].vbit : 0xFF;
+  // which accumulator (if any) this lane updates: dense entries follow fs.dense_word_src, hashed slots acc m
+  const int src = DENSE ? fs.dense_word_src[m] : (int)m;        // -1: row counter (+1), -2: padding (+0), j: accumulator j
+  const bool has_acc = src >= 0 && src < NACC;
+  const int acc_col = has_acc ? fs.acc[src].col : -1;
+  const int acc_kind = has_acc ? fs.acc[src].kind : FAST_ACC_COUNT;
+  const int acc_phys = has_acc ? fs.acc[src].phys : PH_I64;
+  const int acc_word = has_acc ? fs.acc[src].word : 0;
+  const int acc_vbit = has_acc ? fs.acc[src].vbit : 0xFF;
+  unsigned long long* const sink = warp_sink(fs, (long long)blockIdx.x * (FA_BLOCK / 32) + warp, m);
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll
-    for (int u = 0; u < UNITS; u++) {
+#pragma unroll 1
+    for (int u = 0; u < FA_UNITS; u++) {
       const long long rel0 = tile * FA_TILE + (long long)(u * (FA_BLOCK / 32) + warp) * 32 + gl;   // first row of my gang (relative)
       long long key0[G], key1[G]; bool alive[G]; unsigned knull[G];
       unsigned long long val[G]; bool act[G];
-      // ---- loads (independent, issued back to back)
 #pragma unroll
       for (int s = 0; s < G; s++) {
         const long long rel = rel0 + s, row = row_begin + rel;
-        alive[s] = rel < n; knull[s] = 0; key0[s] = 0; key1[s] = 0; val[s] = (DENSE && m == 3) ? 0 : 1; act[s] = alive[s];
+        alive[s] = rel < n; knull[s] = 0; key0[s] = 0; key1[s] = 0; val[s] = src == -2 ? 0 : 1; act[s] = alive[s];
         if (!alive[s]) continue;
         { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) key0[s] = col_load_int(c, fs.key_phys[0], row); else knull[s] |= 1u; }
         if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) key1[s] = col_load_int(c, fs.key_phys[1], row); else knull[s] |= 2u; }
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
           if (acc_kind == FAST_ACC_ADD) val[s] = act[s] ? (unsigned long long)col_load_int(c, acc_phys, row) : 0ULL;
         }
       }
-      // ---- fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
+      // fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
       for (int f = 0; f < fs.nfilt; f++) {
         const DevCol& c = cols.col[fs.filt[f].col];
 #pragma unroll
@@ -105,17 +113,15 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
           if (alive[s]) alive[s] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
         }
       }
-      // ---- slot of every row of the gang (computed redundantly by each lane of the gang)
-      unsigned long long* ptr[G];          // word this lane updates for row s (nullptr: nothing to do)
-      unsigned long long* slot[G]; unsigned flags[G]; bool miss[G]; uint64_t h[G];
-      ulonglong2 hk[G];
+      // entry / slot of every row of the gang (computed redundantly by each lane of the gang)
+      unsigned long long* ptr[G]; unsigned long long* slot[G]; unsigned flags[G]; bool miss[G]; uint64_t h[G]; ulonglong2 hk[G];
 #pragma unroll
       for (int s = 0; s < G; s++) {
         ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; miss[s] = false; h[s] = 0;
         if (!alive[s]) continue;
         if (DENSE) {
           const unsigned long long idx = (unsigned long long)(key0[s] - fs.dense_base);
-          if (knull[s] == 0 && idx < fs.dense_cap) { ptr[s] = fs.dense_tab + idx * 4 + m; continue; }
+          if (knull[s] == 0 && idx < fs.dense_cap) { ptr[s] = fs.dense_tab + idx * G + m; continue; }
         }
         uint64_t hh = mix64(AGG_HASH_SEED ^ (uint64_t)key0[s]);
         if (NK == 2) hh = mix64(hh ^ (uint64_t)key1[s]);
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
         hk[s] = ld_relaxed_v2u64(slot[s]);                                     // {hdr, key0}: one 16-byte probe per row
         miss[s] = true;
       }
+      bool any_miss = false;
 #pragma unroll
       for (int s = 0; s < G; s++) {
         if (!miss[s]) continue;
@@ -131,12 +138,9 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
         flags[s] = (unsigned)(hk[s].x >> 32);
         bool hit = (unsigned)hk[s].x == tag && (flags[s] >> 16) == knull[s] && hk[s].y == (uint64_t)key0[s];
         if (hit && NK == 2) hit = ld_relaxed_u64(slot[s] + 2) == (uint64_t)key1[s];
-        miss[s] = !hit;
+        miss[s] = !hit; any_miss |= !hit;
       }
-      // ---- first probe missed somewhere in the warp: lane 0 of the gang runs the full protocol, then broadcasts
-      bool any_miss = false;
-#pragma unroll
-      for (int s = 0; s < G; s++) any_miss |= miss[s];
+      // first probe missed somewhere in the warp: lane 0 of the gang runs the full protocol, then broadcasts
       if (__any_sync(0xffffffffu, any_miss)) {
 #pragma unroll
         for (int s = 0; s < G; s++) {
@@ -155,11 +159,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
 #pragma unroll
       for (int s = 0; s < G; s++)
         if (alive[s] && slot[s] && has_acc) ptr[s] = slot[s] + acc_word;        // hashed row: this lane's accumulator word
-      // ---- accumulate: step s updates row s; the gang's lanes hit adjacent words of ONE sector in ONE instruction.
-      // The RED is issued UNCONDITIONALLY: a predicated red is if-converted by ptxas into `@P ATOMG ... RZ`
-      // (an atomic WITH a return path, measured 4.5x slower per sector than REDG); lanes with nothing to add
-      // target this warp's private sink sector with the value 0 instead.
-      unsigned long long* const sink = fs.sink + (((blockIdx.x * (FA_BLOCK / 32) + warp) & (FAST_SINK_WARPS - 1)) << 2) + (m & 3);
+      // accumulate: step s updates row s; the gang's lanes hit adjacent words of ONE sector in ONE instruction
 #pragma unroll
       for (int s = 0; s < G; s++) {
         const bool pred = alive[s] && ptr[s] != nullptr;
@@ -173,75 +173,79 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
 // ---------------------------------------------------------------------------------------------------
 // LEAN dense kernel: the hot loop of the M1 shape with everything resolved at compile time.
 // Preconditions (checked on the host per launch): one int64 key column, accumulator/filter columns int64,
-// none of them carries a validity bitmap, all base pointers 32-byte aligned, row_begin % 4 == 0.
-// Per 32 rows a warp issues: 1 (+1) 256-bit streaming loads and 4 REDG — about 2 instructions per row.
+// none of them carries a validity bitmap, base pointers 32-byte aligned, row_begin % 4 == 0.
+// Per 32 rows a warp issues 1 (+1) wide streaming loads and G REDG: ~2 instructions per row.
 // ---------------------------------------------------------------------------------------------------
-struct i64x4 { long long v[4]; };
-__device__ __forceinline__ i64x4 ld_stream_v4(const long long* p) {
-  i64x4 r;
+template <int G> struct i64xG { long long v[G]; };
+__device__ __forceinline__ i64xG<4> ld_stream_vec(const long long* p, i64xG<4>*) {
+  i64xG<4> r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
                : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
   return r;
 }
-__device__ __forceinline__ i64x4 ld_guarded4(const long long* p, long long rel0, long long n, long long fill) {
-  i64x4 r;
+__device__ __forceinline__ i64xG<2> ld_stream_vec(const long long* p, i64xG<2>*) {
+  i64xG<2> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(r.v[0]), "=l"(r.v[1]) : "l"(p));
+  return r;
+}
+template <int G>
+__device__ __forceinline__ i64xG<G> ld_rows(const long long* col, long long rel0, long long n) {
+  if (rel0 + G <= n) return ld_stream_vec(col + rel0, (i64xG<G>*)nullptr);
+  i64xG<G> r;
 #pragma unroll
-  for (int s = 0; s < 4; s++) r.v[s] = rel0 + s < n ? __ldg(p + rel0 + s) : fill;
+  for (int s = 0; s < G; s++) r.v[s] = rel0 + s < n ? __ldg(col + rel0 + s) : 0;
   return r;
 }
 
-template <int NACC>
+template <int NACC, int G>
 __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                   long long row_begin, long long n) {
-  constexpr int U = 2;                                          // units (32 rows) in flight per warp
-  const unsigned lane = threadIdx.x & 31, m = lane & 3, gl = lane & ~3u;
+  constexpr int U = G == 2 ? 4 : 2;                             // 32-row units in flight per warp
+  const unsigned lane = threadIdx.x & 31, m = lane % G, gl = lane - m;
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const long long* kcol = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
-  // operand of the word this lane owns: word 0 = row counter (+1), word 1/2 = acc0/acc1, word 3 = padding (+0)
-  const int my_acc = (int)m - 1;
-  const bool has_acc = my_acc >= 0 && my_acc < NACC;
-  const bool is_add = has_acc && fs.acc[has_acc ? my_acc : 0].kind == FAST_ACC_ADD;
-  const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[my_acc].col].values + row_begin : nullptr;
-  const long long cst = (m == 0 || has_acc) ? 1 : 0;
-  unsigned long long* const sink = fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + m;
+  const int src = fs.dense_word_src[m];                         // -1: row counter (+1), -2: padding (+0), j: accumulator j
+  const bool has_acc = src >= 0 && src < NACC;
+  const bool is_add = has_acc && fs.acc[has_acc ? src : 0].kind == FAST_ACC_ADD;
+  const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[src].col].values + row_begin : nullptr;
+  const long long cst = src == -2 ? 0 : 1;
+  unsigned long long* const sink = warp_sink(fs, gwarp, m);
   const long long base = fs.dense_base; const unsigned long long cap = fs.dense_cap;
   unsigned long long* const dtab = fs.dense_tab + m;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    i64x4 k[U], v[U]; bool alive[U][4];
+    i64xG<G> k[U], v[U]; bool alive[U][G];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long rel0 = (unit0 + u) * 32 + gl;
-      if (rel0 + 4 <= n) {
-        k[u] = ld_stream_v4(kcol + rel0);
-        if (is_add) v[u] = ld_stream_v4(vcol + rel0); else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = cst; }
-      } else {
-        k[u] = ld_guarded4(kcol, rel0, n, 0);
-        if (is_add) v[u] = ld_guarded4(vcol, rel0, n, 0); else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = cst; }
+      k[u] = ld_rows<G>(kcol, rel0, n);
+      if (is_add) v[u] = ld_rows<G>(vcol, rel0, n);
+      else {
+#pragma unroll
+        for (int s = 0; s < G; s++) v[u].v[s] = cst;
       }
 #pragma unroll
-      for (int s = 0; s < 4; s++) alive[u][s] = rel0 + s < n;
+      for (int s = 0; s < G; s++) alive[u][s] = rel0 + s < n;
     }
     for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
       const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const long long rel0 = (unit0 + u) * 32 + gl;
-        const i64x4 x = rel0 + 4 <= n ? ld_stream_v4(fcol + rel0) : ld_guarded4(fcol, rel0, n, 0);
+        const i64xG<G> x = ld_rows<G>(fcol, (unit0 + u) * 32 + gl, n);
 #pragma unroll
-        for (int s = 0; s < 4; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
+        for (int s = 0; s < G; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
       }
     }
     bool oor = false;
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
+      for (int s = 0; s < G; s++) {
         const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
         const bool in = alive[u][s] && idx < cap;
         oor |= alive[u][s] && !in;
-        red_add_u64(in ? dtab + idx * 4 : sink, in ? (unsigned long long)v[u].v[s] : 0ULL);    // 4 lanes -> 1 sector
+        red_add_u64(in ? dtab + idx * G : sink, in ? (unsigned long long)v[u].v[s] : 0ULL);     // G lanes -> 1 sector
       }
     }
     // keys outside the dense range (rare): lane 0 of the gang routes the row through the hash table
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
 #pragma unroll
       for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
+        for (int s = 0; s < G; s++) {
           const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
           bool inserted = false;
           if (alive[u][s] && idx >= cap && m == 0) {
@@ -282,24 +286,25 @@ static int fast_grid(int64_t ntiles) {
 }
 
 template <int NK, int NACC>
-static void launch_gang(bool dense, int grid, cudaStream_t s, const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n) {
-  if (dense) agg_gang_update_kernel<NK, NACC, true><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-  else agg_gang_update_kernel<NK, NACC, false><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+static void launch_gang(int dg, int grid, cudaStream_t s, const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n) {
+  if (dg == 4) agg_gang_update_kernel<NK, NACC, 4><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+  else if (dg == 2) agg_gang_update_kernel<NK, NACC, 2><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+  else agg_gang_update_kernel<NK, NACC, 0><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
 }
 
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
-  const int64_t ntiles = (n + FA_TILE - 1) / FA_TILE;
-  const int grid = fast_grid(ntiles);
-  const bool dense = fs.dense != 0;
-  if (dense && fs.lean) {
-    const int g = fast_grid((n + 32 * 8 * 2 - 1) / (32 * 8 * 2));
-    if (fs.nacc == 2) agg_lean_dense_kernel<2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-    else agg_lean_dense_kernel<1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+  const int dg = fs.dense ? fs.dense_stride : 0;
+  if (dg && fs.lean) {
+    const int u = dg == 2 ? 4 : 2;
+    const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
+    if (fs.nacc == 2) { if (dg == 2) agg_lean_dense_kernel<2, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<2, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    else { if (dg == 2) agg_lean_dense_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<1, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
     return 1;
   }
-  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dense, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dense, grid, s, cols, fs, lay, tab, row_begin, n); }
-  else { if (fs.nacc == 2) launch_gang<2, 2>(false, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(false, grid, s, cols, fs, lay, tab, row_begin, n); }
+  const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);
+  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
+  else { if (fs.nacc == 2) launch_gang<2, 2>(0, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(0, grid, s, cols, fs, lay, tab, row_begin, n); }
   return 1;
 }
 
@@ -344,8 +349,8 @@ __global__ void __launch_bounds__(256) agg_emit_dense_kernel(const FastSpec fs, 
   const uint64_t rounds = (fs.dense_cap + stride - 1) / stride;
   for (uint64_t it = 0; it < rounds; it++) {
     const uint64_t i = it * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const unsigned long long* e = fs.dense_tab + i * 4;
-    const bool occ = i < fs.dense_cap && e[0] != 0;
+    const unsigned long long* e = fs.dense_tab + i * fs.dense_stride;
+    const bool occ = i < fs.dense_cap && e[fs.dense_presence_word] != 0;
     const unsigned m = __ballot_sync(0xffffffffu, occ);
     if (!m) continue;
     unsigned long long base = 0;
@@ -369,16 +374,17 @@ int launch_agg_emit_dense(const FastSpec& fs, const EmitTable& emit, const Dense
   return 1;
 }
 
-// number of occupied dense entries (table growth accounting is not needed: the dense table never fills)
-__global__ void __launch_bounds__(256) dense_count_kernel(const unsigned long long* tab, uint64_t cap, unsigned long long* out) {
+// number of occupied dense entries
+__global__ void __launch_bounds__(256) dense_count_kernel(const FastSpec fs, unsigned long long* out) {
   unsigned long long c = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) c += tab[i * 4] != 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < fs.dense_cap; i += (uint64_t)gridDim.x * blockDim.x)
+    c += fs.dense_tab[i * fs.dense_stride + fs.dense_presence_word] != 0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
-int launch_dense_count(const unsigned long long* tab, uint64_t cap, unsigned long long* d_out, cudaStream_t s) {
-  dense_count_kernel<<<fast_grid(((int64_t)cap + 255) / 256), 256, 0, s>>>(tab, cap, d_out);
+int launch_dense_count(const FastSpec& fs, unsigned long long* d_out, cudaStream_t s) {
+  dense_count_kernel<<<fast_grid(((int64_t)fs.dense_cap + 255) / 256), 256, 0, s>>>(fs, d_out);
   return 1;
 }
 

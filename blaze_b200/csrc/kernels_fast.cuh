@@ -13,8 +13,12 @@ struct FastSpec {
   struct { uint8_t kind; int8_t col; uint8_t phys; uint8_t vbit; uint8_t word; uint8_t _pad[3]; } acc[2];
   struct { int8_t col; uint8_t phys; uint8_t op; uint8_t _pad[5]; long long lit; } filt[4];
   long long dense_base;                                   // DENSE: slot index = key - dense_base
-  unsigned long long dense_cap;                           // entries of 4 words {rows, acc0, acc1, -}
+  unsigned long long dense_cap;                           // entries of dense_stride words
   unsigned long long* dense_tab;
+  int8_t dense_stride;                                    // 2 or 4 words per entry (= gang width)
+  int8_t dense_word_src[4];                               // per entry word: -1 row counter (+1), -2 padding (+0), j accumulator j
+  uint8_t dense_presence_word;                            // word that is non-zero iff the entry holds a group
+  uint8_t _pad1[2];
   unsigned long long* sink;                               // FAST_SINK_WARPS x 4 words: per-warp scratch sector for no-op REDs
 };
 constexpr int FAST_SINK_WARPS = 4096;
@@ -25,6 +29,6 @@ struct DenseEmitMap { uint8_t word[EMIT_MAX_COLS]; uint8_t valid_word[EMIT_MAX_C
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
 int launch_key_range(const DevCol& col, int phys, int64_t n, long long* d_out, cudaStream_t s);
 int launch_agg_emit_dense(const FastSpec& fs, const EmitTable& emit, const DenseEmitMap& map, unsigned long long* d_out_count, cudaStream_t s);
-int launch_dense_count(const unsigned long long* tab, uint64_t cap, unsigned long long* d_out, cudaStream_t s);
+int launch_dense_count(const FastSpec& fs, unsigned long long* d_out, cudaStream_t s);
 
 }  // namespace b200q

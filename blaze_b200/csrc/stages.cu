@@ -451,15 +451,37 @@ class AggStage : public Stage {
     }
     if (dense_possible_) {
       for (size_t c = 0; c < emit_.size(); c++) {
-        dmap_.word[c] = 0; dmap_.valid_word[c] = 0xFF;
         const EmitCol& ec = emit_[c].ec;
         if (ec.kind == EMIT_KEY) continue;
-        if (ec.kind != EMIT_ACC_VALUE || ec.is_order_key) { dense_possible_ = false; break; }
-        int j = -1; for (int i = 0; i < lay_.nacc; i++) if (fs_.acc[i].word == ec.word) j = i;
-        if (j < 0) { dense_possible_ = false; break; }
-        dmap_.word[c] = (uint8_t)(1 + j);
-        if (ec.vbit != 0xFF) for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) dmap_.valid_word[c] = (uint8_t)(1 + i);
+        bool found = false; for (int i = 0; i < lay_.nacc; i++) found |= fs_.acc[i].word == ec.word;
+        if (ec.kind != EMIT_ACC_VALUE || ec.is_order_key || !found) { dense_possible_ = false; break; }
       }
+    }
+  }
+
+  // dense entry layout: {acc0, acc1} (2 words) when a COUNT(*) accumulator doubles as the presence marker,
+  // else {rows, acc0} (2 words) or {rows, acc0, acc1, pad} (4 words)
+  void dense_layout() {
+    int star = -1;
+    for (int j = 0; j < lay_.nacc; j++) if (fs_.acc[j].kind == FAST_ACC_COUNT && fs_.acc[j].col < 0) star = j;
+    int word_of_acc[2] = {0, 0};
+    for (int w = 0; w < 4; w++) fs_.dense_word_src[w] = -2;
+    if (star >= 0) {
+      fs_.dense_stride = 2;
+      for (int j = 0; j < lay_.nacc; j++) { fs_.dense_word_src[j] = (int8_t)j; word_of_acc[j] = j; }
+      fs_.dense_presence_word = (uint8_t)word_of_acc[star];
+    } else {
+      fs_.dense_stride = lay_.nacc == 1 ? 2 : 4;
+      fs_.dense_word_src[0] = -1; fs_.dense_presence_word = 0;
+      for (int j = 0; j < lay_.nacc; j++) { fs_.dense_word_src[1 + j] = (int8_t)j; word_of_acc[j] = 1 + j; }
+    }
+    for (size_t c = 0; c < emit_.size(); c++) {
+      dmap_.word[c] = 0; dmap_.valid_word[c] = 0xFF;
+      const EmitCol& ec = emit_[c].ec;
+      if (ec.kind == EMIT_KEY) continue;
+      int j = 0; for (int i = 0; i < lay_.nacc; i++) if (fs_.acc[i].word == ec.word) j = i;
+      dmap_.word[c] = (uint8_t)word_of_acc[j];
+      if (ec.vbit != 0xFF) for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) dmap_.valid_word[c] = (uint8_t)word_of_acc[i];
     }
   }
 
@@ -482,7 +504,8 @@ class AggStage : public Stage {
     const uint64_t r = (uint64_t)range, margin = r / 8 + 64;
     fs_.dense_base = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
     fs_.dense_cap = r + 2 * margin;
-    dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * 32, cx.stream, true);
+    dense_layout();
+    dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * fs_.dense_stride * 8, cx.stream, true);
     fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;
     fs_.dense = 1;
   }
@@ -639,7 +662,7 @@ class AggStage : public Stage {
     int64_t g = ngroups_;
     if (fs_.dense) {
       DevMemP dc = DevMem::alloc(8, cx.stream, true);
-      cx.m.launches += launch_dense_count(fs_.dense_tab, fs_.dense_cap, (unsigned long long*)dc->ptr, cx.stream);
+      cx.m.launches += launch_dense_count(fs_, (unsigned long long*)dc->ptr, cx.stream);
       unsigned long long hc = 0;
       B200Q_CUDA(cudaMemcpyAsync(&hc, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
       B200Q_CUDA(cudaStreamSynchronize(cx.stream));
