@@ -111,6 +111,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from blaze_b200 import native
+    from blaze_b200.exchange import exchange_columns
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
@@ -157,17 +158,7 @@ def run_ours(args):
         _key_struct(native, ks, ka, cols[0][0], local)
         native.check(native.lib.b200q_murmur3_partition(native.C.addressof(ks), native.C.addressof(ka), world, pids.data_ptr(), None))
         torch.cuda.synchronize()
-        order = torch.argsort(pids, stable=True)
-        send_counts = torch.bincount(pids, minlength=world).to(torch.int64)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        sc, rc = send_counts.tolist(), recv_counts.tolist()
-        recv = []
-        for t, _, _ in cols:
-            src = t[order].contiguous()
-            dst = torch.empty(sum(rc), dtype=torch.int64, device=dev)
-            dist.all_to_all_single(dst, src, output_split_sizes=rc, input_split_sizes=sc)
-            recv.append(dst)
+        recv = exchange_columns([t for t, _, _ in cols], pids, world, dist)
         native.release_device_array(out)
         n_in = recv[0].numel()
         with native.NativeOp(plans["final_col"], conf_col, local) as op:
@@ -209,6 +200,7 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------
     import pyarrow as pa
+    numa = bind_to_gpu_numa(torch, local)        # pinned buffers on the GPU's NUMA node (first touch)
     hk = torch.empty(e2e_rows, dtype=torch.int64, pin_memory=True); hv = torch.empty(e2e_rows, dtype=torch.int64, pin_memory=True)
     hk.copy_(k[:e2e_rows]); hv.copy_(v[:e2e_rows]); torch.cuda.synchronize()
 
@@ -272,6 +264,7 @@ def run_ours(args):
                 "avg_launch_ms": stats["hot_ns"] / launches / 1e6, "alg_bytes_per_launch": alg_bytes_per_launch}
     # ---- CPU baseline (restatement of the reference algorithm) on this box's host cores --------------------
     cpu = None
+    os.sched_setaffinity(0, range(os.cpu_count() or 1))
     if world == 1:
         cpu = cpu_baseline(hk.numpy(), hv.numpy(), min(e2e_rows, env_int("B200Q_BENCH_CPU_ROWS", 1 << 28)))
     line = {
@@ -282,12 +275,30 @@ def run_ours(args):
                    "rows_per_gpu": rows, "groups": CARD, "parallelism": f"dp{world}" + ("" if world == 1 else " + murmur3 pmod all_to_all of partial states"),
                    "l2_policy": "input (16 GB/GPU) is far larger than L2; no flush needed", "plan": "AggExec(Partial) -> AggExec(Final), reference protobuf + C ABI"},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_stats["h2d"], "d2h_bytes_per_step": e2e_stats["d2h"],
-                "rows_per_gpu": e2e_rows, "host_batch_rows": e2e_batch, "steps": e2e_steps},
+                "rows_per_gpu": e2e_rows, "host_batch_rows": e2e_batch, "steps": e2e_steps, "host_numa_node": numa},
         "gpu_launches": stats["launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa(torch, local):
+    """run this process (and first-touch its pinned buffers) on the CPU socket the GPU hangs off"""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def _key_struct(native, ks, ka, key_tensor, device):

@@ -443,7 +443,7 @@ static void conf_defaults(b200q_conf* c) {
   c->partial_agg_skipping_min_rows = 20000;            // agg_ctx.rs:178
   c->staging_rows = 1 << 20;
   c->agg_initial_groups = 1 << 19;
-  c->max_launch_rows = 1 << 26;
+  c->max_launch_rows = 1 << 27;
   c->partial_state_columnar = 0;
   c->force_generic_kernels = 0;
   c->agg_dense_keys = 1;
@@ -493,9 +493,13 @@ b200q_status b200q_op_create(const uint8_t* plan, size_t plan_len, int32_t plan_
     conf_defaults(&op->cx.conf);
     if (conf) { const size_t n = std::min<size_t>(conf->struct_size ? conf->struct_size : sizeof(b200q_conf), sizeof(b200q_conf)); memcpy(&op->cx.conf, conf, n); op->cx.conf.struct_size = sizeof(b200q_conf); }
     if (op->cx.conf.batch_size <= 0) op->cx.conf.batch_size = 10000;
-    if (op->cx.conf.max_launch_rows <= 0) op->cx.conf.max_launch_rows = 1 << 26;
+    if (op->cx.conf.max_launch_rows <= 0) op->cx.conf.max_launch_rows = 1 << 27;
     if (op->cx.conf.agg_initial_groups <= 0) op->cx.conf.agg_initial_groups = 1 << 19;
     B200Q_CUDA(cudaSetDevice(device));
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+      cudaMemPool_t pool; unsigned long long keep = ~0ULL;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     B200Q_CUDA(cudaStreamCreateWithFlags(&op->cx.stream, cudaStreamNonBlocking));
     B200Q_CUDA(cudaEventCreate(&op->cx.ev0)); B200Q_CUDA(cudaEventCreate(&op->cx.ev1));
     build_pipeline(op);

@@ -125,7 +125,7 @@ typedef struct b200q_conf {
                                          rows before one H2D + one kernel launch (default 1<<20)  */
   int64_t agg_initial_groups;         /* initial hash-table sizing hint in groups (default 1<<19) */
   int64_t max_launch_rows;            /* rows per kernel launch for device-resident pushes
-                                         (default 1<<26)                                          */
+                                         (default 1<<27)                                          */
   int32_t partial_state_columnar;     /* 1: non-final agg output/input uses typed state columns
                                          (GPU-to-GPU exchange) instead of the reference's Binary
                                          frozen-row column `#9223372036854775807`                 */

@@ -17,8 +17,9 @@
  *             (acc.rs:243-280, sum.rs:90-115, count.rs:90-126).
  *   Filter+Project  separate passes per batch: predicate mask -> null->false -> compact each column ->
  *             project (cached_exprs_evaluator.rs:90-166,495-524).
- *   T threads = one reference "task" per thread over N/T rows (Spark task parallelism, rt.rs:110-130),
- *             then the Final-mode merge of the T partial tables (agg_ctx.rs:276-301).
+ *   T threads = one reference "task" per thread over N/T rows (Spark task parallelism, rt.rs:110-130): Partial per
+ *             task, partial records bucketed by key hash (the shuffle), then one Final-mode merge per reduce
+ *             partition, also T threads (agg_ctx.rs:276-301).
  *
  * The slot/bucket hash (foldhash 0.1.5 in the reference) is not observable in results; a folded
  * multiply of the same flavour is used.
@@ -142,7 +143,13 @@ static void update_batch(table_t* t, const int64_t* k, const uint8_t* kvalid, co
   for (int i = 0; i < n; i++) t->counts[recs[i]] += bit_get(vvalid, base + i);                                                          /* AggCount::partial_update */
 }
 
-typedef struct { const int64_t* k; const uint8_t* kvalid; const int64_t* v; const uint8_t* vvalid; int64_t begin, end; table_t t; } task_t;
+typedef struct task_s {
+  const int64_t* k; const uint8_t* kvalid; const int64_t* v; const uint8_t* vvalid; int64_t begin, end; table_t t;
+  /* shuffle write: records of this task bucketed by the final partition that owns their key */
+  int nparts; uint32_t* bucket_off; uint32_t* bucket_idx;
+  /* final stage (one reduce partition per thread) */
+  struct task_s* all; int self; table_t fin;
+} task_t;
 
 static void* task_main(void* arg) {
   task_t* ta = (task_t*)arg;
@@ -153,11 +160,39 @@ static void* task_main(void* arg) {
     update_batch(&ta->t, ta->k, ta->kvalid, ta->v, ta->vvalid, b, n, rows, hashes, recs);
   }
   free(rows); free(hashes); free(recs);
+  /* "shuffle write": partition the partial records by owner = hash % nparts (Spark: murmur3 pmod, shuffle/mod.rs:163-188) */
+  int P = ta->nparts; table_t* t = &ta->t;
+  ta->bucket_off = calloc((size_t)P + 1, 4); ta->bucket_idx = malloc((t->nrec ? t->nrec : 1) * 4);
+  for (uint64_t r = 0; r < t->nrec; r++) { const uint8_t* k = t->keys + r * KEY_CELL; ta->bucket_off[1 + (key_hash(k + 1, k[0]) >> 3) % (uint32_t)P]++; }
+  for (int p = 0; p < P; p++) ta->bucket_off[p + 1] += ta->bucket_off[p];
+  uint32_t* cur = malloc((size_t)P * 4); memcpy(cur, ta->bucket_off, (size_t)P * 4);
+  for (uint64_t r = 0; r < t->nrec; r++) { const uint8_t* k = t->keys + r * KEY_CELL; ta->bucket_idx[cur[(key_hash(k + 1, k[0]) >> 3) % (uint32_t)P]++] = (uint32_t)r; }
+  free(cur);
   return NULL;
 }
 
-/* Partial per task + Final merge.  Outputs (caller-allocated, capacity >= number of distinct keys, or NULL to
- * only count): returns the number of groups.  key_valid/sum_valid are one byte per group. */
+/* Final-mode AggExec of one reduce partition: merge the partial records every task bucketed for it (agg_ctx.rs:276-301) */
+static void* final_main(void* arg) {
+  task_t* me = (task_t*)arg; table_t* fin = &me->fin;
+  table_init(fin);
+  for (int i = 0; i < me->nparts; i++) {
+    task_t* src = &me->all[i]; table_t* p = &src->t;
+    uint32_t lo = src->bucket_off[me->self], hi = src->bucket_off[me->self + 1];
+    table_reserve(fin, hi - lo);
+    for (uint32_t x = lo; x < hi; x++) {
+      uint64_t r = src->bucket_idx[x];
+      const uint8_t* key = p->keys + r * KEY_CELL;
+      uint32_t rec = upsert_one(fin, key + 1, key[0], key_hash(key + 1, key[0]));
+      if (p->sum_valid[r]) { if (fin->sum_valid[rec]) fin->sums[rec] = (int64_t)((uint64_t)fin->sums[rec] + (uint64_t)p->sums[r]); else { fin->sums[rec] = p->sums[r]; fin->sum_valid[rec] = 1; } }
+      fin->counts[rec] += p->counts[r];
+    }
+  }
+  return NULL;
+}
+
+/* Partial per task -> shuffle by key hash -> Final per partition, T threads in both stages (Spark's two-stage plan,
+ * NativeAggBase.scala:129-135).  Outputs (caller-allocated, capacity >= number of distinct keys, or NULL to only
+ * count): returns the number of groups.  key_valid/sum_valid are one byte per group. */
 int64_t cpu_ref_hashagg_sum_count(const int64_t* k, const uint8_t* kvalid, const int64_t* v, const uint8_t* vvalid, int64_t n, int nthreads,
                                   int64_t* out_k, uint8_t* out_kvalid, int64_t* out_sum, uint8_t* out_sumvalid, int64_t* out_cnt, int64_t out_cap) {
   if (nthreads < 1) nthreads = 1;
@@ -165,31 +200,26 @@ int64_t cpu_ref_hashagg_sum_count(const int64_t* k, const uint8_t* kvalid, const
   pthread_t* th = calloc((size_t)nthreads, sizeof(pthread_t));
   int64_t per = ((n + nthreads - 1) / nthreads + BATCH_SIZE - 1) / BATCH_SIZE * BATCH_SIZE;
   for (int i = 0; i < nthreads; i++) {
-    tasks[i].k = k; tasks[i].kvalid = kvalid; tasks[i].v = v; tasks[i].vvalid = vvalid;
+    tasks[i].k = k; tasks[i].kvalid = kvalid; tasks[i].v = v; tasks[i].vvalid = vvalid; tasks[i].nparts = nthreads; tasks[i].all = tasks; tasks[i].self = i;
     tasks[i].begin = per * i < n ? per * i : n; tasks[i].end = per * (i + 1) < n ? per * (i + 1) : n;
     if (nthreads == 1) task_main(&tasks[i]); else pthread_create(&th[i], NULL, task_main, &tasks[i]);
   }
   if (nthreads > 1) for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
-  table_t* fin = &tasks[0].t;
-  for (int i = 1; i < nthreads; i++) {                                  /* Final: partial_merge of each task's table */
-    table_t* p = &tasks[i].t;
-    table_reserve(fin, p->nrec);
-    for (uint64_t r = 0; r < p->nrec; r++) {
-      const uint8_t* key = p->keys + r * KEY_CELL;
-      uint32_t rec = upsert_one(fin, key + 1, key[0], key_hash(key + 1, key[0]));
-      if (p->sum_valid[r]) { if (fin->sum_valid[rec]) fin->sums[rec] = (int64_t)((uint64_t)fin->sums[rec] + (uint64_t)p->sums[r]); else { fin->sums[rec] = p->sums[r]; fin->sum_valid[rec] = 1; } }
-      fin->counts[rec] += p->counts[r];
-    }
-    table_free(p);
-  }
-  int64_t g = (int64_t)fin->nrec;
+  for (int i = 0; i < nthreads; i++) { if (nthreads == 1) final_main(&tasks[i]); else pthread_create(&th[i], NULL, final_main, &tasks[i]); }
+  if (nthreads > 1) for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  int64_t g = 0;
+  for (int i = 0; i < nthreads; i++) g += (int64_t)tasks[i].fin.nrec;
   if (out_k && g <= out_cap) {
-    for (int64_t r = 0; r < g; r++) {
-      int valid; out_k[r] = decode_key(fin->keys + r * KEY_CELL + 1, &valid);
-      out_kvalid[r] = (uint8_t)valid; out_sum[r] = fin->sum_valid[r] ? fin->sums[r] : 0; out_sumvalid[r] = fin->sum_valid[r]; out_cnt[r] = fin->counts[r];
+    int64_t o = 0;
+    for (int i = 0; i < nthreads; i++) {
+      table_t* fin = &tasks[i].fin;
+      for (uint64_t r = 0; r < fin->nrec; r++, o++) {
+        int valid; out_k[o] = decode_key(fin->keys + r * KEY_CELL + 1, &valid);
+        out_kvalid[o] = (uint8_t)valid; out_sum[o] = fin->sum_valid[r] ? fin->sums[r] : 0; out_sumvalid[o] = fin->sum_valid[r]; out_cnt[o] = fin->counts[r];
+      }
     }
   }
-  table_free(fin);
+  for (int i = 0; i < nthreads; i++) { table_free(&tasks[i].t); table_free(&tasks[i].fin); free(tasks[i].bucket_off); free(tasks[i].bucket_idx); }
   free(tasks); free(th);
   return g;
 }
