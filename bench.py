@@ -314,9 +314,22 @@ def _key_struct(native, ks, ka, key_tensor, device):
     native.DeviceBatch._live.pop(db._id, None)
 
 
+def usable_cores():
+    """host threads this container may actually run: min(visible CPUs, cgroup cpu.max quota).
+    (oracle/cpu_ref.c peaks there: profiles/r01_cpu_ref_thread_scaling.txt)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(k_np, v_np, sample_rows, threads=None):
     from oracle import cpu_ref
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or usable_cores()
     k, v = k_np[:sample_rows], v_np[:sample_rows]
     cpu_ref.hashagg_time_only(k[: min(sample_rows, 1 << 22)], v[: min(sample_rows, 1 << 22)], threads)    # warm-up
     t0 = time.perf_counter()
@@ -334,7 +347,7 @@ def run_reference(args):
         return
     import numpy as np
     from oracle import cpu_ref
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     rows = env_int("B200Q_BENCH_REF_ROWS", 1 << 28)
     rng = np.random.default_rng(44)
     k = rng.integers(0, CARD, rows, dtype=np.int64); v = rng.integers(-10**6, 10**6, rows, dtype=np.int64)
