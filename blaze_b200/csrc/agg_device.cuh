@@ -28,15 +28,20 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 __device__ __forceinline__ void red_add_f64(unsigned long long* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ void red_min_s64(unsigned long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_max_s64(unsigned long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+constexpr uint64_t AGG_HASH_SEED = 0x9E3779B97F4A7C15ULL;
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
-constexpr uint64_t AGG_HASH_SEED = 0x9E3779B97F4A7C15ULL;
-// hash of the key words (NULL keys canonicalised to 0) and the key-is-NULL mask; not observable in results
+// hash of the key words (NULL keys canonicalised to 0) and the key-is-NULL mask; not observable in results.
+// One 64-bit finaliser per key: extra words / the null mask are folded in with odd multipliers first.
+__device__ __forceinline__ uint64_t agg_hash2(uint64_t k0, uint64_t k1, uint32_t knull) {
+  return mix64((AGG_HASH_SEED ^ k0) + k1 * 0xD6E8FEB86659FD93ULL + (uint64_t)knull * 0xA0761D6478BD642FULL);
+}
 __device__ __forceinline__ uint64_t agg_hash_words(const uint64_t* kw, int nkw, uint32_t knull) {
-  uint64_t h = AGG_HASH_SEED;
-  for (int i = 0; i < nkw; i++) h = mix64(h ^ kw[i]);
-  return mix64(h ^ knull);
+  if (nkw <= 2) return agg_hash2(nkw > 0 ? kw[0] : 0, nkw > 1 ? kw[1] : 0, knull);
+  uint64_t x = AGG_HASH_SEED ^ kw[0];
+  for (int i = 1; i < nkw; i++) x = x * 0xD6E8FEB86659FD93ULL + kw[i];
+  return mix64(x + (uint64_t)knull * 0xA0761D6478BD642FULL);
 }
 
 __device__ __forceinline__ void slot_mark(unsigned long long* slot, unsigned flags_seen, int vbit) {

@@ -123,9 +123,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
           const unsigned long long idx = (unsigned long long)(key0[s] - fs.dense_base);
           if (knull[s] == 0 && idx < fs.dense_cap) { ptr[s] = fs.dense_tab + idx * G + m; continue; }
         }
-        uint64_t hh = mix64(AGG_HASH_SEED ^ (uint64_t)key0[s]);
-        if (NK == 2) hh = mix64(hh ^ (uint64_t)key1[s]);
-        h[s] = mix64(hh ^ knull[s]);
+        h[s] = agg_hash2((uint64_t)key0[s], NK == 2 ? (uint64_t)key1[s] : 0ULL, knull[s]);
         slot[s] = tab.slots + (h[s] & tab.mask) * (uint64_t)lay.slot_words;
         hk[s] = ld_relaxed_v2u64(slot[s]);                                     // {hdr, key0}: one 16-byte probe per row
         miss[s] = true;
@@ -186,6 +184,11 @@ __device__ __forceinline__ i64xG<4> ld_stream_vec(const long long* p, i64xG<4>*)
 __device__ __forceinline__ i64xG<2> ld_stream_vec(const long long* p, i64xG<2>*) {
   i64xG<2> r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0,%1}, [%2];" : "=l"(r.v[0]), "=l"(r.v[1]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ i64xG<1> ld_stream_vec(const long long* p, i64xG<1>*) {
+  i64xG<1> r;
+  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r.v[0]) : "l"(p));
   return r;
 }
 template <int G>
@@ -279,6 +282,104 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// LEAN hashed kernel: 1-2 non-null int64 keys, non-null int64 accumulator/filter columns (same preconditions
+// as the lean dense kernel).  Per row: one 16-byte probe + one sector of REDs; the lanes of a gang (G = number
+// of accumulators) probe the same slot (one LSU access) and update its G accumulator words together.
+// ---------------------------------------------------------------------------------------------------
+template <int NK, int NACC>
+__global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                 long long row_begin, long long n) {
+  constexpr int G = NACC;                                      // 1 or 2
+  constexpr int U = G == 2 ? 2 : 4;                             // 4 rows per lane in flight
+  const unsigned lane = threadIdx.x & 31, m = lane % G, gl = lane - m;
+  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const long long nunits = (n + 31) / 32;
+  const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
+  const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
+  const bool is_add = fs.acc[m].kind == FAST_ACC_ADD;
+  const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[m].col].values + row_begin : nullptr;
+  const int acc_word = fs.acc[m].word, acc_vbit = fs.acc[m].vbit;
+  unsigned long long* const sink = warp_sink(fs, gwarp, m);
+  const uint64_t mask = tab.mask; const int sw = lay.slot_words;
+
+  for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
+    i64xG<G> k0[U], k1[U], v[U]; bool alive[U][G];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long rel0 = (unit0 + u) * (32 / G) * G + gl;   // = (unit0+u)*32 + gl
+      k0[u] = ld_rows<G>(kcol0, rel0, n);
+      if (NK == 2) k1[u] = ld_rows<G>(kcol1, rel0, n);
+      if (is_add) v[u] = ld_rows<G>(vcol, rel0, n);
+      else {
+#pragma unroll
+        for (int s = 0; s < G; s++) v[u].v[s] = 1;
+      }
+#pragma unroll
+      for (int s = 0; s < G; s++) alive[u][s] = rel0 + s < n;
+    }
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
+      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const i64xG<G> x = ld_rows<G>(fcol, (unit0 + u) * 32 + gl, n);
+#pragma unroll
+        for (int s = 0; s < G; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
+      }
+    }
+    // probes of all rows in flight
+    unsigned long long* slot[U][G]; ulonglong2 hk[U][G]; uint64_t h[U][G];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        h[u][s] = agg_hash2((uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL, 0);
+        slot[u][s] = tab.slots + (h[u][s] & mask) * (uint64_t)sw;
+        if (alive[u][s]) hk[u][s] = ld_relaxed_v2u64(slot[u][s]); else { hk[u][s].x = 0; hk[u][s].y = 0; }
+      }
+    }
+    unsigned flags[U][G]; bool miss[U][G]; bool any_miss = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        const unsigned tag = (unsigned)(h[u][s] >> 32) | 0x80000000u;
+        flags[u][s] = (unsigned)(hk[u][s].x >> 32);
+        bool hit = (unsigned)hk[u][s].x == tag && (flags[u][s] >> 16) == 0 && hk[u][s].y == (uint64_t)k0[u].v[s];
+        if (NK == 2 && hit && alive[u][s]) hit = ld_relaxed_u64(slot[u][s] + 2) == (uint64_t)k1[u].v[s];
+        miss[u][s] = alive[u][s] && !hit; any_miss |= miss[u][s];
+      }
+    }
+    if (__any_sync(0xffffffffu, any_miss)) {                    // insert / walk the probe sequence (lane 0 of the gang), then broadcast
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+          unsigned long long sp = (unsigned long long)slot[u][s]; unsigned fl = flags[u][s]; bool ins = false;
+          if (miss[u][s] && m == 0) {
+            uint64_t kw[2] = {(uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL};
+            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, h[u][s], &fl, &ins);
+            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + gl + s); }
+            sp = (unsigned long long)p;
+          }
+          { const unsigned b = __ballot_sync(0xffffffffu, ins); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }
+          if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
+          if (miss[u][s]) { slot[u][s] = (unsigned long long*)sp; flags[u][s] = fl; if (!sp) alive[u][s] = false; }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int s = 0; s < G; s++) {
+        const bool pred = alive[u][s];
+        red_add_u64(pred ? slot[u][s] + acc_word : sink, pred ? (unsigned long long)v[u].v[s] : 0ULL);
+        if (pred) slot_mark(slot[u][s], flags[u][s], acc_vbit);
+      }
+    }
+  }
+}
+
 static int fast_grid(int64_t ntiles) {
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t cap = (int64_t)sms * 8;          // persistent grid: a multiple of the SM count
@@ -300,6 +401,12 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
     const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
     if (fs.nacc == 2) { if (dg == 2) agg_lean_dense_kernel<2, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<2, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
     else { if (dg == 2) agg_lean_dense_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<1, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    return 1;
+  }
+  if (!dg && fs.lean) {
+    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
+    if (fs.nkeys == 1) { if (fs.nacc == 2) agg_lean_hash_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<1, 1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    else { if (fs.nacc == 2) agg_lean_hash_kernel<2, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<2, 1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
     return 1;
   }
   const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);

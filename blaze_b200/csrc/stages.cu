@@ -50,6 +50,41 @@ class FilterProjectStage : public Stage {
   CompiledProgram cp_;
   DevMemP d_prog_;
   bool has_filters_;
+  bool lean_possible_ = false;
+  LeanFpSpec lean_{};
+
+  int slot_of(int col_index) const { for (size_t i = 0; i < cp_.used_cols.size(); i++) if (cp_.used_cols[i] == col_index) return (int)i; return -1; }
+  static bool is_i64(const DType& t) { return t.id == T_INT64 || t.id == T_TIMESTAMP_US; }
+
+  // M0-class plans: `col cmp literal` conjuncts and column / column-op-column|literal projections over int64
+  void detect_lean(const std::vector<ExprP>& filters, const std::vector<ExprP>& outs) {
+    lean_possible_ = false;
+    if (filters.size() > 4 || outs.size() > 8 || outs.empty()) return;
+    LeanFpSpec sp{}; sp.nfilt = (int)filters.size(); sp.nout = (int)outs.size();
+    for (size_t f = 0; f < filters.size(); f++) {
+      const ExprP& p = filters[f];
+      if (p->kind != E_BINARY || p->op < OP_EQ || p->op > OP_GE) return;
+      ExprP l = p->children[0], r = p->children[1]; int op = p->op - OP_EQ;
+      if (l->kind == E_LITERAL && r->kind == E_COLUMN) { std::swap(l, r); static const int flip[] = {CMP_EQ, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE}; op = flip[op]; }
+      if (l->kind != E_COLUMN || r->kind != E_LITERAL || r->lit_null || !is_i64(l->type) || !is_i64(r->type)) return;
+      const int s = slot_of(l->col_index); if (s < 0 || s > 127) return;
+      sp.filt[f].col = (int8_t)s; sp.filt[f].op = (uint8_t)op; sp.filt[f].lit = (long long)r->lit_lo;
+    }
+    for (size_t o = 0; o < outs.size(); o++) {
+      const ExprP& e = outs[o];
+      if (!is_i64(e->type)) return;
+      if (e->kind == E_COLUMN) { const int s = slot_of(e->col_index); if (s < 0 || s > 127) return; sp.out[o].kind = 0; sp.out[o].a = (int8_t)s; sp.out[o].b = -1; continue; }
+      if (e->kind != E_BINARY || (e->op != OP_PLUS && e->op != OP_MINUS && e->op != OP_MUL)) return;
+      const ExprP &l = e->children[0], &r = e->children[1];
+      if (l->kind != E_COLUMN || !is_i64(l->type)) return;
+      const int sa = slot_of(l->col_index); if (sa < 0 || sa > 127) return;
+      sp.out[o].kind = (uint8_t)(e->op == OP_PLUS ? 1 : e->op == OP_MINUS ? 2 : 3); sp.out[o].a = (int8_t)sa;
+      if (r->kind == E_COLUMN && is_i64(r->type)) { const int sb = slot_of(r->col_index); if (sb < 0 || sb > 127) return; sp.out[o].b = (int8_t)sb; }
+      else if (r->kind == E_LITERAL && !r->lit_null && is_i64(r->type)) { sp.out[o].b = -1; sp.out[o].lit = (long long)r->lit_lo; }
+      else return;
+    }
+    lean_ = sp; lean_possible_ = true;
+  }
 
  public:
   FilterProjectStage(OpContext& cx, const SchemaDef& in, const std::vector<ExprP>& filters, const std::vector<ExprP>& outs, const SchemaDef& out) {
@@ -57,6 +92,7 @@ class FilterProjectStage : public Stage {
     has_filters_ = !filters.empty();
     cp_ = compile_program(filters, outs, has_filters_);
     used_input_cols = cp_.used_cols;
+    if (!cx.conf.force_generic_kernels) detect_lean(filters, outs);
     d_prog_ = DevMem::alloc(sizeof(VmProgram), cx.stream);
     B200Q_CUDA(cudaMemcpyAsync(d_prog_->ptr, &cp_.prog, sizeof(VmProgram), cudaMemcpyHostToDevice, cx.stream));
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
@@ -79,12 +115,23 @@ class FilterProjectStage : public Stage {
       ot.values[i] = c.values->ptr; ot.validity[i] = c.validity ? (uint32_t*)c.validity->ptr : nullptr; ot.phys[i] = phys_of(od.type);
       ob.cols.push_back(c);
     }
-    const int64_t ntiles = filter_project_num_tiles(n);
-    DevMemP status = has_filters_ ? DevMem::alloc((size_t)ntiles * 8, cx.stream, true) : nullptr;
+    bool lean = lean_possible_;
+    for (size_t i = 0; lean && i < cp_.used_cols.size(); i++) lean = ct.col[i].validity == nullptr;
     DevMemP scratch = DevMem::alloc(32, cx.stream, true);
+    DevMemP status;
     B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-    cx.m.launches += launch_filter_project((const VmProgram*)d_prog_->ptr, ct, ot, (int)cp_.outs.size(), n, has_filters_,
-                                           status ? (unsigned long long*)status->ptr : nullptr, (unsigned long long*)scratch->ptr, cx.stream);
+    if (lean) {
+      // outputs of non-null inputs are never NULL: the (zeroed) validity bitmaps become all-ones
+      for (auto& c : ob.cols) if (c.validity) B200Q_CUDA(cudaMemsetAsync(c.validity->ptr, 0xFF, c.validity->bytes, cx.stream));
+      if (has_filters_) status = DevMem::alloc((size_t)filter_project_lean_num_tiles(n) * 8, cx.stream, true);
+      long long* outp[8]; for (size_t i = 0; i < cp_.outs.size(); i++) outp[i] = (long long*)ot.values[i];
+      cx.m.launches += launch_filter_project_lean(ct, lean_, outp, n, status ? (unsigned long long*)status->ptr : nullptr, (unsigned long long*)scratch->ptr, cx.stream);
+      cx.m.fast_launches++;
+    } else {
+      if (has_filters_) status = DevMem::alloc((size_t)filter_project_num_tiles(n) * 8, cx.stream, true);
+      cx.m.launches += launch_filter_project((const VmProgram*)d_prog_->ptr, ct, ot, (int)cp_.outs.size(), n, has_filters_,
+                                             status ? (unsigned long long*)status->ptr : nullptr, (unsigned long long*)scratch->ptr, cx.stream);
+    }
     B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
     B200Q_CUDA(cudaGetLastError());
     unsigned long long h[4];
@@ -545,7 +592,7 @@ class AggStage : public Stage {
 
   // no-grouping aggregation always yields exactly one row (agg_exec.rs:280-323): pre-insert the empty key
   void seed_global_group(OpContext& cx) {
-    const uint64_t h = host_mix64(0x9E3779B97F4A7C15ULL ^ 0ULL);
+    const uint64_t h = host_mix64(0x9E3779B97F4A7C15ULL);        // == agg_hash_words(nullptr, 0, 0)
     const uint32_t tag = (uint32_t)(h >> 32) | 0x80000000u;
     const uint64_t s = h & (capacity_ - 1);
     std::vector<uint64_t> img(lay_.slot_words, 0);

@@ -140,3 +140,24 @@ def test_divide_by_zero_is_an_error():
                          PL.MemoryExec.from_arrow([rb]))
     out = PL.collect(plan)
     assert sum(b.num_rows for b in out) == 2
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("thr", [-1, 0, 3, 500, 999, 1000])
+def test_lean_kernel_selectivities(thr, generic):
+    """non-null int64 inputs take the lean (bytecode-free) kernel; it must agree with the VM kernel and the oracle"""
+    rb = m0_batch(300_007, 21, 0.0)
+    A, B = E.Column("a"), E.Column("b")
+    projs = [(A, "a"), (E.BinaryExpr(A, "Plus", B), "c"), (E.BinaryExpr(B, "Minus", E.Literal(7, T.int64)), "d"), (E.BinaryExpr(A, "Multiply", B), "m")]
+    conf = native.default_conf(staging_rows=0, force_generic_kernels=generic)
+    got, plan = run_fp(rb, [E.BinaryExpr(A, "Lt", E.Literal(thr, T.int64)), E.BinaryExpr(E.Literal(-2**40, T.int64), "LtEq", B)], projs, batch_rows=120_000, conf=conf)
+    assert (plan.last_metrics["fast_path_launches"] > 0) == (generic == 0)
+
+
+def test_lean_project_only_and_filter_only():
+    rb = m0_batch(99_999, 22, 0.0)
+    A, B = E.Column("a"), E.Column("b")
+    _, plan = run_fp(rb, [], [(E.BinaryExpr(A, "Multiply", E.Literal(3, T.int64)), "x"), (B, "b")])
+    assert plan.last_metrics["fast_path_launches"] > 0
+    _, plan = run_fp(rb, [E.BinaryExpr(A, "GtEq", E.Literal(990, T.int64))], None)
+    assert plan.last_metrics["fast_path_launches"] > 0
