@@ -71,7 +71,7 @@ struct HostBatch { std::shared_ptr<HostBlock> block; std::vector<HostColumn> col
 struct PendingRelease { ArrowArray arr; cudaEvent_t ev; };
 
 struct StagingSet {
-  struct Col { void* values = nullptr; size_t values_cap = 0; uint8_t* validity = nullptr; int32_t* offsets = nullptr; uint8_t* data = nullptr; size_t data_cap = 0, data_len = 0; };
+  struct Col { bool any_null = false; void* values = nullptr; size_t values_cap = 0; uint8_t* validity = nullptr; int32_t* offsets = nullptr; uint8_t* data = nullptr; size_t data_cap = 0, data_len = 0; };
   std::vector<Col> cols;
   int64_t rows = 0;
   cudaEvent_t ev = nullptr;
@@ -284,7 +284,7 @@ static void staging_flush(b200q_op* op) {
   for (int ci : used) {
     StagingSet::Col& c = st.cols[ci]; DevColumn& dc = db.cols[ci];
     const int64_t n = st.rows;
-    if (c.validity) { const size_t nb = (size_t)(n + 7) / 8; dc.validity = DevMem::alloc(nb + 4, cx.stream); B200Q_CUDA(cudaMemcpyAsync(dc.validity->ptr, c.validity, nb, cudaMemcpyHostToDevice, cx.stream)); cx.m.h2d_bytes += (int64_t)nb; }
+    if (c.validity && c.any_null) { const size_t nb = (size_t)(n + 7) / 8; dc.validity = DevMem::alloc(nb + 4, cx.stream); B200Q_CUDA(cudaMemcpyAsync(dc.validity->ptr, c.validity, nb, cudaMemcpyHostToDevice, cx.stream)); cx.m.h2d_bytes += (int64_t)nb; }
     if (dc.type.id == T_BINARY) {
       dc.offsets = DevMem::alloc((size_t)(n + 1) * 4, cx.stream); B200Q_CUDA(cudaMemcpyAsync(dc.offsets->ptr, c.offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, cx.stream));
       dc.values = DevMem::alloc(c.data_len, cx.stream); if (c.data_len) B200Q_CUDA(cudaMemcpyAsync(dc.values->ptr, c.data, c.data_len, cudaMemcpyHostToDevice, cx.stream));
@@ -298,7 +298,7 @@ static void staging_flush(b200q_op* op) {
   StagingSet& nx = op->staging[op->cur_stage_set];
   if (nx.in_flight) { B200Q_CUDA(cudaEventSynchronize(nx.ev)); nx.in_flight = false; }
   nx.rows = 0;
-  for (auto& c : nx.cols) { c.data_len = 0; if (c.validity) memset(c.validity, 0, (size_t)(cx.conf.staging_rows + 7) / 8 + 8); if (c.values && c.values_cap < (size_t)cx.conf.staging_rows) memset(c.values, 0, c.values_cap); }
+  for (auto& c : nx.cols) { c.data_len = 0; c.any_null = false; if (c.validity) memset(c.validity, 0, (size_t)(cx.conf.staging_rows + 7) / 8 + 8); if (c.values && c.values_cap < (size_t)cx.conf.staging_rows) memset(c.values, 0, c.values_cap); }
   run_stages(op, db, 0);
 }
 
@@ -316,7 +316,7 @@ static void staging_append(b200q_op* op, const ArrowArray* batch) {
       const ArrowArray* c = batch->children[ci]; StagingSet::Col& sc = st.cols[ci]; const DType& t = op->in_schema.fields[ci].type;
       const int64_t off = c->offset + batch->offset + done;
       const uint8_t* validity = c->n_buffers > 0 ? (const uint8_t*)c->buffers[0] : nullptr;
-      if (sc.validity) { if (validity && c->null_count != 0) copy_bits(sc.validity, st.rows, validity, off, take); else set_bits(sc.validity, st.rows, take); }
+      if (sc.validity) { if (validity && c->null_count != 0) { copy_bits(sc.validity, st.rows, validity, off, take); sc.any_null = true; } else set_bits(sc.validity, st.rows, take); }
       if (t.id == T_BINARY) {
         const int32_t* offs = (const int32_t*)c->buffers[1]; const uint8_t* data = (const uint8_t*)c->buffers[2];
         const size_t nbytes = (size_t)(offs[off + take] - offs[off]);

@@ -427,7 +427,8 @@ class AggStage : public Stage {
 
     // ---- table
     uint64_t want = (uint64_t)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * 2;
-    capacity_ = 1ULL << 20;                                       // floor: keeps the insert-overshoot bound (resident threads) below capacity/2
+    capacity_ = 1ULL << 21;                                       // floor: the slack above the load limit (capacity * 0.3) must exceed the
+                                                                  // concurrent-insert overshoot bound (resident threads ~ 303K)
     while (capacity_ < want) capacity_ <<= 1;
     alloc_table(cx, capacity_, slots_, counters_);
     if (lay_.nkeys == 0) seed_global_group(cx);
@@ -606,7 +607,7 @@ class AggStage : public Stage {
 
   AggTable table_view(int deferred_idx) const {
     AggTable t{};
-    t.slots = (unsigned long long*)slots_->ptr; t.mask = capacity_ - 1; t.max_groups = capacity_ / 2;
+    t.slots = (unsigned long long*)slots_->ptr; t.mask = capacity_ - 1; t.max_groups = capacity_ / 10 * 7;
     t.counters = (unsigned long long*)counters_->ptr;
     t.deferred = deferred_[deferred_idx] ? (uint32_t*)deferred_[deferred_idx]->ptr : nullptr;
     return t;
@@ -614,11 +615,11 @@ class AggStage : public Stage {
 
   void grow(OpContext& cx, uint64_t min_groups) {
     uint64_t cap = capacity_;
-    do cap <<= 2; while (cap / 2 < min_groups);
+    do cap <<= 1; while (cap / 10 * 7 < min_groups);
     DevMemP nslots, ncounters;
     alloc_table(cx, cap, nslots, ncounters);
     AggTable oldt = table_view(0);
-    AggTable newt{}; newt.slots = (unsigned long long*)nslots->ptr; newt.mask = cap - 1; newt.max_groups = cap / 2; newt.counters = (unsigned long long*)ncounters->ptr;
+    AggTable newt{}; newt.slots = (unsigned long long*)nslots->ptr; newt.mask = cap - 1; newt.max_groups = cap / 10 * 7; newt.counters = (unsigned long long*)ncounters->ptr;
     cx.m.launches += launch_agg_rehash(lay_, oldt, newt, cx.stream);
     B200Q_CUDA(cudaGetLastError());
     slots_ = nslots; counters_ = ncounters; capacity_ = cap;
