@@ -173,7 +173,7 @@ static int grid_for(int64_t ntiles, int per_sm);
 // a column or `column op column|literal`.  Loads are striped (row = r*256 + tid): perfectly coalesced, and the
 // survivors of a warp-row are written to consecutive positions.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FL_R = 4;
+constexpr int FL_R = 8;                          // 2048 rows per tile: amortises the ticket + look-back + 3 barriers
 constexpr int FL_TILE = FP_BLOCK * FL_R;
 int64_t filter_project_lean_num_tiles(int64_t n) { return (n + FL_TILE - 1) / FL_TILE; }
 struct LeanOutPtrs { long long* p[8]; };
@@ -209,10 +209,12 @@ __global__ void __launch_bounds__(FP_BLOCK) filter_project_lean_kernel(const Col
     for (int r = 0; r < FL_R; r++) { amask[r] = __ballot_sync(0xffffffffu, alive[r]); if (lane == 0) s_cnt[r * FP_NW + warp] = __popc(amask[r]); }
     __syncthreads();
     if (warp == 0) {
-      unsigned v = s_cnt[lane], incl = v;                                  // FL_R * FP_NW == 32
+      static_assert(FL_R * FP_NW == 64, "the warp scan below handles two warp-rows per lane");
+      const unsigned v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1], v = v0 + v1;
+      unsigned incl = v;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      s_off[lane] = incl - v;
+      s_off[2 * lane] = incl - v; s_off[2 * lane + 1] = incl - v + v0;
       const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
       unsigned long long excl = 0;
       if (sp.nfilt == 0) excl = (unsigned long long)tile * FL_TILE;        // nothing filtered: positions are the row numbers
