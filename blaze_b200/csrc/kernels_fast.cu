@@ -327,44 +327,66 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
         for (int s = 0; s < G; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
       }
     }
-    // probes of all rows in flight
-    unsigned long long* slot[U][G]; ulonglong2 hk[U][G]; uint64_t h[U][G];
+    // probe walk: every pending row of every lane advances one slot per round (the lanes of a gang compute the
+    // same thing, so they stay in lockstep without communicating).  Collisions are common at load 0.5 (~25 % of
+    // first probes), so the walk must not serialise the warp; only genuinely NEW keys take the insert section.
+    unsigned long long* slot[U][G]; uint64_t h[U][G], idx[U][G]; unsigned flags[U][G]; bool need[U][G], ins[U][G];
 #pragma unroll
     for (int u = 0; u < U; u++) {
 #pragma unroll
       for (int s = 0; s < G; s++) {
         h[u][s] = agg_hash2((uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL, 0);
-        slot[u][s] = tab.slots + (h[u][s] & mask) * (uint64_t)sw;
-        if (alive[u][s]) hk[u][s] = ld_relaxed_v2u64(slot[u][s]); else { hk[u][s].x = 0; hk[u][s].y = 0; }
+        idx[u][s] = h[u][s] & mask; need[u][s] = alive[u][s]; ins[u][s] = false; slot[u][s] = nullptr; flags[u][s] = 0;
       }
     }
-    unsigned flags[U][G]; bool miss[U][G]; bool any_miss = false;
+    while (true) {
+      ulonglong2 hk[U][G];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
+      for (int u = 0; u < U; u++) {
 #pragma unroll
-      for (int s = 0; s < G; s++) {
-        const unsigned tag = (unsigned)(h[u][s] >> 32) | 0x80000000u;
-        flags[u][s] = (unsigned)(hk[u][s].x >> 32);
-        bool hit = (unsigned)hk[u][s].x == tag && (flags[u][s] >> 16) == 0 && hk[u][s].y == (uint64_t)k0[u].v[s];
-        if (NK == 2 && hit && alive[u][s]) hit = ld_relaxed_u64(slot[u][s] + 2) == (uint64_t)k1[u].v[s];
-        miss[u][s] = alive[u][s] && !hit; any_miss |= miss[u][s];
+        for (int s = 0; s < G; s++) if (need[u][s]) hk[u][s] = ld_relaxed_v2u64(tab.slots + idx[u][s] * (uint64_t)sw);   // {hdr, key0}: one 16-byte probe
       }
-    }
-    if (__any_sync(0xffffffffu, any_miss)) {                    // insert / walk the probe sequence (lane 0 of the gang), then broadcast
+      bool pending = false;
 #pragma unroll
       for (int u = 0; u < U; u++) {
 #pragma unroll
         for (int s = 0; s < G; s++) {
-          unsigned long long sp = (unsigned long long)slot[u][s]; unsigned fl = flags[u][s]; bool ins = false;
-          if (miss[u][s] && m == 0) {
+          if (!need[u][s]) continue;
+          const unsigned tag = (unsigned)(h[u][s] >> 32) | 0x80000000u, t = (unsigned)hk[u][s].x;
+          unsigned long long* sp = tab.slots + idx[u][s] * (uint64_t)sw;
+          if (t == tag) {
+            bool hit = (unsigned)(hk[u][s].x >> 48) == 0 && hk[u][s].y == (uint64_t)k0[u].v[s];
+            if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)k1[u].v[s];
+            if (hit) { slot[u][s] = sp; flags[u][s] = (unsigned)(hk[u][s].x >> 32); need[u][s] = false; }
+            else idx[u][s] = (idx[u][s] + 1) & mask;
+          } else if (t == TAG_EMPTY) { need[u][s] = false; ins[u][s] = true; }
+          else if (t != TAG_LOCKED) idx[u][s] = (idx[u][s] + 1) & mask;      // occupied by another key: next slot (locked: look again)
+          pending |= need[u][s];
+        }
+      }
+      if (!__any_sync(0xffffffffu, pending)) break;
+    }
+    bool any_ins = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int s = 0; s < G; s++) any_ins |= ins[u][s];
+    }
+    if (__any_sync(0xffffffffu, any_ins)) {                     // new keys: lane 0 of the gang inserts, then broadcasts the slot
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+          unsigned long long sp = (unsigned long long)slot[u][s]; unsigned fl = flags[u][s]; bool inserted = false;
+          if (ins[u][s] && m == 0) {
             uint64_t kw[2] = {(uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL};
-            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, h[u][s], &fl, &ins);
+            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, h[u][s], &fl, &inserted);
             if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + gl + s); }
             sp = (unsigned long long)p;
           }
-          { const unsigned b = __ballot_sync(0xffffffffu, ins); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }
+          { const unsigned b = __ballot_sync(0xffffffffu, inserted); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }
           if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
-          if (miss[u][s]) { slot[u][s] = (unsigned long long*)sp; flags[u][s] = fl; if (!sp) alive[u][s] = false; }
+          if (ins[u][s]) { slot[u][s] = (unsigned long long*)sp; flags[u][s] = fl; if (!sp) alive[u][s] = false; }
         }
       }
     }
