@@ -114,44 +114,57 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
         }
       }
       // entry / slot of every row of the gang (computed redundantly by each lane of the gang)
-      unsigned long long* ptr[G]; unsigned long long* slot[G]; unsigned flags[G]; bool miss[G]; uint64_t h[G]; ulonglong2 hk[G];
+      unsigned long long* ptr[G]; unsigned long long* slot[G]; unsigned flags[G]; bool need[G], ins[G]; uint64_t h[G], idx[G];
 #pragma unroll
       for (int s = 0; s < G; s++) {
-        ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; miss[s] = false; h[s] = 0;
+        ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; need[s] = false; ins[s] = false; h[s] = 0; idx[s] = 0;
         if (!alive[s]) continue;
         if (DENSE) {
-          const unsigned long long idx = (unsigned long long)(key0[s] - fs.dense_base);
-          if (knull[s] == 0 && idx < fs.dense_cap) { ptr[s] = fs.dense_tab + idx * G + m; continue; }
+          const unsigned long long di = (unsigned long long)(key0[s] - fs.dense_base);
+          if (knull[s] == 0 && di < fs.dense_cap) { ptr[s] = fs.dense_tab + di * G + m; continue; }
         }
         h[s] = agg_hash2((uint64_t)key0[s], NK == 2 ? (uint64_t)key1[s] : 0ULL, knull[s]);
-        slot[s] = tab.slots + (h[s] & tab.mask) * (uint64_t)lay.slot_words;
-        hk[s] = ld_relaxed_v2u64(slot[s]);                                     // {hdr, key0}: one 16-byte probe per row
-        miss[s] = true;
+        idx[s] = h[s] & tab.mask; need[s] = true;
       }
-      bool any_miss = false;
+      // probe walk: all pending rows advance one slot per round, the lanes of a gang in lockstep (collisions are
+      // common at load 0.5, so they must not serialise the warp); only NEW keys go to the insert section
+      while (true) {
+        ulonglong2 hk[G];
 #pragma unroll
-      for (int s = 0; s < G; s++) {
-        if (!miss[s]) continue;
-        const unsigned tag = (unsigned)(h[s] >> 32) | 0x80000000u;
-        flags[s] = (unsigned)(hk[s].x >> 32);
-        bool hit = (unsigned)hk[s].x == tag && (flags[s] >> 16) == knull[s] && hk[s].y == (uint64_t)key0[s];
-        if (hit && NK == 2) hit = ld_relaxed_u64(slot[s] + 2) == (uint64_t)key1[s];
-        miss[s] = !hit; any_miss |= !hit;
-      }
-      // first probe missed somewhere in the warp: lane 0 of the gang runs the full protocol, then broadcasts
-      if (__any_sync(0xffffffffu, any_miss)) {
+        for (int s = 0; s < G; s++) if (need[s]) hk[s] = ld_relaxed_v2u64(tab.slots + idx[s] * (uint64_t)lay.slot_words);   // {hdr, key0}
+        bool pending = false;
 #pragma unroll
         for (int s = 0; s < G; s++) {
-          unsigned long long sp = (unsigned long long)slot[s]; unsigned fl = flags[s]; bool ins = false;
-          if (miss[s] && m == 0) {
+          if (!need[s]) continue;
+          const unsigned tag = (unsigned)(h[s] >> 32) | 0x80000000u, t = (unsigned)hk[s].x;
+          unsigned long long* sp = tab.slots + idx[s] * (uint64_t)lay.slot_words;
+          if (t == tag) {
+            bool hit = (unsigned)(hk[s].x >> 48) == knull[s] && hk[s].y == (uint64_t)key0[s];
+            if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)key1[s];
+            if (hit) { slot[s] = sp; flags[s] = (unsigned)(hk[s].x >> 32); need[s] = false; }
+            else idx[s] = (idx[s] + 1) & tab.mask;
+          } else if (t == TAG_EMPTY) { need[s] = false; ins[s] = true; }
+          else if (t != TAG_LOCKED) idx[s] = (idx[s] + 1) & tab.mask;
+          pending |= need[s];
+        }
+        if (!__any_sync(0xffffffffu, pending)) break;
+      }
+      bool any_ins = false;
+#pragma unroll
+      for (int s = 0; s < G; s++) any_ins |= ins[s];
+      if (__any_sync(0xffffffffu, any_ins)) {                  // new keys: lane 0 of the gang inserts, then broadcasts
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+          unsigned long long sp = (unsigned long long)slot[s]; unsigned fl = flags[s]; bool inserted = false;
+          if (ins[s] && m == 0) {
             uint64_t kw[2] = {(uint64_t)key0[s], (uint64_t)key1[s]};
-            unsigned long long* p = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &ins);
+            unsigned long long* p = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &inserted);
             if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + s); }
             sp = (unsigned long long)p;
           }
-          { const unsigned b = __ballot_sync(0xffffffffu, ins); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }   // one counter update per warp step
+          { const unsigned b = __ballot_sync(0xffffffffu, inserted); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }   // one counter update per warp step
           if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
-          if (miss[s]) { slot[s] = (unsigned long long*)sp; flags[s] = fl; if (!sp) alive[s] = false; }
+          if (ins[s]) { slot[s] = (unsigned long long*)sp; flags[s] = fl; if (!sp) alive[s] = false; }
         }
       }
 #pragma unroll
