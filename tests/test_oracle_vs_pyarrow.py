@@ -1,0 +1,104 @@
+"""Differential check of the numpy oracle against an independent engine with the same Arrow null
+semantics (pyarrow.compute / Table.group_by) — the cross-check SURVEY.md §8c prescribes for the
+expression semantics the reference's own tests do not pin (parity unpinned there).  CPU only."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+from hypothesis import given, settings, strategies as st
+
+from blaze_b200 import exprs as E, types as T
+from oracle import blaze_oracle as O
+
+
+def _batch(seed, n, null_frac):
+    rng = np.random.default_rng(seed)
+    a = pa.array(rng.integers(-50, 50, n, dtype=np.int64), mask=rng.random(n) < null_frac)
+    b = pa.array(rng.integers(-2**62, 2**62, n, dtype=np.int64), mask=rng.random(n) < null_frac)
+    f = pa.array(rng.normal(0, 10, n), mask=rng.random(n) < null_frac)
+    p = pa.array(rng.random(n) < 0.5, mask=rng.random(n) < null_frac)
+    q = pa.array(rng.random(n) < 0.5, mask=rng.random(n) < null_frac)
+    return pa.RecordBatch.from_arrays([a, b, f, p, q], names=list("abfpq"))
+
+
+def _eq(col: O.Col, arr):
+    exp = O.col_from_arrow(arr)
+    assert np.array_equal(col.valid, exp.valid)
+    if col.dtype.is_float:
+        assert np.array_equal(col.values[col.valid].view(np.int64), exp.values[exp.valid].view(np.int64))
+    else:
+        assert np.array_equal(col.values[col.valid], exp.values[exp.valid])
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 10**6), n=st.integers(0, 300), nf=st.sampled_from([0.0, 0.3]))
+def test_expressions_match_pyarrow(seed, n, nf):
+    rb = _batch(seed, n, nf)
+    ob = O.batch_from_arrow(rb)
+    A, B, F, P, Q = (E.Column(c) for c in "abfpq")
+    a, b, f, p, q = (rb.column(i) for i in range(5))
+    cases = [
+        (E.BinaryExpr(A, "Plus", B), pc.add(a, b)),                     # wrapping
+        (E.BinaryExpr(B, "Minus", A), pc.subtract(b, a)),
+        (E.BinaryExpr(B, "Multiply", B), pc.multiply(b, b)),
+        (E.BinaryExpr(A, "Lt", B), pc.less(a, b)),
+        (E.BinaryExpr(A, "GtEq", E.Literal(3, T.int64)), pc.greater_equal(a, pa.scalar(3, pa.int64()))),
+        (E.BinaryExpr(P, "And", Q), pc.and_kleene(p, q)),
+        (E.BinaryExpr(P, "Or", Q), pc.or_kleene(p, q)),
+        (E.Not(P), pc.invert(p)),
+        (E.IsNull(A), pc.is_null(a)),
+        (E.IsNotNull(F), pc.is_valid(f)),
+        (E.BinaryExpr(F, "Multiply", F), pc.multiply(f, f)),
+        (E.BinaryExpr(F, "Divide", F), pc.divide(f, f)),
+        (E.Negative(A), pc.negate(a)),
+        (E.TryCast(A, T.float64), pc.cast(a, pa.float64())),
+        (E.TryCast(A, T.int8), pc.cast(a, pa.int8())),
+        (E.InList(A, [E.Literal(1, T.int64), E.Literal(-7, T.int64)]), pc.is_in(a, value_set=pa.array([1, -7], pa.int64())) if nf == 0 else None),
+        (E.Case(None, [(E.BinaryExpr(A, "Lt", E.Literal(0, T.int64)), B)], A), pc.if_else(pc.fill_null(pc.less(a, pa.scalar(0, pa.int64())), False), b, a)),
+    ]
+    for expr, exp in cases:
+        if exp is None:
+            continue
+        _eq(O.evaluate(expr, ob).broadcast(n), exp)
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 400), nf=st.sampled_from([0.0, 0.25]), thr=st.integers(-60, 60))
+def test_filter_matches_pyarrow(seed, n, nf, thr):
+    rb = _batch(seed, n, nf)
+    ob = O.batch_from_arrow(rb)
+    preds = [E.BinaryExpr(E.Column("a"), "Lt", E.Literal(thr, T.int64)), E.Column("p")]
+    out = O.filter_batch(preds, ob)
+    mask = pc.and_kleene(pc.less(rb.column(0), pa.scalar(thr, pa.int64())), rb.column(3))
+    exp = rb.filter(mask, null_selection_behavior="drop")
+    assert out.num_rows == exp.num_rows
+    for i in range(rb.num_columns):
+        _eq(out.cols[i], exp.column(i))
+
+
+@settings(max_examples=10, deadline=None)
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 2000), nf=st.sampled_from([0.0, 0.3]))
+def test_group_by_matches_pyarrow(seed, n, nf):
+    rb = _batch(seed, n, nf)
+    ob = O.batch_from_arrow(rb)
+    ins = ob.schema
+    g = [E.GroupingExpr("a", E.Column("a"))]
+    mk = lambda mode, ch: [E.AggExpr("s", mode, E.AggFunctionExpr(E.AGG_SUM, ch(T.int64, "b"), T.int64)),
+                           E.AggExpr("c", mode, E.AggFunctionExpr(E.AGG_COUNT, ch(T.int64, "b"), T.int64)),
+                           E.AggExpr("mn", mode, E.AggFunctionExpr(E.AGG_MIN, ch(T.int64, "b"), T.int64)),
+                           E.AggExpr("mx", mode, E.AggFunctionExpr(E.AGG_MAX, ch(T.float64, "f"), T.float64))]
+    part = O.AggExec(E.HASH_AGG, g, mk(E.PARTIAL, lambda t, c: [E.Column(c)]), False, ins)
+    fin = O.AggExec(E.HASH_AGG, g, mk(E.FINAL, lambda t, c: [E.placeholder(t)]), False, part.schema)
+    out = O.concat_batches(fin.schema, fin.execute(part.execute([ob])))
+    tbl = pa.Table.from_batches([rb]).group_by("a", use_threads=False).aggregate([("b", "sum"), ("b", "count"), ("b", "min"), ("f", "max")])
+    exp = {r["a"]: (r["b_sum"], r["b_count"], r["b_min"], r["f_max"]) for r in tbl.to_pylist()}
+    got = {}
+    for i in range(out.num_rows):
+        vals = [None if not c.valid[i] else c.values[i].item() for c in out.cols]
+        got[vals[0]] = tuple(vals[1:])
+    assert got.keys() == exp.keys()
+    for k in exp:
+        es, ec, emn, emx = exp[k]
+        gs, gc, gmn, gmx = got[k]
+        # pyarrow's hash sum is checked-free wrapping like the reference's; all-null groups are NULL on both sides
+        assert gc == ec and gmn == emn and gmx == emx
+        assert gs == (None if es is None else ((es + 2**63) % 2**64) - 2**63)
