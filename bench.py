@@ -259,8 +259,16 @@ def run_ours(args):
     launches = max(1, stats["hot_launches"])
     alg_bytes_per_launch = (ALG_BYTES_PER_ROW * stats["hot_rows"] + ALG_BYTES_PER_GROUP * stats["groups"] * args.steps) / launches
     achieved = (ALG_BYTES_PER_ROW * stats["hot_rows"]) / max(1, stats["hot_ns"])        # bytes/ns == GB/s
+    traffic = None
+    try:   # DRAM bytes of one launch of the same kernel/size from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        rows_per_launch = stats["hot_rows"] / launches
+        if abs(rows_per_launch - tj["rows_per_launch"]) / tj["rows_per_launch"] < 0.1:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "agg_update", "launches": stats["hot_launches"],
+                "traffic": traffic, "kernel": "agg_update", "launches": stats["hot_launches"],
                 "avg_launch_ms": stats["hot_ns"] / launches / 1e6, "alg_bytes_per_launch": alg_bytes_per_launch}
     # ---- CPU baseline (restatement of the reference algorithm) on this box's host cores --------------------
     cpu = None

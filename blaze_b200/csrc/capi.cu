@@ -339,6 +339,7 @@ static void staging_append(b200q_op* op, const ArrowArray* batch) {
 // ---- stage driver ----------------------------------------------------------------------------------------
 static void run_stages(b200q_op* op, DevBatch& b, size_t from) {
   std::vector<DevBatch> outs;
+  op->cx.cur_stage = (int)from;
   op->stages[from]->push(op->cx, b, outs);
   for (auto& o : outs) {
     if (from + 1 < op->stages.size()) run_stages(op, o, from + 1);
@@ -590,6 +591,7 @@ b200q_status b200q_op_finish(b200q_op* op) {
     if (op->staging_ready) staging_flush(op);
     for (size_t i = 0; i < op->stages.size(); i++) {
       std::vector<DevBatch> outs;
+      op->cx.cur_stage = (int)i;
       op->stages[i]->finish(op->cx, outs);
       for (auto& o : outs) {
         if (i + 1 < op->stages.size()) run_stages(op, o, i + 1);

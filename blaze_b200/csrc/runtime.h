@@ -73,6 +73,7 @@ struct OpContext {
   b200q_conf conf;
   Metrics m;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // timing of the dominant kernel on `stream`
+  int cur_stage = 0;                          // hot_kernel_* metrics describe stage 0 (the stage that sees the input rows)
 };
 
 class Stage {

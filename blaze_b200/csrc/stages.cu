@@ -137,7 +137,7 @@ class FilterProjectStage : public Stage {
     unsigned long long h[4];
     B200Q_CUDA(cudaMemcpyAsync(h, scratch->ptr, 32, cudaMemcpyDeviceToHost, cx.stream));
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-    { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.hot_ms += ms; cx.m.gpu_ms += ms; cx.m.hot_rows += n; cx.m.hot_launches++; }
+    { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; if (cx.cur_stage == 0) { cx.m.hot_ms += ms; cx.m.hot_rows += n; cx.m.hot_launches++; } }
     check_device_error_flags((int)h[2]);
     ob.num_rows = (int64_t)h[1];
     if (ob.num_rows > 0) outs.push_back(std::move(ob));       // sender.send drops empty batches (execution_context.rs:713-716)
@@ -649,7 +649,7 @@ class AggStage : public Stage {
       B200Q_CUDA(cudaGetLastError());
       unsigned long long h[3];
       read_counters(cx, h);
-      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.hot_ms += ms; cx.m.gpu_ms += ms; cx.m.hot_rows += m; cx.m.hot_launches++; }
+      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; if (cx.cur_stage == 0) { cx.m.hot_ms += ms; cx.m.hot_rows += m; cx.m.hot_launches++; } }
       int cur = 0;
       while (h[1] > 0) {
         // the table hit its load limit: grow it, then replay only the rows that could not be inserted
