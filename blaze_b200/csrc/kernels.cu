@@ -173,8 +173,10 @@ static int grid_for(int64_t ntiles, int per_sm);
 // a column or `column op column|literal`.  Loads are striped (row = r*256 + tid): perfectly coalesced, and the
 // survivors of a warp-row are written to consecutive positions.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FL_R = 16;                         // rows per lane: a warp owns a tile of 512 rows
-constexpr int FL_TILE = 32 * FL_R;
+constexpr int FL_BLOCK = 128;                    // small CTAs: more of them resident per SM to overlap the per-tile barriers
+constexpr int FL_NW = FL_BLOCK / 32;
+constexpr int FL_R = 16;                         // 2048 rows per tile
+constexpr int FL_TILE = FL_BLOCK * FL_R;
 int64_t filter_project_lean_num_tiles(int64_t n) { return (n + FL_TILE - 1) / FL_TILE; }
 struct LeanOutPtrs { long long* p[8]; };
 
@@ -182,78 +184,86 @@ __device__ __forceinline__ bool lean_cmp(int op, long long a, long long b) {
   switch (op) { case CMP_EQ: return a == b; case CMP_NE: return a != b; case CMP_LT: return a < b; case CMP_LE: return a <= b; case CMP_GT: return a > b; default: return a >= b; }
 }
 
-// Every WARP is autonomous: it takes a tile ticket, evaluates the conjuncts, gets the survivor counts of its 16
-// warp-rows from ballots (warp-uniform, so no shared memory and no __syncthreads anywhere), performs the
-// decoupled look-back with its 32 lanes and writes its survivors.  Barrier stalls were as large as the memory
-// stalls in the block-wide version (profiles/r01_ncu_lean_kernels.txt).
-__global__ void __launch_bounds__(FP_BLOCK) filter_project_lean_kernel(const ColTable cols, const LeanFpSpec sp, const LeanOutPtrs outs,
+__global__ void __launch_bounds__(FL_BLOCK) filter_project_lean_kernel(const ColTable cols, const LeanFpSpec sp, const LeanOutPtrs outs,
                                                                        long long n, long long ntiles, unsigned long long* tile_status, unsigned long long* scratch) {
-  const unsigned lane = threadIdx.x & 31;
+  __shared__ long long s_tile, s_excl;
+  __shared__ unsigned s_cnt[FL_R * FL_NW], s_off[FL_R * FL_NW];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
   while (true) {
-    long long tile = 0;
-    if (lane == 0) tile = (long long)atomicAdd(scratch + 0, 1ULL);       // ticket: lower tiles are always already running
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(scratch + 0, 1ULL);       // ticket: lower tiles are always already running
+    __syncthreads();
+    const long long tile = s_tile;
     if (tile >= ntiles) break;
-    const long long row0 = tile * FL_TILE + lane;
+    const long long row0 = tile * FL_TILE + threadIdx.x;
     bool alive[FL_R];
 #pragma unroll
-    for (int r = 0; r < FL_R; r++) alive[r] = row0 + r * 32 < n;
+    for (int r = 0; r < FL_R; r++) alive[r] = row0 + r * FL_BLOCK < n;
     for (int f = 0; f < sp.nfilt; f++) {
       const long long* c = (const long long*)cols.col[sp.filt[f].col].values;
       long long x[FL_R];
 #pragma unroll
-      for (int r = 0; r < FL_R; r++) x[r] = row0 + r * 32 < n ? __ldg(c + row0 + r * 32) : 0;
+      for (int r = 0; r < FL_R; r++) x[r] = row0 + r * FL_BLOCK < n ? __ldg(c + row0 + r * FL_BLOCK) : 0;
 #pragma unroll
       for (int r = 0; r < FL_R; r++) alive[r] = alive[r] && lean_cmp(sp.filt[f].op, x[r], sp.filt[f].lit);
     }
-    unsigned amask[FL_R]; unsigned total = 0;
+    unsigned amask[FL_R];
 #pragma unroll
-    for (int r = 0; r < FL_R; r++) { amask[r] = __ballot_sync(0xffffffffu, alive[r]); total += __popc(amask[r]); }
-    unsigned long long excl = 0;
-    if (sp.nfilt == 0) excl = (unsigned long long)tile * FL_TILE;          // nothing filtered: positions are the row numbers
-    else if (tile > 0) {
-      if (lane == 0) st_relaxed_u64(tile_status + tile, ST_AGG | total);
-      long long j = tile - 1;
-      while (true) {
-        const long long idx = j - lane;
-        unsigned long long st = idx >= 0 ? ld_relaxed_u64(tile_status + idx) : ST_PREFIX;
-        if (__any_sync(0xffffffffu, (st >> 62) == 0)) continue;            // a predecessor has not published yet
-        const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-        unsigned long long val = st & ST_VALUE;
-        if (pm) { const int first = __ffs(pm) - 1; if ((int)lane > first) val = 0; }
+    for (int r = 0; r < FL_R; r++) { amask[r] = __ballot_sync(0xffffffffu, alive[r]); if (lane == 0) s_cnt[r * FL_NW + warp] = __popc(amask[r]); }
+    __syncthreads();
+    if (warp == 0) {
+      static_assert(FL_R * FL_NW == 64, "the warp scan below handles two warp-rows per lane");
+      const unsigned v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1], v = v0 + v1;
+      unsigned incl = v;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-        excl += val;
-        if (pm) break;
-        j -= 32;
+      for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      s_off[2 * lane] = incl - v; s_off[2 * lane + 1] = incl - v + v0;
+      const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long excl = 0;
+      if (sp.nfilt == 0) excl = (unsigned long long)tile * FL_TILE;        // nothing filtered: positions are the row numbers
+      else if (tile > 0) {
+        if (lane == 0) st_relaxed_u64(tile_status + tile, ST_AGG | total);
+        long long j = tile - 1;
+        while (true) {
+          const long long idx = j - lane;
+          unsigned long long st = idx >= 0 ? ld_relaxed_u64(tile_status + idx) : ST_PREFIX;
+          if (__any_sync(0xffffffffu, (st >> 62) == 0)) continue;
+          const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+          unsigned long long val = st & ST_VALUE;
+          if (pm) { const int first = __ffs(pm) - 1; if ((int)lane > first) val = 0; }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+          excl += val;
+          if (pm) break;
+          j -= 32;
+        }
+      }
+      if (lane == 0) {
+        if (sp.nfilt) st_relaxed_u64(tile_status + tile, ST_PREFIX | (excl + total));
+        s_excl = (long long)excl;
+        if (tile == ntiles - 1) scratch[1] = excl + total;
       }
     }
-    if (lane == 0) {
-      if (sp.nfilt) st_relaxed_u64(tile_status + tile, ST_PREFIX | (excl + total));
-      if (tile == ntiles - 1) scratch[1] = excl + total;
-    }
+    __syncthreads();
     for (int o = 0; o < sp.nout; o++) {
       const int kind = sp.out[o].kind;
       const long long* ca = (const long long*)cols.col[sp.out[o].a].values;
       const long long* cb = sp.out[o].b >= 0 ? (const long long*)cols.col[sp.out[o].b].values : nullptr;
       long long* dst = outs.p[o];
-      unsigned long long pos = excl;
 #pragma unroll
       for (int r = 0; r < FL_R; r++) {
-        if (alive[r]) {
-          const long long a = __ldg(ca + row0 + r * 32);
-          long long v = a;
-          if (kind) {
-            const long long b = cb ? __ldg(cb + row0 + r * 32) : sp.out[o].lit;
-            v = kind == 1 ? (long long)((unsigned long long)a + (unsigned long long)b) : kind == 2 ? (long long)((unsigned long long)a - (unsigned long long)b)
-                                                                                         : (long long)((unsigned long long)a * (unsigned long long)b);
-          }
-          dst[pos + __popc(amask[r] & lt)] = v;
+        if (!alive[r]) continue;
+        const long long a = __ldg(ca + row0 + r * FL_BLOCK);
+        long long v = a;
+        if (kind) {
+          const long long b = cb ? __ldg(cb + row0 + r * FL_BLOCK) : sp.out[o].lit;
+          v = kind == 1 ? (long long)((unsigned long long)a + (unsigned long long)b) : kind == 2 ? (long long)((unsigned long long)a - (unsigned long long)b)
+                                                                                       : (long long)((unsigned long long)a * (unsigned long long)b);
         }
-        pos += __popc(amask[r]);
+        dst[s_excl + s_off[r * FL_NW + warp] + __popc(amask[r] & lt)] = v;
       }
     }
+    __syncthreads();
   }
 }
 
@@ -262,7 +272,7 @@ int launch_filter_project_lean(const ColTable& cols, const LeanFpSpec& sp, long 
   const int64_t ntiles = filter_project_lean_num_tiles(n);
   if (ntiles == 0) return 0;
   LeanOutPtrs op{}; for (int i = 0; i < sp.nout; i++) op.p[i] = out_values[i];
-  filter_project_lean_kernel<<<grid_for((ntiles + 7) / 8, 8), FP_BLOCK, 0, s>>>(cols, sp, op, n, ntiles, d_tile_status, d_scratch);
+  filter_project_lean_kernel<<<grid_for(ntiles, 12), FL_BLOCK, 0, s>>>(cols, sp, op, n, ntiles, d_tile_status, d_scratch);
   return 1;
 }
 

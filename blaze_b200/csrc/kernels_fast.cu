@@ -297,120 +297,107 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
 
 // ---------------------------------------------------------------------------------------------------
 // LEAN hashed kernel: 1-2 non-null int64 keys, non-null int64 accumulator/filter columns (same preconditions
-// as the lean dense kernel).  Per row: one 16-byte probe + one sector of REDs; the lanes of a gang (G = number
-// of accumulators) probe the same slot (one LSU access) and update its G accumulator words together.
+// as the lean dense kernel).  One row per lane (the hash + probe work is done once per row); with two
+// accumulators the two words of a row are still updated by ONE instruction: neighbouring lanes exchange their
+// slot pointer / second operand with one shuffle pair and lane L updates acc0 of its own row while lane L^1
+// updates acc1 of the same row (step 1: rows of even lanes, step 2: rows of odd lanes).
 // ---------------------------------------------------------------------------------------------------
 template <int NK, int NACC>
 __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                  long long row_begin, long long n) {
-  constexpr int G = NACC;                                      // 1 or 2
-  constexpr int U = G == 2 ? 2 : 4;                             // 4 rows per lane in flight
-  const unsigned lane = threadIdx.x & 31, m = lane % G, gl = lane - m;
+  constexpr int U = 4;                                          // rows per lane in flight
+  const unsigned lane = threadIdx.x & 31;
+  const bool odd = lane & 1;
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
   const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
-  const bool is_add = fs.acc[m].kind == FAST_ACC_ADD;
-  const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[m].col].values + row_begin : nullptr;
-  const int acc_word = fs.acc[m].word, acc_vbit = fs.acc[m].vbit;
-  unsigned long long* const sink = warp_sink(fs, gwarp, m);
+  const long long* vcol0 = fs.acc[0].kind == FAST_ACC_ADD ? (const long long*)cols.col[fs.acc[0].col].values + row_begin : nullptr;
+  const long long* vcol1 = (NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD) ? (const long long*)cols.col[fs.acc[1].col].values + row_begin : nullptr;
+  const int w0 = fs.acc[0].word, w1 = NACC == 2 ? fs.acc[1].word : 0;
+  unsigned long long* const sink = warp_sink(fs, gwarp, lane);
   const uint64_t mask = tab.mask; const int sw = lay.slot_words;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    i64xG<G> k0[U], k1[U], v[U]; bool alive[U][G];
+    long long k0[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const long long rel0 = (unit0 + u) * (32 / G) * G + gl;   // = (unit0+u)*32 + gl
-      k0[u] = ld_rows<G>(kcol0, rel0, n);
-      if (NK == 2) k1[u] = ld_rows<G>(kcol1, rel0, n);
-      if (is_add) v[u] = ld_rows<G>(vcol, rel0, n);
-      else {
-#pragma unroll
-        for (int s = 0; s < G; s++) v[u].v[s] = 1;
-      }
-#pragma unroll
-      for (int s = 0; s < G; s++) alive[u][s] = rel0 + s < n;
+      const long long rel = (unit0 + u) * 32 + lane;
+      alive[u] = rel < n;
+      k0[u] = alive[u] ? ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      k1[u] = (NK == 2 && alive[u]) ? ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      v0[u] = (vcol0 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol0 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
+      v1[u] = (vcol1 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol1 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
     }
     for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
       const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const i64xG<G> x = ld_rows<G>(fcol, (unit0 + u) * 32 + gl, n);
-#pragma unroll
-        for (int s = 0; s < G; s++) alive[u][s] = alive[u][s] && cmp_apply(fs.filt[f].op, x.v[s], fs.filt[f].lit);
+        const long long rel = (unit0 + u) * 32 + lane;
+        const long long x = rel < n ? ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0] : 0;
+        alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
       }
     }
-    // probe walk: every pending row of every lane advances one slot per round (the lanes of a gang compute the
-    // same thing, so they stay in lockstep without communicating).  Collisions are common at load 0.5 (~25 % of
-    // first probes), so the walk must not serialise the warp; only genuinely NEW keys take the insert section.
-    unsigned long long* slot[U][G]; uint64_t h[U][G], idx[U][G]; unsigned flags[U][G]; bool need[U][G], ins[U][G];
+    // probe walk: every pending row advances one slot per round; collisions are common at load 0.5 (~25 % of the
+    // first probes) so the walk is lane-parallel; only genuinely NEW keys take the insert section
+    unsigned long long* slot[U]; uint64_t h[U], idx[U]; unsigned flags[U]; bool need[U], ins[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-#pragma unroll
-      for (int s = 0; s < G; s++) {
-        h[u][s] = agg_hash2((uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL, 0);
-        idx[u][s] = h[u][s] & mask; need[u][s] = alive[u][s]; ins[u][s] = false; slot[u][s] = nullptr; flags[u][s] = 0;
-      }
+      h[u] = agg_hash2((uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL, 0);
+      idx[u] = h[u] & mask; need[u] = alive[u]; ins[u] = false; slot[u] = nullptr; flags[u] = 0;
     }
     while (true) {
-      ulonglong2 hk[U][G];
+      ulonglong2 hk[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-#pragma unroll
-        for (int s = 0; s < G; s++) if (need[u][s]) hk[u][s] = ld_relaxed_v2u64(tab.slots + idx[u][s] * (uint64_t)sw);   // {hdr, key0}: one 16-byte probe
-      }
+      for (int u = 0; u < U; u++) if (need[u]) hk[u] = ld_relaxed_v2u64(tab.slots + idx[u] * (uint64_t)sw);     // {hdr, key0}: one 16-byte probe
       bool pending = false;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-          if (!need[u][s]) continue;
-          const unsigned tag = (unsigned)(h[u][s] >> 32) | 0x80000000u, t = (unsigned)hk[u][s].x;
-          unsigned long long* sp = tab.slots + idx[u][s] * (uint64_t)sw;
-          if (t == tag) {
-            bool hit = (unsigned)(hk[u][s].x >> 48) == 0 && hk[u][s].y == (uint64_t)k0[u].v[s];
-            if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)k1[u].v[s];
-            if (hit) { slot[u][s] = sp; flags[u][s] = (unsigned)(hk[u][s].x >> 32); need[u][s] = false; }
-            else idx[u][s] = (idx[u][s] + 1) & mask;
-          } else if (t == TAG_EMPTY) { need[u][s] = false; ins[u][s] = true; }
-          else if (t != TAG_LOCKED) idx[u][s] = (idx[u][s] + 1) & mask;      // occupied by another key: next slot (locked: look again)
-          pending |= need[u][s];
-        }
+        if (!need[u]) continue;
+        const unsigned tag = (unsigned)(h[u] >> 32) | 0x80000000u, t = (unsigned)hk[u].x;
+        unsigned long long* sp = tab.slots + idx[u] * (uint64_t)sw;
+        if (t == tag) {
+          bool hit = (unsigned)(hk[u].x >> 48) == 0 && hk[u].y == (uint64_t)k0[u];
+          if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)k1[u];
+          if (hit) { slot[u] = sp; flags[u] = (unsigned)(hk[u].x >> 32); need[u] = false; }
+          else idx[u] = (idx[u] + 1) & mask;
+        } else if (t == TAG_EMPTY) { need[u] = false; ins[u] = true; }
+        else if (t != TAG_LOCKED) idx[u] = (idx[u] + 1) & mask;             // another key: next slot (locked: look again)
+        pending |= need[u];
       }
       if (!__any_sync(0xffffffffu, pending)) break;
     }
     bool any_ins = false;
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-#pragma unroll
-      for (int s = 0; s < G; s++) any_ins |= ins[u][s];
-    }
-    if (__any_sync(0xffffffffu, any_ins)) {                     // new keys: lane 0 of the gang inserts, then broadcasts the slot
+    for (int u = 0; u < U; u++) any_ins |= ins[u];
+    if (__any_sync(0xffffffffu, any_ins)) {                     // new keys: full insert protocol, one counter update per warp step
 #pragma unroll
       for (int u = 0; u < U; u++) {
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-          unsigned long long sp = (unsigned long long)slot[u][s]; unsigned fl = flags[u][s]; bool inserted = false;
-          if (ins[u][s] && m == 0) {
-            uint64_t kw[2] = {(uint64_t)k0[u].v[s], NK == 2 ? (uint64_t)k1[u].v[s] : 0ULL};
-            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, h[u][s], &fl, &inserted);
-            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + gl + s); }
-            sp = (unsigned long long)p;
-          }
-          { const unsigned b = __ballot_sync(0xffffffffu, inserted); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }
-          if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
-          if (ins[u][s]) { slot[u][s] = (unsigned long long*)sp; flags[u][s] = fl; if (!sp) alive[u][s] = false; }
+        bool inserted = false;
+        if (ins[u]) {
+          uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
+          slot[u] = agg_find_or_insert(lay, tab, kw, 0, h[u], &flags[u], &inserted);
+          if (!slot[u]) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); alive[u] = false; }
         }
+        const unsigned b = __ballot_sync(0xffffffffu, inserted);
+        if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
       }
     }
+    // accumulate (REDs unconditional: idle lanes add 0 to the warp's sink sector)
 #pragma unroll
     for (int u = 0; u < U; u++) {
-#pragma unroll
-      for (int s = 0; s < G; s++) {
-        const bool pred = alive[u][s];
-        red_add_u64(pred ? slot[u][s] + acc_word : sink, pred ? (unsigned long long)v[u].v[s] : 0ULL);
-        if (pred) slot_mark(slot[u][s], flags[u][s], acc_vbit);
+      const bool live = alive[u] && slot[u] != nullptr;
+      if (NACC == 1) {
+        red_add_u64(live ? slot[u] + w0 : sink, live ? v0[u] : 0ULL);
+      } else {
+        const unsigned long long ps = __shfl_xor_sync(0xffffffffu, live ? (unsigned long long)slot[u] : 0ULL, 1);
+        const unsigned long long pv1 = __shfl_xor_sync(0xffffffffu, v1[u], 1);
+        unsigned long long* const mine = live ? slot[u] + w0 : sink;  const unsigned long long mv = live ? v0[u] : 0ULL;
+        unsigned long long* const theirs = ps ? (unsigned long long*)ps + w1 : sink;  const unsigned long long tv = ps ? pv1 : 0ULL;
+        red_add_u64(odd ? theirs : mine, odd ? tv : mv);        // step 1: rows of even lanes: {acc0 by the owner, acc1 by its odd neighbour}
+        red_add_u64(odd ? mine : theirs, odd ? mv : tv);        // step 2: rows of odd lanes
       }
+      if (live) { slot_mark(slot[u], flags[u], fs.acc[0].vbit); if (NACC == 2) slot_mark(slot[u], flags[u], fs.acc[1].vbit); }
     }
   }
 }
