@@ -105,6 +105,8 @@ template <class F>
 static b200q_status guarded(b200q_op* op, F&& f) {
   try {
     if (op && op->sticky_code) return fail(op->sticky_code, op->sticky_error);
+    cudaGetLastError();      // drop stale (non-sticky) error state left by other CUDA users of this thread (torch, NCCL): our
+                             // launch checks must only see our own launches
     f();
     return B200Q_OK;
   } catch (const PlanError& e) { return fail(e.code, e.what());
