@@ -95,6 +95,7 @@ struct b200q_op {
   std::vector<PendingRelease> pending;
   StagingSet staging[2]; int cur_stage_set = 0; bool staging_ready = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  std::shared_ptr<StreamRef> stream_ref;
 };
 
 namespace b200q {
@@ -503,7 +504,8 @@ b200q_status b200q_op_create(const uint8_t* plan, size_t plan_len, int32_t plan_
       cudaMemPool_t pool; unsigned long long keep = ~0ULL;
       if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    B200Q_CUDA(cudaStreamCreateWithFlags(&op->cx.stream, cudaStreamNonBlocking));
+    op->stream_ref = stream_ref_create(device);
+    op->cx.stream = op->stream_ref->s;
     B200Q_CUDA(cudaEventCreate(&op->cx.ev0)); B200Q_CUDA(cudaEventCreate(&op->cx.ev1));
     build_pipeline(op);
     if (input_schema) {
@@ -513,7 +515,7 @@ b200q_status b200q_op_create(const uint8_t* plan, size_t plan_len, int32_t plan_
           throw PlanError(B200Q_ERR_INVALID_ARG, "input_schema does not match the plan leaf: type of column " + std::to_string(i));
     }
   });
-  if (st != B200Q_OK) { if (op) { if (op->cx.stream) cudaStreamDestroy(op->cx.stream); delete op; } return st; }
+  if (st != B200Q_OK) { if (op) { op->stages.clear(); delete op; } return st; }
   *out = op;
   return B200Q_OK;
 }
@@ -670,8 +672,8 @@ void b200q_op_destroy(b200q_op* op) {
   staging_free(op);
   if (op->cx.ev0) cudaEventDestroy(op->cx.ev0);
   if (op->cx.ev1) cudaEventDestroy(op->cx.ev1);
-  if (op->cx.stream) { cudaStreamSynchronize(op->cx.stream); cudaStreamDestroy(op->cx.stream); }
-  delete op;
+  if (op->cx.stream) cudaStreamSynchronize(op->cx.stream);
+  delete op;                     // the stream itself goes away with the last allocation that references it
 }
 
 b200q_status b200q_murmur3_partition(const struct ArrowSchema* key_schema, const struct ArrowDeviceArray* keys, int32_t num_partitions,

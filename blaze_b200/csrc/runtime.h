@@ -33,6 +33,15 @@ struct ExecError : std::runtime_error {
     if (_e != cudaSuccess) throw ::b200q::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));      \
   } while (0)
 
+// The op's CUDA stream outlives the op while exported device arrays still reference allocations made on it
+// (their release frees stream-ordered memory): the stream is destroyed when the last reference goes away.
+struct StreamRef {
+  cudaStream_t s = nullptr; int device = 0;
+  ~StreamRef();
+};
+std::shared_ptr<StreamRef> stream_ref_create(int device);
+std::shared_ptr<StreamRef> stream_ref_lookup(cudaStream_t s);
+
 // a device allocation (stream-ordered) or a borrowed device pointer kept alive by `owner`
 struct DevMem {
   void* ptr = nullptr;
@@ -40,6 +49,7 @@ struct DevMem {
   cudaStream_t stream = nullptr;
   bool owned = false;
   std::shared_ptr<void> owner;
+  std::shared_ptr<StreamRef> stream_keep;
   ~DevMem();
   static std::shared_ptr<DevMem> alloc(size_t bytes, cudaStream_t s, bool zero = false);
   static std::shared_ptr<DevMem> borrow(const void* p, size_t bytes, std::shared_ptr<void> owner);

@@ -1,6 +1,8 @@
 // Stage implementations: FilterProjectStage and AggStage (see runtime.h).
 #include <algorithm>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "runtime.h"
 #include "kernels_fast.cuh"
@@ -8,12 +10,34 @@
 namespace b200q {
 
 // ---------------------------------------------------------------------------------------------------
+static std::mutex g_stream_mu;
+static std::unordered_map<cudaStream_t, std::weak_ptr<StreamRef>> g_streams;
+
+StreamRef::~StreamRef() {
+  { std::lock_guard<std::mutex> l(g_stream_mu); g_streams.erase(s); }
+  if (s) { cudaSetDevice(device); cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+}
+std::shared_ptr<StreamRef> stream_ref_create(int device) {
+  auto r = std::make_shared<StreamRef>(); r->device = device;
+  B200Q_CUDA(cudaStreamCreateWithFlags(&r->s, cudaStreamNonBlocking));
+  std::lock_guard<std::mutex> l(g_stream_mu); g_streams[r->s] = r;
+  return r;
+}
+std::shared_ptr<StreamRef> stream_ref_lookup(cudaStream_t s) {
+  std::lock_guard<std::mutex> l(g_stream_mu);
+  auto it = g_streams.find(s);
+  return it == g_streams.end() ? nullptr : it->second.lock();
+}
+
 DevMem::~DevMem() {
-  if (owned && ptr) cudaFreeAsync(ptr, stream);
+  if (owned && ptr) {
+    if (stream_keep) { cudaSetDevice(stream_keep->device); cudaFreeAsync(ptr, stream_keep->s); }
+    else cudaFree(ptr);
+  }
 }
 DevMemP DevMem::alloc(size_t bytes, cudaStream_t s, bool zero) {
   auto m = std::make_shared<DevMem>();
-  m->bytes = bytes; m->stream = s; m->owned = true;
+  m->bytes = bytes; m->stream = s; m->owned = true; m->stream_keep = stream_ref_lookup(s);
   if (bytes == 0) bytes = 16;
   B200Q_CUDA(cudaMallocAsync(&m->ptr, bytes, s));
   if (zero) B200Q_CUDA(cudaMemsetAsync(m->ptr, 0, bytes, s));
