@@ -44,44 +44,51 @@ __device__ __forceinline__ uint64_t agg_hash_words(const uint64_t* kw, int nkw, 
   return mix64(x + (uint64_t)knull * 0xA0761D6478BD642FULL);
 }
 
-__device__ __forceinline__ void slot_mark(unsigned long long* slot, unsigned flags_seen, int vbit) {
-  if (vbit != 0xFF && !((flags_seen >> vbit) & 1)) atomicOr((unsigned*)slot + 1, 1u << vbit);
+// set an accumulator-valid bit in the key entry's header (only when the copy we saw did not have it yet)
+__device__ __forceinline__ void slot_mark(unsigned long long* key_entry, unsigned flags_seen, int vbit) {
+  if (vbit != 0xFF && !((flags_seen >> vbit) & 1)) atomicOr((unsigned*)key_entry + 1, 1u << vbit);
 }
 
-// Returns the slot of the key (inserting it if absent) or nullptr when the table is at its load limit and
-// the row must be deferred.  *flags = the slot's flags word as last seen (may be stale: only used to skip
-// redundant validity marking).  `s` = first slot index to probe.
-__device__ __forceinline__ unsigned long long* agg_find_or_insert(const AggLayout& lay, const AggTable& tab, const uint64_t* kw, uint32_t knull,
-                                                                   uint64_t h, unsigned* flags_out, bool* inserted) {
-  const unsigned tag = (unsigned)(h >> 32) | 0x80000000u;
-  uint64_t s = h & tab.mask;
+__device__ __forceinline__ uint64_t agg_first_slot(uint64_t h, uint64_t capacity) { return __umul64hi(h, capacity); }
+__device__ __forceinline__ unsigned agg_tag(uint64_t h) { return (unsigned)h | 0x80000000u; }
+__device__ __forceinline__ uint64_t agg_next_slot(uint64_t s, uint64_t capacity) { return s + 1 == capacity ? 0 : s + 1; }
+constexpr uint64_t AGG_NO_SLOT = ~0ULL;
+
+// Returns the slot number of the key (inserting it if absent) or AGG_NO_SLOT when the table is at its load limit
+// and the row must be deferred.  *flags = the slot's flags word as last seen (may be stale: only used to skip
+// redundant validity marking).
+__device__ __forceinline__ uint64_t agg_find_or_insert(const AggLayout& lay, const AggTable& tab, const uint64_t* kw, uint32_t knull,
+                                                       uint64_t h, unsigned* flags_out, bool* inserted) {
+  const unsigned tag = agg_tag(h);
+  uint64_t s = agg_first_slot(h, tab.capacity);
   while (true) {
-    unsigned long long* slot = tab.slots + s * (uint64_t)lay.slot_words;
-    const unsigned long long hdr = ld_relaxed_u64(slot);
+    unsigned long long* ke = tab.keys + s * (uint64_t)lay.kstride;
+    const unsigned long long hdr = ld_relaxed_u64(ke);
     const unsigned t = (unsigned)hdr;
     unsigned flags = (unsigned)(hdr >> 32);
     if (t == tag) {
       bool eq = (flags >> 16) == knull;
-      for (int i = 0; eq && i < lay.nkw; i++) eq = ld_relaxed_u64(slot + 1 + i) == kw[i];
-      if (eq) { *flags_out = flags; return slot; }
+      for (int i = 0; eq && i < lay.nkw; i++) eq = ld_relaxed_u64(ke + 1 + i) == kw[i];
+      if (eq) { *flags_out = flags; return s; }
     } else if (t == TAG_EMPTY) {
-      if (ld_relaxed_u64(tab.counters) >= tab.max_groups) return nullptr;       // at the load limit: defer the row
-      if (atomicCAS((unsigned*)slot, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
-        for (int i = 0; i < lay.nkw; i++) slot[1 + i] = kw[i];
-        for (int i = 1 + lay.nkw; i < lay.slot_words; i++) slot[i] = lay.init[i];
+      if (ld_relaxed_u64(tab.counters) >= tab.max_groups) return AGG_NO_SLOT;   // at the load limit: defer the row
+      if (atomicCAS((unsigned*)ke, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
+        for (int i = 0; i < lay.nkw; i++) ke[1 + i] = kw[i];
+        unsigned long long* ae = tab.accs + s * (uint64_t)lay.astride;
+        for (int i = 0; i < lay.astride; i++) ae[i] = lay.init[i];
         flags = lay.init_flags | (knull << 16);
-        ((unsigned*)slot)[1] = flags;
+        ((unsigned*)ke)[1] = flags;
         __threadfence();
-        st_release_u32((unsigned*)slot, tag);
+        st_release_u32((unsigned*)ke, tag);
         *inserted = true;            // the caller adds to tab.counters[0] (warp-aggregated where it can)
         *flags_out = flags;
-        return slot;
+        return s;
       }
       continue;                                                                 // lost the race: look at the same slot again
     } else if (t == TAG_LOCKED) {
       continue;                                                                 // being published by another thread
     }
-    s = (s + 1) & tab.mask;
+    s = agg_next_slot(s, tab.capacity);
   }
 }
 

@@ -307,11 +307,11 @@ __device__ __forceinline__ uint64_t hash_keys(const AggLayout& lay, const uint64
   return agg_hash_words(kw, w, knull);
 }
 
-__device__ __forceinline__ void dec_minmax(unsigned long long* slot, int word, i128_t v, bool is_min) {
-  unsigned* flags = (unsigned*)slot + 1;
+__device__ __forceinline__ void dec_minmax(unsigned long long* key_entry, unsigned long long* acc_word, i128_t v, bool is_min) {
+  unsigned* flags = (unsigned*)key_entry + 1;
   while (atomicOr(flags, FLAG_SLOT_LOCK) & FLAG_SLOT_LOCK) {}
   __threadfence();
-  volatile unsigned long long* p = slot + word;
+  volatile unsigned long long* p = acc_word;
   const i128_t cur = mk128(p[0], p[1]);
   if (is_min ? v < cur : v > cur) { p[0] = lo64(v); p[1] = hi64(v); }
   __threadfence();
@@ -325,9 +325,11 @@ __device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable&
   const uint64_t h = hash_keys(lay, buf, vb, knull, kw);
   unsigned flags;
   bool inserted = false;
-  unsigned long long* slot = agg_find_or_insert(lay, tab, kw, knull, h, &flags, &inserted);
-  if (!slot) return false;
+  const uint64_t slot = agg_find_or_insert(lay, tab, kw, knull, h, &flags, &inserted);
+  if (slot == AGG_NO_SLOT) return false;
   if (inserted) atomicAdd(tab.counters, 1ULL);
+  unsigned long long* const ke = tab.keys + slot * (uint64_t)lay.kstride;
+  unsigned long long* const ae = tab.accs + slot * (uint64_t)lay.astride;
   // accumulate (K6 / K7)
   for (int j = 0; j < lay.nacc; j++) {
     const AccOp a = lay.acc[j];
@@ -336,7 +338,7 @@ __device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable&
     bool valid = true;
     for (int i = 0; i < a.nargs; i++) valid = valid && ((vb >> a.arg_out[i]) & 1);
     if (!valid) continue;
-    unsigned long long* w = slot + a.word;
+    unsigned long long* w = ae + a.word;
     switch (a.kind) {
       case ACC_ADD_I64: red_add_u64(w, arg[0]); break;
       case ACC_ADD_F64: red_add_f64(w, as_f64(arg[0])); break;
@@ -351,10 +353,10 @@ __device__ __forceinline__ bool agg_upsert(const AggLayout& lay, const AggTable&
       case ACC_MAX_I64: red_max_s64(w, (long long)arg[0]); break;
       case ACC_MIN_F64: red_min_s64(w, total_order_key(arg[0])); break;
       case ACC_MAX_F64: red_max_s64(w, total_order_key(arg[0])); break;
-      case ACC_MIN_DEC: dec_minmax(slot, a.word, mk128(arg[0], arg[1]), true); break;
-      default: dec_minmax(slot, a.word, mk128(arg[0], arg[1]), false); break;
+      case ACC_MIN_DEC: dec_minmax(ke, w, mk128(arg[0], arg[1]), true); break;
+      default: dec_minmax(ke, w, mk128(arg[0], arg[1]), false); break;
     }
-    slot_mark(slot, flags, a.vbit);
+    slot_mark(ke, flags, a.vbit);
   }
   return true;
 }
@@ -410,31 +412,32 @@ int launch_agg_update(const VmProgram* d_prog, const ColTable& cols, const AggLa
 // HashAgg: grow (rehash into a larger table)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) agg_rehash_kernel(const AggLayout lay, const AggTable old_tab, const AggTable new_tab) {
-  const uint64_t cap = old_tab.mask + 1;
+  const uint64_t cap = old_tab.capacity;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-    const unsigned long long* src = old_tab.slots + i * (uint64_t)lay.slot_words;
+    const unsigned long long* src = old_tab.keys + i * (uint64_t)lay.kstride;
     const unsigned long long hdr = src[0];
     if ((unsigned)hdr < 2) continue;
     const unsigned knull = (unsigned)(hdr >> 48);
     const uint64_t h = agg_hash_words((const uint64_t*)src + 1, lay.nkw, knull);
-    uint64_t s = h & new_tab.mask;
+    uint64_t s = agg_first_slot(h, new_tab.capacity);
     while (true) {
-      unsigned long long* dst = new_tab.slots + s * (uint64_t)lay.slot_words;
+      unsigned long long* dst = new_tab.keys + s * (uint64_t)lay.kstride;
       if (atomicCAS((unsigned*)dst, TAG_EMPTY, TAG_LOCKED) == TAG_EMPTY) {
-        for (int w = 1; w < lay.slot_words; w++) dst[w] = src[w];
+        for (int w = 1; w < lay.kstride; w++) dst[w] = src[w];
+        for (int w = 0; w < lay.astride; w++) new_tab.accs[s * (uint64_t)lay.astride + w] = old_tab.accs[i * (uint64_t)lay.astride + w];
         ((unsigned*)dst)[1] = (unsigned)(hdr >> 32) & ~FLAG_SLOT_LOCK;
         __threadfence();
         st_release_u32((unsigned*)dst, (unsigned)hdr);
         atomicAdd(new_tab.counters, 1ULL);
         break;
       }
-      s = (s + 1) & new_tab.mask;
+      s = agg_next_slot(s, new_tab.capacity);
     }
   }
 }
 
 int launch_agg_rehash(const AggLayout& lay, const AggTable& old_tab, const AggTable& new_tab, cudaStream_t s) {
-  const int64_t cap = (int64_t)old_tab.mask + 1;
+  const int64_t cap = (int64_t)old_tab.capacity;
   agg_rehash_kernel<<<grid_for((cap + 255) / 256, 8), 256, 0, s>>>(lay, old_tab, new_tab);
   return 1;
 }
@@ -456,15 +459,16 @@ __device__ __forceinline__ void emit_store(const EmitCol& c, unsigned long long 
 }
 
 __global__ void __launch_bounds__(256) agg_emit_kernel(const AggLayout lay, const AggTable tab, const EmitTable emit, unsigned long long* out_count) {
-  const uint64_t cap = tab.mask + 1;
+  const uint64_t cap = tab.capacity;
   const unsigned lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t rounds = (cap + stride - 1) / stride;
   for (uint64_t it = 0; it < rounds; it++) {
     const uint64_t i = it * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const unsigned long long* slot = tab.slots + i * (uint64_t)lay.slot_words;
+    const unsigned long long* ke = tab.keys + i * (uint64_t)lay.kstride;
+    const unsigned long long* slot = tab.accs + i * (uint64_t)lay.astride;      // accumulator entry
     unsigned long long hdr = 0;
-    if (i < cap) hdr = slot[0];
+    if (i < cap) hdr = ke[0];
     const bool occ = (unsigned)hdr >= 2;
     const unsigned m = __ballot_sync(0xffffffffu, occ);
     if (!m) continue;
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(const AggLayout lay, cons
       switch (ec.kind) {
         case EMIT_KEY: {
           const bool valid = !((flags >> (16 + ec.key)) & 1);
-          emit_store(ec, at, slot[ec.word], ec.phys == PH_DEC128 ? slot[ec.word + 1] : 0, valid);
+          emit_store(ec, at, ke[ec.word], ec.phys == PH_DEC128 ? ke[ec.word + 1] : 0, valid);
           break;
         }
         case EMIT_ACC_VALUE: {
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(const AggLayout lay, cons
 }
 
 int launch_agg_emit(const AggLayout& lay, const AggTable& tab, const EmitTable& emit, unsigned long long* d_out_count, cudaStream_t s) {
-  const int64_t cap = (int64_t)tab.mask + 1;
+  const int64_t cap = (int64_t)tab.capacity;
   agg_emit_kernel<<<grid_for((cap + 255) / 256, 8), 256, 0, s>>>(lay, tab, emit, d_out_count);
   return 1;
 }

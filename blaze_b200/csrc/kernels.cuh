@@ -25,29 +25,34 @@ enum AccKind : uint8_t {
 
 struct AccOp {
   uint8_t kind;
-  uint8_t word;        // word offset inside the slot
+  uint8_t word;        // word offset inside the accumulator entry
   uint8_t vbit;        // bit in the slot header's flags marking "accumulator has a value" (0xFF: always valid)
   uint8_t nargs;       // arguments (ACC_COUNT may have 0..4; others exactly 1)
   uint8_t arg_out[4];  // VM output index of each argument
 };
 
-// Slot = [hdr][key words...][acc words...], 32-byte aligned stride.
+// The table is split in two arrays indexed by the slot number (measured on B200, profiles/r01_microbench_probe_*:
+// a probe load followed by a RED on the SAME sector runs at 5.2e10 rows/s, probing one array and RED-ing another
+// at 1.0e11 — the L2s of the two dies keep read copies that every atomic on the line must invalidate):
+//   key entry  = [hdr][key words...]           kstride words, probed with plain loads, written once at insertion
+//   acc entry  = [accumulator words...]        astride words, only ever touched by RED/ATOM
 //   hdr low 32 bits : tag  (0 empty, 1 locked, else 0x80000000|fingerprint — cf. agg_hash_map.rs:228-234)
 //   hdr high 32 bits: flags (bits 0..15 accumulator-valid bits, bits 16..31 key-is-NULL bits)
 struct AggLayout {
-  int32_t nkeys, nkw, nacc, slot_words, nouts;
+  int32_t nkeys, nkw, nacc, kstride, astride, nouts;
   uint8_t key_out[AGG_MAX_KEYS];     // VM output index of key k
-  uint8_t key_word[AGG_MAX_KEYS];    // first word of key k inside the slot (>= 1)
+  uint8_t key_word[AGG_MAX_KEYS];    // first word of key k inside the key entry (>= 1)
   uint8_t key_nwords[AGG_MAX_KEYS];  // 1, or 2 for decimal128
   uint8_t out_word[VM_MAX_OUT];      // VM output index -> word in the per-row scratch buffer
   AccOp acc[AGG_MAX_ACC];
-  uint64_t init[AGG_MAX_SLOT_WORDS]; // initial slot image (accumulator identities)
+  uint64_t init[AGG_MAX_SLOT_WORDS]; // initial accumulator entry (identities)
   uint32_t init_flags;               // accumulator-valid bits set at insertion (accumulators with vbit == 0xFF have none)
 };
 
 struct AggTable {
-  unsigned long long* slots;
-  uint64_t mask;            // capacity - 1 (capacity is a power of two)
+  unsigned long long* keys;       // capacity * kstride words
+  unsigned long long* accs;       // capacity * astride words
+  uint64_t capacity;        // any size: slot = mulhi64(hash, capacity), linear probing with wrap-around
   uint64_t max_groups;      // load limit: inserts beyond it are deferred (table grown by the host, rows replayed)
   unsigned long long* counters;   // [0] ngroups, [1] ndeferred, [2] (int) error flags
   uint32_t* deferred;       // row indices that could not be inserted
@@ -61,7 +66,7 @@ enum EmitKind : uint8_t {
   EMIT_AVG_DEC,        // i128 sum div_euclid count -> decimal128   (avg.rs:158-165)
 };
 struct EmitCol {
-  uint8_t kind, phys, word, word2;
+  uint8_t kind, phys, word, word2;   // word: offset in the key entry (EMIT_KEY) or in the accumulator entry
   uint8_t vbit;        // 0xFF: always valid
   uint8_t key;         // key index for EMIT_KEY
   uint8_t sum_is_f64;  // EMIT_AVG_F64: the sum word holds an f64 (else i64)

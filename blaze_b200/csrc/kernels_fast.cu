@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
         }
       }
       // entry / slot of every row of the gang (computed redundantly by each lane of the gang)
-      unsigned long long* ptr[G]; unsigned long long* slot[G]; unsigned flags[G]; bool need[G], ins[G]; uint64_t h[G], idx[G];
+      unsigned long long* ptr[G]; unsigned long long* slot[G] /* key entry of a hashed row */; unsigned flags[G]; bool need[G], ins[G]; uint64_t h[G], idx[G];
 #pragma unroll
       for (int s = 0; s < G; s++) {
         ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; need[s] = false; ins[s] = false; h[s] = 0; idx[s] = 0;
@@ -124,27 +124,27 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
           if (knull[s] == 0 && di < fs.dense_cap) { ptr[s] = fs.dense_tab + di * G + m; continue; }
         }
         h[s] = agg_hash2((uint64_t)key0[s], NK == 2 ? (uint64_t)key1[s] : 0ULL, knull[s]);
-        idx[s] = h[s] & tab.mask; need[s] = true;
+        idx[s] = agg_first_slot(h[s], tab.capacity); need[s] = true;
       }
       // probe walk: all pending rows advance one slot per round, the lanes of a gang in lockstep (collisions are
       // common at load 0.5, so they must not serialise the warp); only NEW keys go to the insert section
       while (true) {
         ulonglong2 hk[G];
 #pragma unroll
-        for (int s = 0; s < G; s++) if (need[s]) hk[s] = ld_relaxed_v2u64(tab.slots + idx[s] * (uint64_t)lay.slot_words);   // {hdr, key0}
+        for (int s = 0; s < G; s++) if (need[s]) hk[s] = ld_relaxed_v2u64(tab.keys + idx[s] * (uint64_t)lay.kstride);   // {hdr, key0}
         bool pending = false;
 #pragma unroll
         for (int s = 0; s < G; s++) {
           if (!need[s]) continue;
-          const unsigned tag = (unsigned)(h[s] >> 32) | 0x80000000u, t = (unsigned)hk[s].x;
-          unsigned long long* sp = tab.slots + idx[s] * (uint64_t)lay.slot_words;
+          const unsigned tag = agg_tag(h[s]), t = (unsigned)hk[s].x;
+          unsigned long long* sp = tab.keys + idx[s] * (uint64_t)lay.kstride;
           if (t == tag) {
             bool hit = (unsigned)(hk[s].x >> 48) == knull[s] && hk[s].y == (uint64_t)key0[s];
             if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)key1[s];
             if (hit) { slot[s] = sp; flags[s] = (unsigned)(hk[s].x >> 32); need[s] = false; }
-            else idx[s] = (idx[s] + 1) & tab.mask;
+            else idx[s] = agg_next_slot(idx[s], tab.capacity);
           } else if (t == TAG_EMPTY) { need[s] = false; ins[s] = true; }
-          else if (t != TAG_LOCKED) idx[s] = (idx[s] + 1) & tab.mask;
+          else if (t != TAG_LOCKED) idx[s] = agg_next_slot(idx[s], tab.capacity);
           pending |= need[s];
         }
         if (!__any_sync(0xffffffffu, pending)) break;
@@ -155,21 +155,20 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
       if (__any_sync(0xffffffffu, any_ins)) {                  // new keys: lane 0 of the gang inserts, then broadcasts
 #pragma unroll
         for (int s = 0; s < G; s++) {
-          unsigned long long sp = (unsigned long long)slot[s]; unsigned fl = flags[s]; bool inserted = false;
+          unsigned long long si = idx[s]; unsigned fl = flags[s]; bool inserted = false;
           if (ins[s] && m == 0) {
             uint64_t kw[2] = {(uint64_t)key0[s], (uint64_t)key1[s]};
-            unsigned long long* p = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &inserted);
-            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + s); }
-            sp = (unsigned long long)p;
+            si = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &inserted);
+            if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + s); }
           }
           { const unsigned b = __ballot_sync(0xffffffffu, inserted); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }   // one counter update per warp step
-          if (G > 1) { sp = __shfl_sync(0xffffffffu, sp, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
-          if (ins[s]) { slot[s] = (unsigned long long*)sp; flags[s] = fl; if (!sp) alive[s] = false; }
+          if (G > 1) { si = __shfl_sync(0xffffffffu, si, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
+          if (ins[s]) { idx[s] = si; flags[s] = fl; slot[s] = si == AGG_NO_SLOT ? nullptr : tab.keys + si * (uint64_t)lay.kstride; if (si == AGG_NO_SLOT) alive[s] = false; }
         }
       }
 #pragma unroll
       for (int s = 0; s < G; s++)
-        if (alive[s] && slot[s] && has_acc) ptr[s] = slot[s] + acc_word;        // hashed row: this lane's accumulator word
+        if (alive[s] && slot[s] && has_acc) ptr[s] = tab.accs + idx[s] * (uint64_t)lay.astride + acc_word;   // hashed row: this lane's accumulator word
       // accumulate: step s updates row s; the gang's lanes hit adjacent words of ONE sector in ONE instruction
 #pragma unroll
       for (int s = 0; s < G; s++) {
@@ -276,14 +275,15 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
             const long long rel = (unit0 + u) * 32 + gl + s;
             uint64_t kw[2] = {(uint64_t)k[u].v[s], 0};
             unsigned fl;
-            unsigned long long* p = agg_find_or_insert(lay, tab, kw, 0, agg_hash_words(kw, 1, 0), &fl, &inserted);
-            if (!p) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
+            const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash_words(kw, 1, 0), &fl, &inserted);
+            if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
             else {
+              unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
 #pragma unroll
               for (int j = 0; j < NACC; j++) {
                 const unsigned long long x = fs.acc[j].kind == FAST_ACC_ADD ? (unsigned long long)__ldg((const long long*)cols.col[fs.acc[j].col].values + row_begin + rel) : 1ULL;
                 atomicAdd(p + fs.acc[j].word, x);
-                slot_mark(p, fl, fs.acc[j].vbit);
+                slot_mark(tab.keys + si * (uint64_t)lay.kstride, fl, fs.acc[j].vbit);
               }
             }
           }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
   const long long* vcol1 = (NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD) ? (const long long*)cols.col[fs.acc[1].col].values + row_begin : nullptr;
   const int w0 = fs.acc[0].word, w1 = NACC == 2 ? fs.acc[1].word : 0;
   unsigned long long* const sink = warp_sink(fs, gwarp, lane);
-  const uint64_t mask = tab.mask; const int sw = lay.slot_words;
+  const uint64_t cap = tab.capacity; const int ks = lay.kstride, as = lay.astride;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
     long long k0[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U];
@@ -344,25 +344,25 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
 #pragma unroll
     for (int u = 0; u < U; u++) {
       h[u] = agg_hash2((uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL, 0);
-      idx[u] = h[u] & mask; need[u] = alive[u]; ins[u] = false; slot[u] = nullptr; flags[u] = 0;
+      idx[u] = agg_first_slot(h[u], cap); need[u] = alive[u]; ins[u] = false; slot[u] = nullptr; flags[u] = 0;
     }
     while (true) {
       ulonglong2 hk[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) if (need[u]) hk[u] = ld_relaxed_v2u64(tab.slots + idx[u] * (uint64_t)sw);     // {hdr, key0}: one 16-byte probe
+      for (int u = 0; u < U; u++) if (need[u]) hk[u] = ld_relaxed_v2u64(tab.keys + idx[u] * (uint64_t)ks);     // {hdr, key0}: one 16-byte probe
       bool pending = false;
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (!need[u]) continue;
-        const unsigned tag = (unsigned)(h[u] >> 32) | 0x80000000u, t = (unsigned)hk[u].x;
-        unsigned long long* sp = tab.slots + idx[u] * (uint64_t)sw;
+        const unsigned tag = agg_tag(h[u]), t = (unsigned)hk[u].x;
+        unsigned long long* sp = tab.keys + idx[u] * (uint64_t)ks;
         if (t == tag) {
           bool hit = (unsigned)(hk[u].x >> 48) == 0 && hk[u].y == (uint64_t)k0[u];
           if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)k1[u];
           if (hit) { slot[u] = sp; flags[u] = (unsigned)(hk[u].x >> 32); need[u] = false; }
-          else idx[u] = (idx[u] + 1) & mask;
+          else idx[u] = agg_next_slot(idx[u], cap);
         } else if (t == TAG_EMPTY) { need[u] = false; ins[u] = true; }
-        else if (t != TAG_LOCKED) idx[u] = (idx[u] + 1) & mask;             // another key: next slot (locked: look again)
+        else if (t != TAG_LOCKED) idx[u] = agg_next_slot(idx[u], cap);      // another key: next slot (locked: look again)
         pending |= need[u];
       }
       if (!__any_sync(0xffffffffu, pending)) break;
@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
         bool inserted = false;
         if (ins[u]) {
           uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
-          slot[u] = agg_find_or_insert(lay, tab, kw, 0, h[u], &flags[u], &inserted);
-          if (!slot[u]) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); alive[u] = false; }
+          idx[u] = agg_find_or_insert(lay, tab, kw, 0, h[u], &flags[u], &inserted);
+          if (idx[u] == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); alive[u] = false; slot[u] = nullptr; }
+          else slot[u] = tab.keys + idx[u] * (uint64_t)ks;
         }
         const unsigned b = __ballot_sync(0xffffffffu, inserted);
         if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
@@ -387,12 +388,13 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const bool live = alive[u] && slot[u] != nullptr;
+      unsigned long long* const ae = tab.accs + idx[u] * (uint64_t)as;          // accumulator entry (never read here: RED only)
       if (NACC == 1) {
-        red_add_u64(live ? slot[u] + w0 : sink, live ? v0[u] : 0ULL);
+        red_add_u64(live ? ae + w0 : sink, live ? v0[u] : 0ULL);
       } else {
-        const unsigned long long ps = __shfl_xor_sync(0xffffffffu, live ? (unsigned long long)slot[u] : 0ULL, 1);
+        const unsigned long long ps = __shfl_xor_sync(0xffffffffu, live ? (unsigned long long)ae : 0ULL, 1);
         const unsigned long long pv1 = __shfl_xor_sync(0xffffffffu, v1[u], 1);
-        unsigned long long* const mine = live ? slot[u] + w0 : sink;  const unsigned long long mv = live ? v0[u] : 0ULL;
+        unsigned long long* const mine = live ? ae + w0 : sink;  const unsigned long long mv = live ? v0[u] : 0ULL;
         unsigned long long* const theirs = ps ? (unsigned long long*)ps + w1 : sink;  const unsigned long long tv = ps ? pv1 : 0ULL;
         red_add_u64(odd ? theirs : mine, odd ? tv : mv);        // step 1: rows of even lanes: {acc0 by the owner, acc1 by its odd neighbour}
         red_add_u64(odd ? mine : theirs, odd ? mv : tv);        // step 2: rows of odd lanes

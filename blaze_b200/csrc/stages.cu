@@ -251,7 +251,7 @@ class AggStage : public Stage {
   int first_state_col_ = 0;             // index of the first state column in the program's column space
 
   // table
-  DevMemP slots_, counters_, deferred_[2];
+  DevMemP keys_, accs_, counters_, deferred_[2];
   uint64_t capacity_ = 0;
   int64_t deferred_cap_ = 0;
   int64_t ngroups_ = 0;
@@ -317,17 +317,11 @@ class AggStage : public Stage {
       word += lay_.key_nwords[k];
     }
     lay_.nkw = word - 1;
+    const int key_entry_words = word;
+    word = 0;                                                     // from here on `word` counts words of the accumulator entry
     for (int i = 0; i < AGG_MAX_SLOT_WORDS; i++) lay_.init[i] = 0;
     lay_.init_flags = 0;
     int vbits = 0, state_k = 0;
-    {   // keep narrow accumulator sets inside one 32-byte sector (one L2 sector operation per row)
-      int total_acc_words = 0;
-      for (auto& a : agg.aggs) {
-        if (a.fn != AGG_COUNT) total_acc_words += a.data_type.is_decimal() ? 2 : 1;
-        if (a.fn == AGG_COUNT || a.fn == AGG_AVG) total_acc_words += 1;
-      }
-      if (total_acc_words <= 4 && (word % 4) + total_acc_words > 4) word = (word + 3) & ~3;
-    }
     auto new_vbit = [&]() { if (vbits >= 15) throw PlanError(B200Q_ERR_UNSUPPORTED, "too many nullable accumulators in one aggregate"); return (uint8_t)vbits++; };
     auto state_col_expr = [&](const FieldDef& f) {
       auto e = std::make_shared<Expr>(); e->kind = E_COLUMN; e->col_index = first_state_col_ + state_k++; e->name = f.name; e->type = f.type; e->nullable = f.nullable;
@@ -417,8 +411,11 @@ class AggStage : public Stage {
       }
     }
     if (lay_.nkeys == 0 && lay_.nacc == 0) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate without groupings and aggregates");
-    lay_.slot_words = (word + 3) & ~3;                           // 32-byte aligned slots: one L2 sector per probe for narrow aggregates
-    if (lay_.slot_words > AGG_MAX_SLOT_WORDS) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate state too wide for one table slot");
+    // entry strides: powers of two up to a 32-byte sector (an entry never straddles a sector), multiples of 4 words beyond
+    auto stride_of = [](int words) { return words <= 1 ? 1 : words <= 2 ? 2 : words <= 4 ? 4 : (words + 3) & ~3; };
+    lay_.kstride = std::max(2, stride_of(key_entry_words));      // {hdr, key0} is probed with one 16-byte load
+    lay_.astride = stride_of(std::max(word, 1));
+    if (lay_.kstride > AGG_MAX_SLOT_WORDS || lay_.astride > AGG_MAX_SLOT_WORDS) throw PlanError(B200Q_ERR_UNSUPPORTED, "aggregate state too wide for one table slot");
 
     if (!final_ && columnar_) {          // typed state columns instead of the Binary agg-buffer column
       out_schema.fields.resize(lay_.nkeys);
@@ -450,11 +447,11 @@ class AggStage : public Stage {
     }
 
     // ---- table
-    uint64_t want = (uint64_t)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * 2;
-    capacity_ = 1ULL << 21;                                       // floor: the slack above the load limit (capacity * 0.3) must exceed the
-                                                                  // concurrent-insert overshoot bound (resident threads ~ 303K)
-    while (capacity_ < want) capacity_ <<= 1;
-    alloc_table(cx, capacity_, slots_, counters_);
+    // capacity: any size (slot = mulhi(hash, capacity)); sized for a load of ~0.6 at the hinted group count so that
+    // key area + accumulator area stay L2-resident; floor 2^20 keeps the slack above the load limit (0.3 * capacity)
+    // larger than the concurrent-insert overshoot bound (resident threads ~ 303K)
+    capacity_ = std::max<uint64_t>(1ULL << 20, (uint64_t)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * 5 / 3);
+    alloc_table(cx, capacity_, keys_, accs_, counters_);
     if (lay_.nkeys == 0) seed_global_group(cx);
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
     cx.m.table_capacity = (int64_t)capacity_;
@@ -610,20 +607,22 @@ class AggStage : public Stage {
     return launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, m, list, cx.stream);
   }
 
-  void alloc_table(OpContext& cx, uint64_t cap, DevMemP& slots, DevMemP& counters) {
-    slots = DevMem::alloc((size_t)cap * lay_.slot_words * 8, cx.stream, true);
+  void alloc_table(OpContext& cx, uint64_t cap, DevMemP& keys, DevMemP& accs, DevMemP& counters) {
+    keys = DevMem::alloc((size_t)cap * lay_.kstride * 8, cx.stream, true);
+    accs = DevMem::alloc((size_t)cap * lay_.astride * 8, cx.stream);       // initialised at insertion
     counters = DevMem::alloc(64, cx.stream, true);
   }
 
   // no-grouping aggregation always yields exactly one row (agg_exec.rs:280-323): pre-insert the empty key
   void seed_global_group(OpContext& cx) {
     const uint64_t h = host_mix64(0x9E3779B97F4A7C15ULL);        // == agg_hash_words(nullptr, 0, 0)
-    const uint32_t tag = (uint32_t)(h >> 32) | 0x80000000u;
-    const uint64_t s = h & (capacity_ - 1);
-    std::vector<uint64_t> img(lay_.slot_words, 0);
-    for (int i = 1; i < lay_.slot_words; i++) img[i] = lay_.init[i];
-    img[0] = (uint64_t)tag | ((uint64_t)lay_.init_flags << 32);
-    B200Q_CUDA(cudaMemcpyAsync((uint8_t*)slots_->ptr + s * lay_.slot_words * 8, img.data(), img.size() * 8, cudaMemcpyHostToDevice, cx.stream));
+    const uint64_t s = (uint64_t)(((unsigned __int128)h * capacity_) >> 64);     // == agg_first_slot
+    const uint32_t tag2 = (uint32_t)h | 0x80000000u;                             // == agg_tag
+    std::vector<uint64_t> kimg(lay_.kstride, 0), aimg(lay_.astride, 0);
+    for (int i = 0; i < lay_.astride; i++) aimg[i] = lay_.init[i];
+    kimg[0] = (uint64_t)tag2 | ((uint64_t)lay_.init_flags << 32);
+    B200Q_CUDA(cudaMemcpyAsync((uint8_t*)keys_->ptr + s * lay_.kstride * 8, kimg.data(), kimg.size() * 8, cudaMemcpyHostToDevice, cx.stream));
+    B200Q_CUDA(cudaMemcpyAsync((uint8_t*)accs_->ptr + s * lay_.astride * 8, aimg.data(), aimg.size() * 8, cudaMemcpyHostToDevice, cx.stream));
     const unsigned long long one = 1;
     B200Q_CUDA(cudaMemcpyAsync(counters_->ptr, &one, 8, cudaMemcpyHostToDevice, cx.stream));
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));
@@ -631,7 +630,7 @@ class AggStage : public Stage {
 
   AggTable table_view(int deferred_idx) const {
     AggTable t{};
-    t.slots = (unsigned long long*)slots_->ptr; t.mask = capacity_ - 1; t.max_groups = capacity_ / 10 * 7;
+    t.keys = (unsigned long long*)keys_->ptr; t.accs = (unsigned long long*)accs_->ptr; t.capacity = capacity_; t.max_groups = capacity_ / 10 * 7;
     t.counters = (unsigned long long*)counters_->ptr;
     t.deferred = deferred_[deferred_idx] ? (uint32_t*)deferred_[deferred_idx]->ptr : nullptr;
     return t;
@@ -640,13 +639,13 @@ class AggStage : public Stage {
   void grow(OpContext& cx, uint64_t min_groups) {
     uint64_t cap = capacity_;
     do cap <<= 1; while (cap / 10 * 7 < min_groups);
-    DevMemP nslots, ncounters;
-    alloc_table(cx, cap, nslots, ncounters);
+    DevMemP nkeys, naccs, ncounters;
+    alloc_table(cx, cap, nkeys, naccs, ncounters);
     AggTable oldt = table_view(0);
-    AggTable newt{}; newt.slots = (unsigned long long*)nslots->ptr; newt.mask = cap - 1; newt.max_groups = cap / 10 * 7; newt.counters = (unsigned long long*)ncounters->ptr;
+    AggTable newt{}; newt.keys = (unsigned long long*)nkeys->ptr; newt.accs = (unsigned long long*)naccs->ptr; newt.capacity = cap; newt.max_groups = cap / 10 * 7; newt.counters = (unsigned long long*)ncounters->ptr;
     cx.m.launches += launch_agg_rehash(lay_, oldt, newt, cx.stream);
     B200Q_CUDA(cudaGetLastError());
-    slots_ = nslots; counters_ = ncounters; capacity_ = cap;
+    keys_ = nkeys; accs_ = naccs; counters_ = ncounters; capacity_ = cap;
     cx.m.grow_count++; cx.m.table_capacity = (int64_t)cap;
   }
 
