@@ -49,7 +49,8 @@ __device__ __forceinline__ void slot_mark(unsigned long long* key_entry, unsigne
   if (vbit != 0xFF && !((flags_seen >> vbit) & 1)) atomicOr((unsigned*)key_entry + 1, 1u << vbit);
 }
 
-__device__ __forceinline__ uint64_t agg_first_slot(uint64_t h, uint64_t capacity) { return __umul64hi(h, capacity); }
+// capacity < 2^32 slots: the slot comes from the high 32 hash bits with one 32-bit multiply-high, the tag from the low bits
+__device__ __forceinline__ uint64_t agg_first_slot(uint64_t h, uint64_t capacity) { return __umulhi((unsigned)(h >> 32), (unsigned)capacity); }
 __device__ __forceinline__ unsigned agg_tag(uint64_t h) { return (unsigned)h | 0x80000000u; }
 __device__ __forceinline__ uint64_t agg_next_slot(uint64_t s, uint64_t capacity) { return s + 1 == capacity ? 0 : s + 1; }
 constexpr uint64_t AGG_NO_SLOT = ~0ULL;

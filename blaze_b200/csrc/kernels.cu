@@ -11,6 +11,8 @@
 //   agg_emit_kernel        K8+K9: table scan -> dense Arrow columns (build_agg_columns, agg_ctx.rs:303-326).
 //   frozen_* kernels       the reference's frozen accumulator-row byte format (acc.rs:335-365,
 //                          count.rs:193-211, io/mod.rs:60-83) for the Binary `#9223372036854775807` column.
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -168,69 +170,171 @@ int launch_filter_project(const VmProgram* d_prog, const ColTable& cols, const O
 static int grid_for(int64_t ntiles, int per_sm);
 
 // ---------------------------------------------------------------------------------------------------
-// lean FilterExec / ProjectExec: same single-pass ordered compaction, expressions evaluated directly
-// (no bytecode) for the M0 shape: non-null int64 columns, `col cmp literal` conjuncts, projections that are
-// a column or `column op column|literal`.  Loads are striped (row = r*256 + tid): perfectly coalesced, and the
-// survivors of a warp-row are written to consecutive positions.
+// lean FilterExec / ProjectExec for the M0 shape: 1-4 non-null int64 input columns, `col cmp literal` conjuncts,
+// projections that are a column or `column op column|literal`; expressions evaluated directly (no bytecode).
+//
+// Measured on B200 (profiles/r01_filter_lookback_phases.txt): in the single-pass look-back form a tile spends 65 %
+// of its life WAITING for its exclusive prefix (7.4 us of 11.4 us at 2048-row tiles) with its rows parked in
+// registers and no loads in flight; wider windows, larger tiles, back-off and earlier tickets all end at
+// 1.1-1.3e11 rows/s (0.39-0.44 of the HBM roofline).  Large batches therefore take an order-free two-pass form:
+//   pass 1  count : every warp streams the FILTER columns of its 256-row chunks and writes one survivor count
+//   (scan)        : exclusive scan of the chunk counts (3 tiny launches)
+//   pass 2  apply : every warp streams all referenced columns of its chunks, re-evaluates the conjuncts and
+//                   writes the projected survivors at the chunk's offset (warps are fully independent: no
+//                   barriers, no spinning, 2 x NC x 8 independent loads per lane in flight)
+// The filter columns are read twice (M0: 32 B/row of traffic for 24 algorithmic bytes) but both passes stream
+// at HBM speed.  Small batches (latency-bound anyway) keep the single-pass kernel: one launch.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FL_BLOCK = 128;                    // small CTAs: more of them resident per SM to overlap the per-tile barriers
+constexpr int FL_R = 8;                          // rows per lane per chunk
+constexpr int FL_CHUNK = 32 * FL_R;              // 256 rows: the unit of the order-free form
+constexpr int FL_BLOCK = 256;                    // single-pass form: 8 chunks per tile
 constexpr int FL_NW = FL_BLOCK / 32;
-constexpr int FL_R = 16;                         // 2048 rows per tile
 constexpr int FL_TILE = FL_BLOCK * FL_R;
-int64_t filter_project_lean_num_tiles(int64_t n) { return (n + FL_TILE - 1) / FL_TILE; }
-struct LeanOutPtrs { long long* p[8]; };
-
-__device__ __forceinline__ bool lean_cmp(int op, long long a, long long b) {
-  switch (op) { case CMP_EQ: return a == b; case CMP_NE: return a != b; case CMP_LT: return a < b; case CMP_LE: return a <= b; case CMP_GT: return a > b; default: return a >= b; }
+constexpr int64_t FL_TWO_PASS_MIN_ROWS = 1 << 20;
+struct LeanFpDev {
+  int32_t nfilt, nout, nfcols;
+  const long long* col[4];
+  uint8_t fcol[4];                                                       // distinct columns the conjuncts read
+  struct { uint8_t slot, mask; long long lit; } filt[4];                 // mask: bit0 '<', bit1 '==', bit2 '>'
+  struct { uint8_t kind, a, b; long long lit; long long* dst; } out[8];  // b == 0xFF: literal operand
+};
+static int64_t fl_num_chunks(int64_t n) { return (n + FL_CHUNK - 1) / FL_CHUNK; }
+int64_t filter_project_lean_scratch_bytes(int64_t n) {
+  const int64_t nc = fl_num_chunks(n);
+  if (n >= FL_TWO_PASS_MIN_ROWS) return (nc + (nc + 1) + scan_num_blocks(nc) + 8) * 4;     // counts, offsets, block sums
+  return ((n + FL_TILE - 1) / FL_TILE) * 8;                                               // tile status words
 }
 
-__global__ void __launch_bounds__(FL_BLOCK) filter_project_lean_kernel(const ColTable cols, const LeanFpSpec sp, const LeanOutPtrs outs,
-                                                                       long long n, long long ntiles, unsigned long long* tile_status, unsigned long long* scratch) {
-  __shared__ long long s_tile, s_excl;
-  __shared__ unsigned s_cnt[FL_R * FL_NW], s_off[FL_R * FL_NW];
+__device__ __forceinline__ long long ld_stream_i64(const long long* p) {
+  long long v; asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ bool fl_cmp(unsigned mask, long long x, long long lit) { return mask & (x < lit ? 1u : (x == lit ? 2u : 4u)); }
+
+// one chunk: 8 x 8-byte streaming loads per lane and column (row = row0 + r*32: 256 contiguous bytes per warp instruction)
+template <int NCOLS>
+__device__ __forceinline__ void fl_load(const LeanFpDev& sp, const uint8_t* slots, long long row0, long long n, long long (&x)[NCOLS][FL_R]) {
+  if (row0 - (threadIdx.x & 31) + FL_CHUNK <= n) {
+#pragma unroll
+    for (int c = 0; c < NCOLS; c++)
+#pragma unroll
+      for (int r = 0; r < FL_R; r++) x[c][r] = ld_stream_i64(sp.col[slots ? slots[c] : c] + row0 + r * 32);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCOLS; c++)
+#pragma unroll
+      for (int r = 0; r < FL_R; r++) x[c][r] = row0 + r * 32 < n ? ld_stream_i64(sp.col[slots ? slots[c] : c] + row0 + r * 32) : 0;
+  }
+}
+// survivors of a chunk as one ballot per warp-row; `slots` maps register column -> input slot (null: identity)
+template <int NCOLS>
+__device__ __forceinline__ unsigned fl_filter(const LeanFpDev& sp, const uint8_t* slots, long long row0, long long n, const long long (&x)[NCOLS][FL_R], unsigned (&am)[FL_R]) {
+  bool alive[FL_R];
+#pragma unroll
+  for (int r = 0; r < FL_R; r++) alive[r] = row0 + r * 32 < n;
+  for (int f = 0; f < sp.nfilt; f++) {
+    const unsigned mask = sp.filt[f].mask; const long long lit = sp.filt[f].lit; const int slot = sp.filt[f].slot;
+#pragma unroll
+    for (int c = 0; c < NCOLS; c++) {
+      if (slot != (slots ? slots[c] : c)) continue;
+#pragma unroll
+      for (int r = 0; r < FL_R; r++) alive[r] = alive[r] && fl_cmp(mask, x[c][r], lit);
+    }
+  }
+  unsigned total = 0;
+#pragma unroll
+  for (int r = 0; r < FL_R; r++) { am[r] = __ballot_sync(0xffffffffu, alive[r]); total += __popc(am[r]); }
+  return total;
+}
+// projected survivors of a chunk -> consecutive positions from `wbase`
+template <int NC>
+__device__ __forceinline__ void fl_store(const LeanFpDev& sp, const long long (&x)[NC][FL_R], const unsigned (&am)[FL_R], long long wbase) {
+  const unsigned lane = threadIdx.x & 31, lt = lanemask_lt();
+  for (int o = 0; o < sp.nout; o++) {
+    const int kind = sp.out[o].kind, sa = sp.out[o].a, sb = sp.out[o].b;
+    long long* const dst = sp.out[o].dst + wbase;
+    unsigned rank = 0;
+#pragma unroll
+    for (int r = 0; r < FL_R; r++) {
+      long long va = x[0][r], vb = sp.out[o].lit;
+#pragma unroll
+      for (int c = 1; c < NC; c++) va = sa == c ? x[c][r] : va;
+#pragma unroll
+      for (int c = 0; c < NC; c++) vb = sb == c ? x[c][r] : vb;
+      const unsigned long long a = (unsigned long long)va, b = (unsigned long long)vb;
+      const unsigned long long v = kind == 0 ? a : kind == 1 ? a + b : kind == 2 ? a - b : a * b;     // wrapping, like the reference
+      if ((am[r] >> lane) & 1) dst[rank + __popc(am[r] & lt)] = (long long)v;
+      rank += __popc(am[r]);
+    }
+  }
+}
+
+// ---- order-free two-pass form ----
+template <int NFC>
+__global__ void __launch_bounds__(256) filter_count_lean_kernel(const LeanFpDev sp, long long n, long long nchunks, int32_t* __restrict__ counts) {
+  const long long gwarp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
+  const unsigned lane = threadIdx.x & 31;
+  for (long long ch = gwarp; ch < nchunks; ch += nwarps) {
+    const long long row0 = ch * FL_CHUNK + lane;
+    long long x[NFC][FL_R]; unsigned am[FL_R];
+    fl_load<NFC>(sp, sp.fcol, row0, n, x);
+    const unsigned total = fl_filter<NFC>(sp, sp.fcol, row0, n, x, am);
+    if (lane == 0) counts[ch] = (int32_t)total;
+  }
+}
+template <int NC>
+__global__ void __launch_bounds__(256) filter_apply_lean_kernel(const LeanFpDev sp, long long n, long long nchunks, const int32_t* __restrict__ offsets,
+                                                                 unsigned long long* scratch) {
+  const long long gwarp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
+  const unsigned lane = threadIdx.x & 31;
+  for (long long ch = gwarp; ch < nchunks; ch += nwarps) {
+    const long long row0 = ch * FL_CHUNK + lane;
+    const long long wbase = offsets[ch];
+    long long x[NC][FL_R]; unsigned am[FL_R];
+    fl_load<NC>(sp, nullptr, row0, n, x);
+    const unsigned total = fl_filter<NC>(sp, nullptr, row0, n, x, am);
+    fl_store<NC>(sp, x, am, wbase);
+    if (ch == nchunks - 1 && lane == 0) scratch[1] = (unsigned long long)(wbase + total);
+  }
+}
+
+// ---- single-pass form (decoupled look-back over 2048-row tiles, ticketed) ----
+template <int NC, int OCC>
+__global__ void __launch_bounds__(FL_BLOCK, OCC) filter_project_lean_kernel(const LeanFpDev sp, long long n, long long ntiles,
+                                                                            unsigned long long* tile_status, unsigned long long* scratch) {
+  __shared__ long long s_tile, s_base[FL_NW];
+  __shared__ unsigned s_cnt[FL_NW];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = lanemask_lt();
   while (true) {
-    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(scratch + 0, 1ULL);       // ticket: lower tiles are always already running
+    // ticket: lower tiles are always already running (deadlock-free whatever the residency of the grid is).  Taken as
+    // late as possible: a ticket held by a CTA that has not published its aggregate yet stalls every later tile
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(scratch + 0, 1ULL);
     __syncthreads();
     const long long tile = s_tile;
     if (tile >= ntiles) break;
-    const long long row0 = tile * FL_TILE + threadIdx.x;
-    bool alive[FL_R];
-#pragma unroll
-    for (int r = 0; r < FL_R; r++) alive[r] = row0 + r * FL_BLOCK < n;
-    for (int f = 0; f < sp.nfilt; f++) {
-      const long long* c = (const long long*)cols.col[sp.filt[f].col].values;
-      long long x[FL_R];
-#pragma unroll
-      for (int r = 0; r < FL_R; r++) x[r] = row0 + r * FL_BLOCK < n ? __ldg(c + row0 + r * FL_BLOCK) : 0;
-#pragma unroll
-      for (int r = 0; r < FL_R; r++) alive[r] = alive[r] && lean_cmp(sp.filt[f].op, x[r], sp.filt[f].lit);
-    }
-    unsigned amask[FL_R];
-#pragma unroll
-    for (int r = 0; r < FL_R; r++) { amask[r] = __ballot_sync(0xffffffffu, alive[r]); if (lane == 0) s_cnt[r * FL_NW + warp] = __popc(amask[r]); }
+    const long long row0 = tile * FL_TILE + warp * FL_CHUNK + lane;
+    long long x[NC][FL_R]; unsigned am[FL_R];
+    fl_load<NC>(sp, nullptr, row0, n, x);
+    const unsigned wt = fl_filter<NC>(sp, nullptr, row0, n, x, am);
+    if (lane == 0) s_cnt[warp] = wt;
     __syncthreads();
     if (warp == 0) {
-      static_assert(FL_R * FL_NW == 64, "the warp scan below handles two warp-rows per lane");
-      const unsigned v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1], v = v0 + v1;
+      const unsigned v = lane < FL_NW ? s_cnt[lane] : 0;
       unsigned incl = v;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      s_off[2 * lane] = incl - v; s_off[2 * lane + 1] = incl - v + v0;
-      const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+      for (int d = 1; d < FL_NW; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      const unsigned long long total = __shfl_sync(0xffffffffu, incl, FL_NW - 1);
       unsigned long long excl = 0;
       if (sp.nfilt == 0) excl = (unsigned long long)tile * FL_TILE;        // nothing filtered: positions are the row numbers
       else if (tile > 0) {
         if (lane == 0) st_relaxed_u64(tile_status + tile, ST_AGG | total);
         long long j = tile - 1;
-        while (true) {
+        while (true) {                                                     // decoupled look-back, 32 predecessors per round
           const long long idx = j - lane;
           unsigned long long st = idx >= 0 ? ld_relaxed_u64(tile_status + idx) : ST_PREFIX;
-          if (__any_sync(0xffffffffu, (st >> 62) == 0)) continue;
+          if (__any_sync(0xffffffffu, (st >> 62) == 0)) { __nanosleep(64); continue; }   // a predecessor has not published yet
           const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
           unsigned long long val = st & ST_VALUE;
-          if (pm) { const int first = __ffs(pm) - 1; if ((int)lane > first) val = 0; }
+          if (pm) { const int first = __ffs(pm) - 1; if ((int)lane > first) val = 0; }   // nearest tile with an inclusive prefix
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
           excl += val;
@@ -240,39 +344,59 @@ __global__ void __launch_bounds__(FL_BLOCK) filter_project_lean_kernel(const Col
       }
       if (lane == 0) {
         if (sp.nfilt) st_relaxed_u64(tile_status + tile, ST_PREFIX | (excl + total));
-        s_excl = (long long)excl;
         if (tile == ntiles - 1) scratch[1] = excl + total;
       }
+      if (lane < FL_NW) s_base[lane] = (long long)(excl + (incl - v));
     }
     __syncthreads();
-    for (int o = 0; o < sp.nout; o++) {
-      const int kind = sp.out[o].kind;
-      const long long* ca = (const long long*)cols.col[sp.out[o].a].values;
-      const long long* cb = sp.out[o].b >= 0 ? (const long long*)cols.col[sp.out[o].b].values : nullptr;
-      long long* dst = outs.p[o];
-#pragma unroll
-      for (int r = 0; r < FL_R; r++) {
-        if (!alive[r]) continue;
-        const long long a = __ldg(ca + row0 + r * FL_BLOCK);
-        long long v = a;
-        if (kind) {
-          const long long b = cb ? __ldg(cb + row0 + r * FL_BLOCK) : sp.out[o].lit;
-          v = kind == 1 ? (long long)((unsigned long long)a + (unsigned long long)b) : kind == 2 ? (long long)((unsigned long long)a - (unsigned long long)b)
-                                                                                       : (long long)((unsigned long long)a * (unsigned long long)b);
-        }
-        dst[s_excl + s_off[r * FL_NW + warp] + __popc(amask[r] & lt)] = v;
-      }
-    }
-    __syncthreads();
+    fl_store<NC>(sp, x, am, s_base[warp]);
   }
 }
 
-int launch_filter_project_lean(const ColTable& cols, const LeanFpSpec& sp, long long* const* out_values, int64_t n,
-                               unsigned long long* d_tile_status, unsigned long long* d_scratch, cudaStream_t s) {
-  const int64_t ntiles = filter_project_lean_num_tiles(n);
-  if (ntiles == 0) return 0;
-  LeanOutPtrs op{}; for (int i = 0; i < sp.nout; i++) op.p[i] = out_values[i];
-  filter_project_lean_kernel<<<grid_for(ntiles, 12), FL_BLOCK, 0, s>>>(cols, sp, op, n, ntiles, d_tile_status, d_scratch);
+int launch_filter_project_lean(const ColTable& cols, int ncols, const LeanFpSpec& sp, long long* const* out_values, int64_t n,
+                               void* d_work /* filter_project_lean_scratch_bytes(n), zeroed */, unsigned long long* d_scratch, cudaStream_t s) {
+  if (n <= 0) return 0;
+  static const uint8_t cmp_mask[6] = {2, 5, 1, 3, 4, 6};                   // CMP_EQ, NE, LT, LE, GT, GE
+  LeanFpDev d{}; d.nfilt = sp.nfilt; d.nout = sp.nout;
+  for (int c = 0; c < ncols; c++) d.col[c] = (const long long*)cols.col[c].values;
+  for (int f = 0; f < sp.nfilt; f++) {
+    d.filt[f].slot = (uint8_t)sp.filt[f].col; d.filt[f].mask = cmp_mask[sp.filt[f].op]; d.filt[f].lit = sp.filt[f].lit;
+    bool seen = false;
+    for (int i = 0; i < d.nfcols; i++) seen |= d.fcol[i] == d.filt[f].slot;
+    if (!seen) d.fcol[d.nfcols++] = d.filt[f].slot;
+  }
+  for (int o = 0; o < sp.nout; o++) {
+    d.out[o].kind = sp.out[o].kind; d.out[o].a = (uint8_t)sp.out[o].a; d.out[o].b = sp.out[o].b < 0 ? 0xFF : (uint8_t)sp.out[o].b;
+    d.out[o].lit = sp.out[o].lit; d.out[o].dst = out_values[o];
+  }
+  if (sp.nfilt && n >= FL_TWO_PASS_MIN_ROWS) {
+    const int64_t nch = fl_num_chunks(n);
+    int32_t* counts = (int32_t*)d_work; int32_t* offsets = counts + nch; int32_t* sums = offsets + nch + 1;
+    const unsigned grid = grid_for((nch + 7) / 8, 8);
+    switch (d.nfcols) {
+      case 1: filter_count_lean_kernel<1><<<grid, 256, 0, s>>>(d, n, nch, counts); break;
+      case 2: filter_count_lean_kernel<2><<<grid, 256, 0, s>>>(d, n, nch, counts); break;
+      case 3: filter_count_lean_kernel<3><<<grid, 256, 0, s>>>(d, n, nch, counts); break;
+      default: filter_count_lean_kernel<4><<<grid, 256, 0, s>>>(d, n, nch, counts); break;
+    }
+    const int scan_launches = launch_exclusive_scan_i32(counts, offsets, nch, sums, s);
+    const unsigned grid2 = grid_for((nch + 7) / 8, ncols <= 2 ? 6 : 3);
+    switch (ncols) {
+      case 1: filter_apply_lean_kernel<1><<<grid2, 256, 0, s>>>(d, n, nch, offsets, d_scratch); break;
+      case 2: filter_apply_lean_kernel<2><<<grid2, 256, 0, s>>>(d, n, nch, offsets, d_scratch); break;
+      case 3: filter_apply_lean_kernel<3><<<grid2, 256, 0, s>>>(d, n, nch, offsets, d_scratch); break;
+      default: filter_apply_lean_kernel<4><<<grid2, 256, 0, s>>>(d, n, nch, offsets, d_scratch); break;
+    }
+    return 2 + scan_launches;
+  }
+  const int64_t ntiles = (n + FL_TILE - 1) / FL_TILE;
+  unsigned long long* status = (unsigned long long*)d_work;
+  switch (ncols) {
+    case 1: filter_project_lean_kernel<1, 4><<<grid_for(ntiles, 4), FL_BLOCK, 0, s>>>(d, n, ntiles, status, d_scratch); break;
+    case 2: filter_project_lean_kernel<2, 4><<<grid_for(ntiles, 4), FL_BLOCK, 0, s>>>(d, n, ntiles, status, d_scratch); break;
+    case 3: filter_project_lean_kernel<3, 2><<<grid_for(ntiles, 2), FL_BLOCK, 0, s>>>(d, n, ntiles, status, d_scratch); break;
+    default: filter_project_lean_kernel<4, 2><<<grid_for(ntiles, 2), FL_BLOCK, 0, s>>>(d, n, ntiles, status, d_scratch); break;
+  }
   return 1;
 }
 

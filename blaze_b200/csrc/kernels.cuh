@@ -103,9 +103,9 @@ struct LeanFpSpec {
   struct { int8_t col; uint8_t op; uint8_t _pad[6]; long long lit; } filt[4];
   struct { uint8_t kind; int8_t a; int8_t b; uint8_t _pad[5]; long long lit; } out[8];   // kind 0: col a; 1: a+b 2: a-b 3: a*b (b<0: literal)
 };
-int launch_filter_project_lean(const ColTable& cols, const LeanFpSpec& sp, long long* const* out_values, int64_t n,
-                               unsigned long long* d_tile_status, unsigned long long* d_scratch, cudaStream_t s);
-int64_t filter_project_lean_num_tiles(int64_t n);
+int launch_filter_project_lean(const ColTable& cols, int ncols /*1..4, every one referenced*/, const LeanFpSpec& sp, long long* const* out_values, int64_t n,
+                               void* d_work /* filter_project_lean_scratch_bytes(n) bytes, zeroed */, unsigned long long* d_scratch, cudaStream_t s);
+int64_t filter_project_lean_scratch_bytes(int64_t n);
 
 int launch_agg_update(const VmProgram* d_prog, const ColTable& cols, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n,
                       const uint32_t* d_row_list /*replay of deferred rows, or null*/, cudaStream_t s);

@@ -22,6 +22,8 @@
 //
 // REDs are issued UNCONDITIONALLY: ptxas if-converts a predicated `red` into `@P ATOMG ... RZ` (an atomic
 // with a return path); lanes with nothing to add send +0 to their warp's private sink sector instead.
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -296,36 +298,123 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LEAN hashed kernel: 1-2 non-null int64 keys, non-null int64 accumulator/filter columns (same preconditions
-// as the lean dense kernel).  One row per lane (the hash + probe work is done once per row); with two
-// accumulators the two words of a row are still updated by ONE instruction: neighbouring lanes exchange their
-// slot pointer / second operand with one shuffle pair and lane L updates acc0 of its own row while lane L^1
-// updates acc1 of the same row (step 1: rows of even lanes, step 2: rows of odd lanes).
+// LEAN hashed kernel: 1-2 non-null int64 keys, non-null int64 accumulator/filter columns (same preconditions as
+// the lean dense kernel), one row per lane, compacted probe rounds.  A lane-parallel probe walk waits, per warp
+// step, for the LONGEST collision chain among its rows (a dependent L2 round trip per extra slot with most lanes
+// idle: 2.6e10 rows/s on M1).  Here every row gets one first probe in the streaming step; rows that must look at
+// another slot are pushed onto a per-warp shared-memory stack (warp-synchronous: no atomics) and re-probed 32 at a
+// time, so every probe round issues a full warp of useful loads whatever the chain lengths are (5.6-6.7e10 rows/s).
+// With two accumulators the two words of a row are updated by ONE instruction: neighbouring lanes exchange their
+// slot / second operand with one shuffle pair and lane L updates acc0 of its own row while lane L^1 updates acc1
+// of the same row (step 1: rows of even lanes, step 2: rows of odd lanes).
 // ---------------------------------------------------------------------------------------------------
+constexpr int LH_BLOCK = 128, LH_U = 4, LH_QCAP = 32 * (LH_U + 1);
+template <int NK> struct LhQueue {
+  unsigned long long k0[LH_QCAP]; unsigned long long k1[NK == 2 ? LH_QCAP : 1]; unsigned long long v0[LH_QCAP], v1[LH_QCAP];
+  unsigned idx[LH_QCAP], tag[LH_QCAP], row[LH_QCAP];
+};
+enum { LH_HIT = 0, LH_AGAIN = 1, LH_NEW = 2, LH_IDLE = 3 };
+
+template <int NK>
+__device__ __forceinline__ int lh_eval(const AggTable& tab, int ks, unsigned cap, ulonglong2 hk, unsigned tag, unsigned long long k0, unsigned long long k1,
+                                       unsigned& idx, unsigned& flags) {
+  const unsigned t = (unsigned)hk.x;
+  if (t == tag) {
+    bool hit = (unsigned)(hk.x >> 48) == 0 && hk.y == k0;
+    if (NK == 2 && hit) hit = ld_relaxed_u64(tab.keys + (uint64_t)idx * ks + 2) == k1;
+    if (hit) { flags = (unsigned)(hk.x >> 32); return LH_HIT; }
+  } else if (t == TAG_EMPTY) return LH_NEW;
+  else if (t == TAG_LOCKED) return LH_AGAIN;                     // being inserted: look at the same slot again
+  idx = idx + 1 == cap ? 0 : idx + 1;
+  return LH_AGAIN;
+}
+
+// one warp step of rows that have a status: inserts for LH_NEW, the paired REDs for hits, push of LH_AGAIN rows
 template <int NK, int NACC>
-__global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
-                                                                 long long row_begin, long long n) {
-  constexpr int U = 4;                                          // rows per lane in flight
-  const unsigned lane = threadIdx.x & 31;
+__device__ __forceinline__ void lh_finish(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK>& q, int& count, unsigned lane,
+                                          unsigned long long* sink, bool has_v1, int st, unsigned idx, unsigned flags, unsigned tag,
+                                          unsigned long long k0, unsigned long long k1, unsigned long long v0, unsigned long long v1, unsigned row) {
+  constexpr unsigned NONE = 0xFFFFFFFFu;
+  if (__any_sync(0xffffffffu, st == LH_NEW)) {                  // new keys: full insert protocol, one counter update per warp step
+    bool inserted = false;
+    if (st == LH_NEW) {
+      uint64_t kw[2] = {k0, NK == 2 ? k1 : 0ULL};
+      const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash2(k0, NK == 2 ? k1 : 0ULL, 0), &flags, &inserted);
+      if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = row; st = LH_IDLE; }
+      else { idx = (unsigned)si; st = LH_HIT; }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, inserted);
+    if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
+  }
+  // accumulate (REDs unconditional: idle lanes add 0 to the warp's sink sector); accumulator entries are only ever RED
   const bool odd = lane & 1;
-  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const int as = lay.astride, w0 = fs.acc[0].word, w1 = NACC == 2 ? fs.acc[1].word : 0;
+  const unsigned mi = st == LH_HIT ? idx : NONE;
+  unsigned long long* const mine = mi != NONE ? tab.accs + (uint64_t)mi * as + w0 : sink;
+  const unsigned long long mv = mi != NONE ? v0 : 0ULL;
+  if (NACC == 1) red_add_u64(mine, mv);
+  else {
+    const unsigned pi = __shfl_xor_sync(0xffffffffu, mi, 1);                                       // neighbour's slot
+    const unsigned long long pv1 = has_v1 ? __shfl_xor_sync(0xffffffffu, v1, 1) : 1ULL;
+    unsigned long long* const theirs = pi != NONE ? tab.accs + (uint64_t)pi * as + w1 : sink;
+    const unsigned long long tv = pi != NONE ? pv1 : 0ULL;
+    red_add_u64(odd ? theirs : mine, odd ? tv : mv);            // step 1: rows of even lanes: {acc0 by the owner, acc1 by its odd neighbour}
+    red_add_u64(odd ? mine : theirs, odd ? mv : tv);            // step 2: rows of odd lanes
+  }
+  if (mi != NONE) {
+    unsigned long long* ke = tab.keys + (uint64_t)mi * lay.kstride;
+    slot_mark(ke, flags, fs.acc[0].vbit); if (NACC == 2) slot_mark(ke, flags, fs.acc[1].vbit);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, st == LH_AGAIN);
+  if (m) {
+    if (st == LH_AGAIN) {
+      const int at = count + __popc(m & ((1u << lane) - 1));
+      q.k0[at] = k0; if (NK == 2) q.k1[at] = k1; q.v0[at] = v0; q.v1[at] = v1; q.idx[at] = idx; q.tag[at] = tag; q.row[at] = row;
+    }
+    count += __popc(m);
+  }
+}
+
+template <int NK, int NACC>
+__device__ __forceinline__ void lh_drain(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK>& q, int& count, unsigned lane,
+                                         unsigned long long* sink, bool has_v1) {
+  const int nb = count < 32 ? count : 32;
+  __syncwarp();
+  count -= nb;
+  const bool act = (int)lane < nb; const int e = count + (act ? lane : 0);
+  const unsigned long long k0 = q.k0[e], k1 = NK == 2 ? q.k1[e] : 0ULL, v0 = q.v0[e], v1 = q.v1[e];
+  unsigned idx = q.idx[e], flags = 0; const unsigned tag = q.tag[e], row = q.row[e];
+  __syncwarp();                                                 // entries are in registers: the stack may be overwritten
+  int st = LH_IDLE;
+  if (act) st = lh_eval<NK>(tab, lay.kstride, (unsigned)tab.capacity, ld_relaxed_v2u64(tab.keys + (uint64_t)idx * lay.kstride), tag, k0, k1, idx, flags);
+  lh_finish<NK, NACC>(fs, lay, tab, q, count, lane, sink, has_v1, st, idx, flags, tag, k0, k1, v0, v1, row);
+}
+
+template <int NK, int NACC>
+__global__ void __launch_bounds__(LH_BLOCK, 6) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                     long long row_begin, long long n) {
+  constexpr int U = LH_U;
+  __shared__ LhQueue<NK> queues[LH_BLOCK / 32];
+  LhQueue<NK>& q = queues[threadIdx.x >> 5];
+  int count = 0;                                                // warp-uniform stack height
+  const unsigned lane = threadIdx.x & 31;
+  const long long gwarp = (long long)blockIdx.x * (LH_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (LH_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
   const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
   const long long* vcol0 = fs.acc[0].kind == FAST_ACC_ADD ? (const long long*)cols.col[fs.acc[0].col].values + row_begin : nullptr;
   const long long* vcol1 = (NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD) ? (const long long*)cols.col[fs.acc[1].col].values + row_begin : nullptr;
-  const int w0 = fs.acc[0].word, w1 = NACC == 2 ? fs.acc[1].word : 0;
   unsigned long long* const sink = warp_sink(fs, gwarp, lane);
-  const uint64_t cap = tab.capacity; const int ks = lay.kstride, as = lay.astride;
+  const unsigned cap = (unsigned)tab.capacity; const int ks = lay.kstride;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    long long k0[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U];
+    unsigned long long k0[U], k1[U], v0[U], v1[U]; bool alive[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long rel = (unit0 + u) * 32 + lane;
       alive[u] = rel < n;
-      k0[u] = alive[u] ? ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
-      k1[u] = (NK == 2 && alive[u]) ? ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      k0[u] = alive[u] ? (unsigned long long)ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      k1[u] = (NK == 2 && alive[u]) ? (unsigned long long)ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
       v0[u] = (vcol0 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol0 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
       v1[u] = (vcol1 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol1 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
     }
@@ -338,70 +427,23 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_hash_kernel(const ColTable 
         alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
       }
     }
-    // probe walk: every pending row advances one slot per round; collisions are common at load 0.5 (~25 % of the
-    // first probes) so the walk is lane-parallel; only genuinely NEW keys take the insert section
-    unsigned long long* slot[U]; uint64_t h[U], idx[U]; unsigned flags[U]; bool need[U], ins[U];
+    unsigned idx[U], tag[U]; ulonglong2 hk[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {                               // first probes: U independent 16-byte loads in flight per lane
+      const uint64_t h = agg_hash2(k0[u], NK == 2 ? k1[u] : 0ULL, 0);
+      idx[u] = __umulhi((unsigned)(h >> 32), cap); tag[u] = agg_tag(h);
+      if (alive[u]) hk[u] = ld_relaxed_v2u64(tab.keys + (uint64_t)idx[u] * ks);                   // {hdr, key0}
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      h[u] = agg_hash2((uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL, 0);
-      idx[u] = agg_first_slot(h[u], cap); need[u] = alive[u]; ins[u] = false; slot[u] = nullptr; flags[u] = 0;
+      unsigned flags = 0;
+      const int st = alive[u] ? lh_eval<NK>(tab, ks, cap, hk[u], tag[u], k0[u], k1[u], idx[u], flags) : LH_IDLE;
+      lh_finish<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr, st, idx[u], flags, tag[u], k0[u], k1[u], v0[u], v1[u],
+                          (unsigned)((unit0 + u) * 32 + lane));
     }
-    while (true) {
-      ulonglong2 hk[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) if (need[u]) hk[u] = ld_relaxed_v2u64(tab.keys + idx[u] * (uint64_t)ks);     // {hdr, key0}: one 16-byte probe
-      bool pending = false;
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (!need[u]) continue;
-        const unsigned tag = agg_tag(h[u]), t = (unsigned)hk[u].x;
-        unsigned long long* sp = tab.keys + idx[u] * (uint64_t)ks;
-        if (t == tag) {
-          bool hit = (unsigned)(hk[u].x >> 48) == 0 && hk[u].y == (uint64_t)k0[u];
-          if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)k1[u];
-          if (hit) { slot[u] = sp; flags[u] = (unsigned)(hk[u].x >> 32); need[u] = false; }
-          else idx[u] = agg_next_slot(idx[u], cap);
-        } else if (t == TAG_EMPTY) { need[u] = false; ins[u] = true; }
-        else if (t != TAG_LOCKED) idx[u] = agg_next_slot(idx[u], cap);      // another key: next slot (locked: look again)
-        pending |= need[u];
-      }
-      if (!__any_sync(0xffffffffu, pending)) break;
-    }
-    bool any_ins = false;
-#pragma unroll
-    for (int u = 0; u < U; u++) any_ins |= ins[u];
-    if (__any_sync(0xffffffffu, any_ins)) {                     // new keys: full insert protocol, one counter update per warp step
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        bool inserted = false;
-        if (ins[u]) {
-          uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
-          idx[u] = agg_find_or_insert(lay, tab, kw, 0, h[u], &flags[u], &inserted);
-          if (idx[u] == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); alive[u] = false; slot[u] = nullptr; }
-          else slot[u] = tab.keys + idx[u] * (uint64_t)ks;
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, inserted);
-        if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
-      }
-    }
-    // accumulate (REDs unconditional: idle lanes add 0 to the warp's sink sector)
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const bool live = alive[u] && slot[u] != nullptr;
-      unsigned long long* const ae = tab.accs + idx[u] * (uint64_t)as;          // accumulator entry (never read here: RED only)
-      if (NACC == 1) {
-        red_add_u64(live ? ae + w0 : sink, live ? v0[u] : 0ULL);
-      } else {
-        const unsigned long long ps = __shfl_xor_sync(0xffffffffu, live ? (unsigned long long)ae : 0ULL, 1);
-        const unsigned long long pv1 = __shfl_xor_sync(0xffffffffu, v1[u], 1);
-        unsigned long long* const mine = live ? ae + w0 : sink;  const unsigned long long mv = live ? v0[u] : 0ULL;
-        unsigned long long* const theirs = ps ? (unsigned long long*)ps + w1 : sink;  const unsigned long long tv = ps ? pv1 : 0ULL;
-        red_add_u64(odd ? theirs : mine, odd ? tv : mv);        // step 1: rows of even lanes: {acc0 by the owner, acc1 by its odd neighbour}
-        red_add_u64(odd ? mine : theirs, odd ? mv : tv);        // step 2: rows of odd lanes
-      }
-      if (live) { slot_mark(slot[u], flags[u], fs.acc[0].vbit); if (NACC == 2) slot_mark(slot[u], flags[u], fs.acc[1].vbit); }
-    }
+    while (count >= 32) lh_drain<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr);
   }
+  while (count > 0) lh_drain<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr);
 }
 
 static int fast_grid(int64_t ntiles) {
@@ -428,9 +470,10 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
     return 1;
   }
   if (!dg && fs.lean) {
-    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
-    if (fs.nkeys == 1) { if (fs.nacc == 2) agg_lean_hash_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<1, 1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
-    else { if (fs.nacc == 2) agg_lean_hash_kernel<2, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<2, 1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    const int64_t tiles = (n + 32 * (LH_BLOCK / 32) * LH_U - 1) / (32 * (LH_BLOCK / 32) * LH_U);
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)fast_grid(1 << 30) / 8 * 6));
+    if (fs.nkeys == 1) { if (fs.nacc == 2) agg_lean_hash_kernel<1, 2><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<1, 1><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    else { if (fs.nacc == 2) agg_lean_hash_kernel<2, 2><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<2, 1><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
     return 1;
   }
   const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);

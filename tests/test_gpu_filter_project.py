@@ -161,3 +161,19 @@ def test_lean_project_only_and_filter_only():
     assert plan.last_metrics["fast_path_launches"] > 0
     _, plan = run_fp(rb, [E.BinaryExpr(A, "GtEq", E.Literal(990, T.int64))], None)
     assert plan.last_metrics["fast_path_launches"] > 0
+
+
+@pytest.mark.parametrize("n", [1 << 20, 3_000_037])
+def test_lean_two_pass_form_large_batches(n):
+    """batches of >= 2^20 rows take the order-free count / scan / apply form: ragged tail, 3 input columns,
+    conjuncts on two of them, every selectivity regime inside one batch (sorted run + random part)"""
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 1000, n, dtype=np.int64); a[: n // 4] = np.sort(a[: n // 4])
+    b = rng.integers(-2**31, 2**31, n, dtype=np.int64)
+    c = rng.integers(-5, 5, n, dtype=np.int64)
+    rb = rb_from_cols(["a", "b", "c"], [a, b, c])
+    A, B, C = E.Column("a"), E.Column("b"), E.Column("c")
+    preds = [E.BinaryExpr(A, "GtEq", E.Literal(200, T.int64)), E.BinaryExpr(A, "LtEq", E.Literal(700, T.int64)), E.BinaryExpr(C, "NotEq", E.Literal(0, T.int64))]
+    projs = [(B, "b"), (E.BinaryExpr(A, "Multiply", C), "ac"), (E.BinaryExpr(B, "Minus", A), "d")]
+    got, plan = run_fp(rb, preds, projs, batch_rows=n, conf=native.default_conf(staging_rows=0))
+    assert plan.last_metrics["fast_path_launches"] > 0 and plan.last_metrics["gpu_kernel_launches"] >= 5

@@ -10,7 +10,10 @@ dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(42)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 
+ONLY = os.environ.get("SHAPES")       # comma-separated substrings of shape names to run
+
 def run(name, plan_bytes, cols, alg_bytes_per_row, conf=None, reps=3, steady=False):
+    if ONLY and not any(t in name for t in ONLY.split(",")): return
     best = None; steady_ns = None
     for _ in range(reps):
         with native.NativeOp(plan_bytes, conf or native.default_conf(), 0) as op:
@@ -55,6 +58,8 @@ m1 = PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs, True, PL
 run("M1 dense (lean)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20))
 run("M1 hash (gang, paired REDs)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0))
 run("M1 hash", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
+for ig in (1 << 21, 1 << 22):
+    run("M1 hash initial_groups=%d" % ig, m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=ig, agg_dense_keys=0), reps=1, steady=True)
 run("M1 generic VM kernel", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
 del k
 # M2: q1-shaped: f BETWEEN lo AND hi (s = 0.2), keys (k1 ~ U[0,2^17), k2 ~ U[0,8)), SUM(v)   (32 B/row)
