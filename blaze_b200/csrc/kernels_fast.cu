@@ -67,7 +67,8 @@ __device__ __forceinline__ unsigned long long* warp_sink(const FastSpec& fs, lon
 }
 
 // ---------------------------------------------------------------------------------------------------
-// generic gang kernel: any integer widths, validity bitmaps, 1-2 keys; DG = dense gang width (0: no dense table)
+// typed DENSE gang kernel: any integer widths, validity bitmaps; DG = dense gang width (2 or 4 words per entry).
+// (The hashed form of typed inputs is agg_lean_hash_kernel<.., TYPED = true> below.)
 // ---------------------------------------------------------------------------------------------------
 template <int NK, int NACC, int DG>
 __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
@@ -309,18 +310,20 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
 // of the same row (step 1: rows of even lanes, step 2: rows of odd lanes).
 // ---------------------------------------------------------------------------------------------------
 constexpr int LH_BLOCK = 128, LH_U = 4, LH_QCAP = 32 * (LH_U + 1);
-template <int NK> struct LhQueue {
+template <int NK, bool TYPED> struct LhQueue {
   unsigned long long k0[LH_QCAP]; unsigned long long k1[NK == 2 ? LH_QCAP : 1]; unsigned long long v0[LH_QCAP], v1[LH_QCAP];
   unsigned idx[LH_QCAP], tag[LH_QCAP], row[LH_QCAP];
+  uint8_t meta[TYPED ? LH_QCAP : 1];                            // TYPED: bits 0-1 key-is-NULL, bits 2-3 accumulator argument valid
 };
 enum { LH_HIT = 0, LH_AGAIN = 1, LH_NEW = 2, LH_IDLE = 3 };
+constexpr unsigned LH_META_PLAIN = 0xC;                         // no NULL key, both accumulator arguments valid
 
 template <int NK>
-__device__ __forceinline__ int lh_eval(const AggTable& tab, int ks, unsigned cap, ulonglong2 hk, unsigned tag, unsigned long long k0, unsigned long long k1,
-                                       unsigned& idx, unsigned& flags) {
+__device__ __forceinline__ int lh_eval(const AggTable& tab, int ks, unsigned cap, ulonglong2 hk, unsigned tag, unsigned knull, unsigned long long k0,
+                                       unsigned long long k1, unsigned& idx, unsigned& flags) {
   const unsigned t = (unsigned)hk.x;
   if (t == tag) {
-    bool hit = (unsigned)(hk.x >> 48) == 0 && hk.y == k0;
+    bool hit = (unsigned)(hk.x >> 48) == knull && hk.y == k0;
     if (NK == 2 && hit) hit = ld_relaxed_u64(tab.keys + (uint64_t)idx * ks + 2) == k1;
     if (hit) { flags = (unsigned)(hk.x >> 32); return LH_HIT; }
   } else if (t == TAG_EMPTY) return LH_NEW;
@@ -330,23 +333,25 @@ __device__ __forceinline__ int lh_eval(const AggTable& tab, int ks, unsigned cap
 }
 
 // one warp step of rows that have a status: inserts for LH_NEW, the paired REDs for hits, push of LH_AGAIN rows
-template <int NK, int NACC>
-__device__ __forceinline__ void lh_finish(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK>& q, int& count, unsigned lane,
-                                          unsigned long long* sink, bool has_v1, int st, unsigned idx, unsigned flags, unsigned tag,
+template <int NK, int NACC, bool TYPED>
+__device__ __forceinline__ void lh_finish(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK, TYPED>& q, int& count, unsigned lane,
+                                          unsigned long long* sink, bool has_v1, int st, unsigned idx, unsigned flags, unsigned tag, unsigned meta,
                                           unsigned long long k0, unsigned long long k1, unsigned long long v0, unsigned long long v1, unsigned row) {
   constexpr unsigned NONE = 0xFFFFFFFFu;
   if (__any_sync(0xffffffffu, st == LH_NEW)) {                  // new keys: full insert protocol, one counter update per warp step
     bool inserted = false;
     if (st == LH_NEW) {
       uint64_t kw[2] = {k0, NK == 2 ? k1 : 0ULL};
-      const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash2(k0, NK == 2 ? k1 : 0ULL, 0), &flags, &inserted);
+      const unsigned knull = TYPED ? (meta & 3u) : 0u;
+      const uint64_t si = agg_find_or_insert(lay, tab, kw, knull, agg_hash2(k0, NK == 2 ? k1 : 0ULL, knull), &flags, &inserted);
       if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = row; st = LH_IDLE; }
       else { idx = (unsigned)si; st = LH_HIT; }
     }
     const unsigned b = __ballot_sync(0xffffffffu, inserted);
     if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
   }
-  // accumulate (REDs unconditional: idle lanes add 0 to the warp's sink sector); accumulator entries are only ever RED
+  // accumulate (REDs unconditional: idle lanes add 0 to the warp's sink sector); accumulator entries are only ever RED.
+  // A NULL argument arrives as the value 0 and only skips the "has a value" mark.
   const bool odd = lane & 1;
   const int as = lay.astride, w0 = fs.acc[0].word, w1 = NACC == 2 ? fs.acc[1].word : 0;
   const unsigned mi = st == LH_HIT ? idx : NONE;
@@ -363,87 +368,226 @@ __device__ __forceinline__ void lh_finish(const FastSpec& fs, const AggLayout& l
   }
   if (mi != NONE) {
     unsigned long long* ke = tab.keys + (uint64_t)mi * lay.kstride;
-    slot_mark(ke, flags, fs.acc[0].vbit); if (NACC == 2) slot_mark(ke, flags, fs.acc[1].vbit);
+    if (!TYPED || (meta & 4u)) slot_mark(ke, flags, fs.acc[0].vbit);
+    if (NACC == 2 && (!TYPED || (meta & 8u))) slot_mark(ke, flags, fs.acc[1].vbit);
   }
   const unsigned m = __ballot_sync(0xffffffffu, st == LH_AGAIN);
   if (m) {
     if (st == LH_AGAIN) {
       const int at = count + __popc(m & ((1u << lane) - 1));
       q.k0[at] = k0; if (NK == 2) q.k1[at] = k1; q.v0[at] = v0; q.v1[at] = v1; q.idx[at] = idx; q.tag[at] = tag; q.row[at] = row;
+      if (TYPED) q.meta[at] = (uint8_t)meta;
     }
     count += __popc(m);
   }
 }
 
-template <int NK, int NACC>
-__device__ __forceinline__ void lh_drain(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK>& q, int& count, unsigned lane,
+template <int NK, int NACC, bool TYPED>
+__device__ __forceinline__ void lh_drain(const FastSpec& fs, const AggLayout& lay, const AggTable& tab, LhQueue<NK, TYPED>& q, int& count, unsigned lane,
                                          unsigned long long* sink, bool has_v1) {
   const int nb = count < 32 ? count : 32;
   __syncwarp();
   count -= nb;
   const bool act = (int)lane < nb; const int e = count + (act ? lane : 0);
   const unsigned long long k0 = q.k0[e], k1 = NK == 2 ? q.k1[e] : 0ULL, v0 = q.v0[e], v1 = q.v1[e];
-  unsigned idx = q.idx[e], flags = 0; const unsigned tag = q.tag[e], row = q.row[e];
+  unsigned idx = q.idx[e], flags = 0; const unsigned tag = q.tag[e], row = q.row[e], meta = TYPED ? q.meta[e] : LH_META_PLAIN;
   __syncwarp();                                                 // entries are in registers: the stack may be overwritten
   int st = LH_IDLE;
-  if (act) st = lh_eval<NK>(tab, lay.kstride, (unsigned)tab.capacity, ld_relaxed_v2u64(tab.keys + (uint64_t)idx * lay.kstride), tag, k0, k1, idx, flags);
-  lh_finish<NK, NACC>(fs, lay, tab, q, count, lane, sink, has_v1, st, idx, flags, tag, k0, k1, v0, v1, row);
+  if (act) st = lh_eval<NK>(tab, lay.kstride, (unsigned)tab.capacity, ld_relaxed_v2u64(tab.keys + (uint64_t)idx * lay.kstride), tag, TYPED ? (meta & 3u) : 0u, k0, k1, idx, flags);
+  lh_finish<NK, NACC, TYPED>(fs, lay, tab, q, count, lane, sink, has_v1, st, idx, flags, tag, meta, k0, k1, v0, v1, row);
 }
 
-template <int NK, int NACC>
-__global__ void __launch_bounds__(LH_BLOCK, 6) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
-                                                                     long long row_begin, long long n) {
+// TYPED = false: non-null 8-byte-aligned int64 columns (plain streaming loads); TYPED = true: any integer width,
+// validity bitmaps on keys (NULL is a group of its own: its bit goes into the hash and the header), on accumulator
+// arguments (NULL adds nothing) and on filter columns (NULL -> row dropped, cached_exprs_evaluator.rs:518-520)
+template <int NK, int NACC, bool TYPED>
+__global__ void __launch_bounds__(LH_BLOCK, TYPED ? 4 : 6) agg_lean_hash_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                                long long row_begin, long long n) {
   constexpr int U = LH_U;
-  __shared__ LhQueue<NK> queues[LH_BLOCK / 32];
-  LhQueue<NK>& q = queues[threadIdx.x >> 5];
+  __shared__ LhQueue<NK, TYPED> queues[LH_BLOCK / 32];
+  LhQueue<NK, TYPED>& q = queues[threadIdx.x >> 5];
   int count = 0;                                                // warp-uniform stack height
   const unsigned lane = threadIdx.x & 31;
   const long long gwarp = (long long)blockIdx.x * (LH_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (LH_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
+  const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
   const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
   const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
-  const long long* vcol0 = fs.acc[0].kind == FAST_ACC_ADD ? (const long long*)cols.col[fs.acc[0].col].values + row_begin : nullptr;
-  const long long* vcol1 = (NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD) ? (const long long*)cols.col[fs.acc[1].col].values + row_begin : nullptr;
+  const long long* vcol0 = add0 ? (const long long*)cols.col[fs.acc[0].col].values + row_begin : nullptr;
+  const long long* vcol1 = add1 ? (const long long*)cols.col[fs.acc[1].col].values + row_begin : nullptr;
   unsigned long long* const sink = warp_sink(fs, gwarp, lane);
   const unsigned cap = (unsigned)tab.capacity; const int ks = lay.kstride;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    unsigned long long k0[U], k1[U], v0[U], v1[U]; bool alive[U];
+    unsigned long long k0[U], k1[U], v0[U], v1[U]; bool alive[U]; unsigned meta[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long rel = (unit0 + u) * 32 + lane;
-      alive[u] = rel < n;
-      k0[u] = alive[u] ? (unsigned long long)ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
-      k1[u] = (NK == 2 && alive[u]) ? (unsigned long long)ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
-      v0[u] = (vcol0 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol0 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
-      v1[u] = (vcol1 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol1 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
+      alive[u] = rel < n; meta[u] = LH_META_PLAIN;
+      if (!TYPED) {
+        k0[u] = alive[u] ? (unsigned long long)ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+        k1[u] = (NK == 2 && alive[u]) ? (unsigned long long)ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+        v0[u] = (vcol0 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol0 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
+        v1[u] = (vcol1 && alive[u]) ? (unsigned long long)ld_stream_vec(vcol1 + rel, (i64xG<1>*)nullptr).v[0] : 1ULL;
+      } else {
+        k0[u] = 0; k1[u] = 0; v0[u] = 1; v1[u] = 1;
+        if (alive[u]) {
+          const long long row = row_begin + rel;
+          { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) k0[u] = (unsigned long long)col_load_int(c, fs.key_phys[0], row); else meta[u] |= 1u; }
+          if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) k1[u] = (unsigned long long)col_load_int(c, fs.key_phys[1], row); else meta[u] |= 2u; }
+          if (fs.acc[0].col >= 0) {
+            const DevCol& c = cols.col[fs.acc[0].col];
+            if (!col_valid(c, row)) { meta[u] &= ~4u; v0[u] = 0; } else if (add0) v0[u] = (unsigned long long)col_load_int(c, fs.acc[0].phys, row);
+          }
+          if (NACC == 2 && fs.acc[1].col >= 0) {
+            const DevCol& c = cols.col[fs.acc[1].col];
+            if (!col_valid(c, row)) { meta[u] &= ~8u; v1[u] = 0; } else if (add1) v1[u] = (unsigned long long)col_load_int(c, fs.acc[1].phys, row);
+          }
+        }
+      }
     }
     for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
-      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
+      if (!TYPED) {
+        const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const long long rel = (unit0 + u) * 32 + lane;
-        const long long x = rel < n ? ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0] : 0;
-        alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
+        for (int u = 0; u < U; u++) {
+          const long long rel = (unit0 + u) * 32 + lane;
+          const long long x = rel < n ? ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0] : 0;
+          alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
+        }
+      } else {
+        const DevCol& c = cols.col[fs.filt[f].col];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long row = row_begin + (unit0 + u) * 32 + lane;
+          if (alive[u]) alive[u] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
+        }
       }
     }
     unsigned idx[U], tag[U]; ulonglong2 hk[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {                               // first probes: U independent 16-byte loads in flight per lane
-      const uint64_t h = agg_hash2(k0[u], NK == 2 ? k1[u] : 0ULL, 0);
+      const uint64_t h = agg_hash2(k0[u], NK == 2 ? k1[u] : 0ULL, TYPED ? (meta[u] & 3u) : 0u);
       idx[u] = __umulhi((unsigned)(h >> 32), cap); tag[u] = agg_tag(h);
       if (alive[u]) hk[u] = ld_relaxed_v2u64(tab.keys + (uint64_t)idx[u] * ks);                   // {hdr, key0}
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       unsigned flags = 0;
-      const int st = alive[u] ? lh_eval<NK>(tab, ks, cap, hk[u], tag[u], k0[u], k1[u], idx[u], flags) : LH_IDLE;
-      lh_finish<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr, st, idx[u], flags, tag[u], k0[u], k1[u], v0[u], v1[u],
-                          (unsigned)((unit0 + u) * 32 + lane));
+      const int st = alive[u] ? lh_eval<NK>(tab, ks, cap, hk[u], tag[u], TYPED ? (meta[u] & 3u) : 0u, k0[u], k1[u], idx[u], flags) : LH_IDLE;
+      lh_finish<NK, NACC, TYPED>(fs, lay, tab, q, count, lane, sink, TYPED ? NACC == 2 : vcol1 != nullptr, st, idx[u], flags, tag[u], meta[u], k0[u], k1[u], v0[u], v1[u],
+                                 (unsigned)((unit0 + u) * 32 + lane));
     }
-    while (count >= 32) lh_drain<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr);
+    while (count >= 32) lh_drain<NK, NACC, TYPED>(fs, lay, tab, q, count, lane, sink, TYPED ? NACC == 2 : vcol1 != nullptr);
   }
-  while (count > 0) lh_drain<NK, NACC>(fs, lay, tab, q, count, lane, sink, vcol1 != nullptr);
+  while (count > 0) lh_drain<NK, NACC, TYPED>(fs, lay, tab, q, count, lane, sink, TYPED ? NACC == 2 : vcol1 != nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMALL dense tables (<= 4096 words, i.e. a few hundred to 2048 groups): CTA-private copy in shared memory.
+// With few groups every RED of a warp lands on a handful of L2 sectors and the L2 serialises them: 64 groups ran
+// at 4.6e9 rows/s through the global-table kernel.  Here each CTA accumulates into its own shared-memory table with
+// native 32-bit shared atomics (a 64-bit wrapping add = low-half add returning the old value + high-half add of
+// the carry: exact mod 2^64 in any order) and adds its non-zero words to the global dense table once, at the end.
+// TYPED = false: non-null int64 columns; TYPED = true: any integer width + validity bitmaps (NULL key -> hashed slot).
+// ---------------------------------------------------------------------------------------------------
+constexpr int DS_MAX_WORDS = 4096;
+__device__ __forceinline__ void smem_add64(unsigned* w, unsigned long long v) {
+  const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  unsigned carry = 0;
+  if (lo) { const unsigned old = atomicAdd(w, lo); carry = old + lo < old; }
+  if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+template <int NACC, bool TYPED>
+__global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                  long long row_begin, long long n) {
+  constexpr int U = 4;
+  __shared__ unsigned s_tab[2 * DS_MAX_WORDS];
+  const int G = fs.dense_stride;
+  const unsigned nwords = (unsigned)fs.dense_cap * G;
+  for (unsigned i = threadIdx.x; i < 2 * nwords; i += FA_BLOCK) s_tab[i] = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const long long nunits = (n + 31) / 32;
+  const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
+  const long long base = fs.dense_base; const unsigned long long cap = fs.dense_cap;
+
+  for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
+    long long k[U]; unsigned long long v0[U], v1[U]; bool alive[U]; unsigned meta[U];       // meta: bit0 key NULL, bit2/3 argument valid
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long rel = (unit0 + u) * 32 + lane, row = row_begin + rel;
+      alive[u] = rel < n; meta[u] = 0xC; k[u] = 0; v0[u] = 1; v1[u] = 1;
+      if (!alive[u]) continue;
+      if (!TYPED) {
+        k[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[0]].values + row, (i64xG<1>*)nullptr).v[0];
+        if (add0) v0[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[0].col].values + row, (i64xG<1>*)nullptr).v[0];
+        if (add1) v1[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[1].col].values + row, (i64xG<1>*)nullptr).v[0];
+      } else {
+        { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) k[u] = col_load_int(c, fs.key_phys[0], row); else meta[u] |= 1u; }
+        if (fs.acc[0].col >= 0) {
+          const DevCol& c = cols.col[fs.acc[0].col];
+          if (!col_valid(c, row)) { meta[u] &= ~4u; v0[u] = 0; } else if (add0) v0[u] = (unsigned long long)col_load_int(c, fs.acc[0].phys, row);
+        }
+        if (NACC == 2 && fs.acc[1].col >= 0) {
+          const DevCol& c = cols.col[fs.acc[1].col];
+          if (!col_valid(c, row)) { meta[u] &= ~8u; v1[u] = 0; } else if (add1) v1[u] = (unsigned long long)col_load_int(c, fs.acc[1].phys, row);
+        }
+      }
+    }
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts (NULL -> row dropped)
+      const DevCol& c = cols.col[fs.filt[f].col];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long row = row_begin + (unit0 + u) * 32 + lane;
+        if (!alive[u]) continue;
+        if (!TYPED) alive[u] = cmp_apply(fs.filt[f].op, ld_stream_vec((const long long*)c.values + row, (i64xG<1>*)nullptr).v[0], fs.filt[f].lit);
+        else alive[u] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned long long idx = (unsigned long long)(k[u] - base);
+      const bool in = alive[u] && !(meta[u] & 1u) && idx < cap;
+      if (in) {
+        unsigned* const e = s_tab + 2 * (unsigned)idx * G;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (m >= G) break;
+          const int src = fs.dense_word_src[m];                 // -1: row counter, -2: padding, j: accumulator j
+          if (src == -1) smem_add64(e + 2 * m, 1ULL);
+          else if (src == 0) { if (meta[u] & 4u) smem_add64(e + 2 * m, v0[u]); }
+          else if (src == 1 && NACC == 2) { if (meta[u] & 8u) smem_add64(e + 2 * m, v1[u]); }
+        }
+      }
+      // keys outside the dense range / NULL keys (rare): straight to the hashed slots
+      const bool fb = alive[u] && !in;
+      if (__any_sync(0xffffffffu, fb)) {
+        bool inserted = false;
+        if (fb) {
+          uint64_t kw[2] = {(uint64_t)k[u], 0};
+          const unsigned knull = meta[u] & 1u;
+          unsigned fl = 0;
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, knull, agg_hash2(kw[0], 0ULL, knull), &fl, &inserted);
+          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); }
+          else {
+            unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
+            unsigned long long* const ke = tab.keys + si * (uint64_t)lay.kstride;
+            if (meta[u] & 4u) { red_add_u64(p + fs.acc[0].word, v0[u]); slot_mark(ke, fl, fs.acc[0].vbit); }
+            if (NACC == 2 && (meta[u] & 8u)) { red_add_u64(p + fs.acc[1].word, v1[u]); slot_mark(ke, fl, fs.acc[1].vbit); }
+          }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, inserted);
+        if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
+      }
+    }
+  }
+  __syncthreads();
+  for (unsigned w = threadIdx.x; w < nwords; w += FA_BLOCK) {
+    const unsigned long long val = (unsigned long long)s_tab[2 * w] | ((unsigned long long)s_tab[2 * w + 1] << 32);
+    if (val) red_add_u64(fs.dense_tab + w, val);
+  }
 }
 
 static int fast_grid(int64_t ntiles) {
@@ -455,13 +599,19 @@ static int fast_grid(int64_t ntiles) {
 template <int NK, int NACC>
 static void launch_gang(int dg, int grid, cudaStream_t s, const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n) {
   if (dg == 4) agg_gang_update_kernel<NK, NACC, 4><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-  else if (dg == 2) agg_gang_update_kernel<NK, NACC, 2><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-  else agg_gang_update_kernel<NK, NACC, 0><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
+  else agg_gang_update_kernel<NK, NACC, 2><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
 }
 
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
   const int dg = fs.dense ? fs.dense_stride : 0;
+  if (dg && fs.dense_cap * (unsigned long long)dg <= (unsigned long long)DS_MAX_WORDS) {
+    // persistent CTAs, 3 per SM (32 KB of shared memory each); every CTA flushes its private table once
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + FA_BLOCK * 4 - 1) / (FA_BLOCK * 4), (int64_t)fast_grid(1 << 30) / 8 * 3));
+    if (fs.lean) { if (fs.nacc == 2) agg_dense_smem_kernel<2, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_dense_smem_kernel<1, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    else { if (fs.nacc == 2) agg_dense_smem_kernel<2, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_dense_smem_kernel<1, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    return 1;
+  }
   if (dg && fs.lean) {
     const int u = dg == 2 ? 4 : 2;
     const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
@@ -469,16 +619,18 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
     else { if (dg == 2) agg_lean_dense_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<1, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
     return 1;
   }
-  if (!dg && fs.lean) {
+  if (!dg) {
     const int64_t tiles = (n + 32 * (LH_BLOCK / 32) * LH_U - 1) / (32 * (LH_BLOCK / 32) * LH_U);
-    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)fast_grid(1 << 30) / 8 * 6));
-    if (fs.nkeys == 1) { if (fs.nacc == 2) agg_lean_hash_kernel<1, 2><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<1, 1><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
-    else { if (fs.nacc == 2) agg_lean_hash_kernel<2, 2><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_hash_kernel<2, 1><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)fast_grid(1 << 30) / 8 * (fs.lean ? 6 : 4)));
+#define B200Q_LH(NK, NACC, TYPED) agg_lean_hash_kernel<NK, NACC, TYPED><<<g, LH_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.lean) { if (fs.nkeys == 1) { if (fs.nacc == 2) B200Q_LH(1, 2, false); else B200Q_LH(1, 1, false); } else { if (fs.nacc == 2) B200Q_LH(2, 2, false); else B200Q_LH(2, 1, false); } }
+    else { if (fs.nkeys == 1) { if (fs.nacc == 2) B200Q_LH(1, 2, true); else B200Q_LH(1, 1, true); } else { if (fs.nacc == 2) B200Q_LH(2, 2, true); else B200Q_LH(2, 1, true); } }
+#undef B200Q_LH
     return 1;
   }
   const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);
-  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
-  else { if (fs.nacc == 2) launch_gang<2, 2>(0, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(0, grid, s, cols, fs, lay, tab, row_begin, n); }
+  // typed dense table (one key): rows outside the dense range / NULL keys fall through to the hashed slots inside the kernel
+  if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n);
   return 1;
 }
 

@@ -572,6 +572,9 @@ class AggStage : public Stage {
     const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(h[2], cx.conf.agg_initial_groups), 1 << 16);
     if (range > budget || range > ((uint64_t)1 << 26)) return;          // sparse keys: stay on the hash table
     const uint64_t r = (uint64_t)range, margin = r / 8 + 64;
+    // typed / nullable inputs: the hashed kernel (3.6e10 rows/s on M1) beats the typed dense-table kernel (2.2e10) unless
+    // the table is small enough for the shared-memory form
+    if (!lean_ok(ct, 0) && (r + 2 * margin) * 4 > 4096) return;
     fs_.dense_base = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
     fs_.dense_cap = r + 2 * margin;
     dense_layout();

@@ -12,15 +12,18 @@ peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PE
 
 ONLY = os.environ.get("SHAPES")       # comma-separated substrings of shape names to run
 
-def run(name, plan_bytes, cols, alg_bytes_per_row, conf=None, reps=3, steady=False):
+def run(name, plan_bytes, cols, alg_bytes_per_row, conf=None, reps=3, steady=False, valid=None):
     if ONLY and not any(t in name for t in ONLY.split(",")): return
+    valid = valid or [None] * len(cols)
+    spec = [(c.data_ptr(), (vb.data_ptr() if vb is not None else 0), rows) for c, vb in zip(cols, valid)]
+    keep = list(cols) + [vb for vb in valid if vb is not None]
     best = None; steady_ns = None
     for _ in range(reps):
         with native.NativeOp(plan_bytes, conf or native.default_conf(), 0) as op:
-            op.push_device(native.DeviceBatch([(c.data_ptr(), 0, rows) for c in cols], rows, 0, keepalive=cols))
+            op.push_device(native.DeviceBatch(spec, rows, 0, keepalive=keep))
             if steady:      # second pass over the same rows: every group already exists (steady-state cost, no inserts)
                 op.sync(); m0 = op.metrics()
-                op.push_device(native.DeviceBatch([(c.data_ptr(), 0, rows) for c in cols], rows, 0, keepalive=cols))
+                op.push_device(native.DeviceBatch(spec, rows, 0, keepalive=keep))
                 op.sync(); m1 = op.metrics()
                 steady_ns = m1["hot_kernel_ns"] - m0["hot_kernel_ns"]
             op.finish()
@@ -60,6 +63,20 @@ run("M1 hash (gang, paired REDs)", m1.plan_bytes(), [k, v], 16.0, native.default
 run("M1 hash", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
 for ig in (1 << 21, 1 << 22):
     run("M1 hash initial_groups=%d" % ig, m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=ig, agg_dense_keys=0), reps=1, steady=True)
+# typed / nullable inputs through the hashed path: int32 key, 10 % NULL values (validity bitmaps)  (12.25 B/row)
+k32 = k.to(torch.int32)
+vbits = torch.full(((rows + 7) // 8,), 0xFF, dtype=torch.uint8, device=dev); vbits[::10] = 0
+s1t = T.Schema([T.Field("k", T.int32, False), T.Field("v", T.int64, True)])
+aggs_t = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], s1t, T.int64)), E.AggExpr("c", E.PARTIAL, PL.create_agg(E.AGG_COUNT, [E.Column("v")], s1t, T.int64))]
+m1t = PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs_t, True, PL.MemoryExec(s1t))
+run("M1 typed hash (int32 key, nullable v)", m1t.plan_bytes(), [k32, v], 12.125, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True, valid=[None, vbits])
+run("M1 typed dense (int32 key, nullable v)", m1t.plan_bytes(), [k32, v], 12.125, native.default_conf(agg_initial_groups=1 << 20), reps=2, valid=[None, vbits])
+del k32, vbits
+# low cardinality: 64 groups (every RED of a warp lands on a handful of sectors)
+klow = torch.randint(0, 64, (rows,), dtype=torch.int64, device=dev, generator=g)
+run("M1 low cardinality (64 groups) dense", m1.plan_bytes(), [klow, v], 16.0, native.default_conf())
+run("M1 low cardinality (64 groups) hash", m1.plan_bytes(), [klow, v], 16.0, native.default_conf(agg_dense_keys=0), reps=1, steady=True)
+del klow
 run("M1 generic VM kernel", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
 del k
 # M2: q1-shaped: f BETWEEN lo AND hi (s = 0.2), keys (k1 ~ U[0,2^17), k2 ~ U[0,8)), SUM(v)   (32 B/row)
