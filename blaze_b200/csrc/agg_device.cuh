@@ -79,8 +79,7 @@ __device__ __forceinline__ uint64_t agg_find_or_insert(const AggLayout& lay, con
         for (int i = 0; i < lay.astride; i++) ae[i] = lay.init[i];
         flags = lay.init_flags | (knull << 16);
         ((unsigned*)ke)[1] = flags;
-        __threadfence();
-        st_release_u32((unsigned*)ke, tag);
+        st_release_u32((unsigned*)ke, tag);                                       // release: key words, flags and accumulator identities first
         *inserted = true;            // the caller adds to tab.counters[0] (warp-aggregated where it can)
         *flags_out = flags;
         return s;

@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
   const unsigned m = lane % G, gl = lane - m;                   // my word index inside the gang, first lane of my gang
   const long long ntiles = (n + FA_TILE - 1) / FA_TILE;
   // which accumulator (if any) this lane updates: dense entries follow fs.dense_word_src, hashed slots acc m
-  const int src = DENSE ? fs.dense_word_src[m] : (int)m;        // -1: row counter (+1), -2: padding (+0), j: accumulator j
+  const int src = DENSE ? fs.dense_word_src[m] : (int)m;        // -1: row counter (+1), -2: padding (+0), j: accumulator j, 2+j: valid arguments of j (+1)
   const bool has_acc = src >= 0 && src < NACC;
+  const int vsrc_col = src >= 2 ? fs.acc[src - 2].col : -1;     // valid counter: counts the rows whose argument is not NULL
   const int acc_col = has_acc ? fs.acc[src].col : -1;
   const int acc_kind = has_acc ? fs.acc[src].kind : FAST_ACC_COUNT;
   const int acc_phys = has_acc ? fs.acc[src].phys : PH_I64;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
           act[s] = col_valid(c, row);
           if (acc_kind == FAST_ACC_ADD) val[s] = act[s] ? (unsigned long long)col_load_int(c, acc_phys, row) : 0ULL;
         }
+        if (vsrc_col >= 0) act[s] = col_valid(cols.col[vsrc_col], row);
       }
       // fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
       for (int f = 0; f < fs.nfilt; f++) {
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const long long* kcol = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
-  const int src = fs.dense_word_src[m];                         // -1: row counter (+1), -2: padding (+0), j: accumulator j
+  const int src = fs.dense_word_src[m];                         // -1: row counter (+1), -2: padding (+0), j: accumulator j, 2+j: valid arguments of j (+1: inputs are non-null here)
   const bool has_acc = src >= 0 && src < NACC;
   const bool is_add = has_acc && fs.acc[has_acc ? src : 0].kind == FAST_ACC_ADD;
   const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[src].col].values + row_begin : nullptr;
@@ -555,10 +557,11 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable
 #pragma unroll
         for (int m = 0; m < 4; m++) {
           if (m >= G) break;
-          const int src = fs.dense_word_src[m];                 // -1: row counter, -2: padding, j: accumulator j
+          const int src = fs.dense_word_src[m];                 // -1: row counter, -2: padding, j: accumulator j, 2+j: its valid counter
           if (src == -1) smem_add64(e + 2 * m, 1ULL);
           else if (src == 0) { if (meta[u] & 4u) smem_add64(e + 2 * m, v0[u]); }
           else if (src == 1 && NACC == 2) { if (meta[u] & 8u) smem_add64(e + 2 * m, v1[u]); }
+          else if (src >= 2) { if (meta[u] & (4u << (src - 2))) smem_add64(e + 2 * m, 1ULL); }     // valid arguments of accumulator src-2
         }
       }
       // keys outside the dense range / NULL keys (rare): straight to the hashed slots

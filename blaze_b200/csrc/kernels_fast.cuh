@@ -16,7 +16,7 @@ struct FastSpec {
   unsigned long long dense_cap;                           // entries of dense_stride words
   unsigned long long* dense_tab;
   int8_t dense_stride;                                    // 2 or 4 words per entry (= gang width)
-  int8_t dense_word_src[4];                               // per entry word: -1 row counter (+1), -2 padding (+0), j accumulator j
+  int8_t dense_word_src[4];                               // per entry word: -1 row counter (+1), -2 padding (+0), j accumulator j, 2+j valid arguments of accumulator j
   uint8_t dense_presence_word;                            // word that is non-zero iff the entry holds a group
   uint8_t _pad1[2];
   unsigned long long* sink;                               // FAST_SINK_WARPS x 4 words: per-warp scratch sector for no-op REDs

@@ -510,15 +510,8 @@ class AggStage : public Stage {
     sink_ = DevMem::alloc((size_t)FAST_SINK_WARPS * 32, cx.stream, true);
     fs.sink = (unsigned long long*)sink_->ptr;
     fs_ = fs; fast_ok_ = true;
-    // DENSE mode needs: one key; every SUM either never NULL or validated by a COUNT over the same column
+    // DENSE mode needs: one key and an entry of at most 4 words (dense_layout)
     dense_possible_ = lay_.nkeys == 1 && cx.conf.agg_dense_keys != 0;
-    for (int j = 0; j < lay_.nacc && dense_possible_; j++) {
-      if (fs_.acc[j].kind == FAST_ACC_ADD && fs_.acc[j].vbit != 0xFF) {
-        bool ok = false;
-        for (int i = 0; i < lay_.nacc; i++) ok |= i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col;
-        dense_possible_ = ok;
-      }
-    }
     if (dense_possible_) {
       for (size_t c = 0; c < emit_.size(); c++) {
         const EmitCol& ec = emit_[c].ec;
@@ -527,32 +520,37 @@ class AggStage : public Stage {
         if (ec.kind != EMIT_ACC_VALUE || ec.is_order_key || !found) { dense_possible_ = false; break; }
       }
     }
+    if (dense_possible_) dense_possible_ = dense_layout();
   }
 
-  // dense entry layout: {acc0, acc1} (2 words) when a COUNT(*) accumulator doubles as the presence marker,
-  // else {rows, acc0} (2 words) or {rows, acc0, acc1, pad} (4 words)
-  void dense_layout() {
+  // dense entry layout (2 or 4 words): [row counter unless a COUNT(*) accumulator doubles as the presence marker]
+  // [accumulators] [one "valid arguments" counter per nullable SUM that has no COUNT over the same column beside it]
+  bool dense_layout() {
     int star = -1;
     for (int j = 0; j < lay_.nacc; j++) if (fs_.acc[j].kind == FAST_ACC_COUNT && fs_.acc[j].col < 0) star = j;
-    int word_of_acc[2] = {0, 0};
-    for (int w = 0; w < 4; w++) fs_.dense_word_src[w] = -2;
-    if (star >= 0) {
-      fs_.dense_stride = 2;
-      for (int j = 0; j < lay_.nacc; j++) { fs_.dense_word_src[j] = (int8_t)j; word_of_acc[j] = j; }
-      fs_.dense_presence_word = (uint8_t)word_of_acc[star];
-    } else {
-      fs_.dense_stride = lay_.nacc == 1 ? 2 : 4;
-      fs_.dense_word_src[0] = -1; fs_.dense_presence_word = 0;
-      for (int j = 0; j < lay_.nacc; j++) { fs_.dense_word_src[1 + j] = (int8_t)j; word_of_acc[j] = 1 + j; }
+    int word_of_acc[2] = {0, 0}, valid_word_of_acc[2] = {0xFF, 0xFF}, w = 0;
+    for (int i = 0; i < 4; i++) fs_.dense_word_src[i] = -2;
+    int8_t src[8]; for (int i = 0; i < 8; i++) src[i] = -2;
+    if (star < 0) src[w++] = -1;
+    for (int j = 0; j < lay_.nacc; j++) { word_of_acc[j] = w; src[w++] = (int8_t)j; }
+    for (int j = 0; j < lay_.nacc; j++) {
+      if (fs_.acc[j].kind != FAST_ACC_ADD || fs_.acc[j].vbit == 0xFF) continue;
+      for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) valid_word_of_acc[j] = word_of_acc[i];
+      if (valid_word_of_acc[j] == 0xFF) { valid_word_of_acc[j] = w; src[w++] = (int8_t)(2 + j); }
     }
+    if (w > 4) return false;
+    fs_.dense_stride = w <= 2 ? 2 : 4;
+    for (int i = 0; i < 4; i++) fs_.dense_word_src[i] = src[i];
+    fs_.dense_presence_word = (uint8_t)(star >= 0 ? word_of_acc[star] : 0);
     for (size_t c = 0; c < emit_.size(); c++) {
       dmap_.word[c] = 0; dmap_.valid_word[c] = 0xFF;
       const EmitCol& ec = emit_[c].ec;
       if (ec.kind == EMIT_KEY) continue;
       int j = 0; for (int i = 0; i < lay_.nacc; i++) if (fs_.acc[i].word == ec.word) j = i;
       dmap_.word[c] = (uint8_t)word_of_acc[j];
-      if (ec.vbit != 0xFF) for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) dmap_.valid_word[c] = (uint8_t)word_of_acc[i];
+      if (ec.vbit != 0xFF) dmap_.valid_word[c] = (uint8_t)valid_word_of_acc[j];
     }
+    return true;
   }
 
   // decide DENSE mode from the key range of (a sample of) the first batch
@@ -572,9 +570,6 @@ class AggStage : public Stage {
     const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(h[2], cx.conf.agg_initial_groups), 1 << 16);
     if (range > budget || range > ((uint64_t)1 << 26)) return;          // sparse keys: stay on the hash table
     const uint64_t r = (uint64_t)range, margin = r / 8 + 64;
-    // typed / nullable inputs: the hashed kernel (3.6e10 rows/s on M1) beats the typed dense-table kernel (2.2e10) unless
-    // the table is small enough for the shared-memory form
-    if (!lean_ok(ct, 0) && (r + 2 * margin) * 4 > 4096) return;
     fs_.dense_base = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
     fs_.dense_cap = r + 2 * margin;
     dense_layout();

@@ -10,11 +10,13 @@ dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(42)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 
+REPS = int(os.environ.get("REPS", 0))      # override the repetitions of every shape (profiling)
 ONLY = os.environ.get("SHAPES")       # comma-separated substrings of shape names to run
 
 def run(name, plan_bytes, cols, alg_bytes_per_row, conf=None, reps=3, steady=False, valid=None):
     if ONLY and not any(t in name for t in ONLY.split(",")): return
     valid = valid or [None] * len(cols)
+    reps = REPS or reps
     spec = [(c.data_ptr(), (vb.data_ptr() if vb is not None else 0), rows) for c, vb in zip(cols, valid)]
     keep = list(cols) + [vb for vb in valid if vb is not None]
     best = None; steady_ns = None
