@@ -281,7 +281,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "M1: HashAggregateExec SUM(v),COUNT(v) GROUP BY k; k~U[0,2^20) int64, v~U[-1e6,1e6) int64 (BASELINE.json configs[1])",
                    "rows_per_gpu": rows, "groups": CARD, "parallelism": f"dp{world}" + ("" if world == 1 else " + murmur3 pmod all_to_all of partial states"),
-                   "l2_policy": "input (16 GB/GPU) is far larger than L2; no flush needed", "plan": "AggExec(Partial) -> AggExec(Final), reference protobuf + C ABI"},
+                   "l2_policy": "input (%.1f GB/GPU) is far larger than the 126 MB L2; no flush needed" % (rows * 16 / 1e9), "plan": "AggExec(Partial) -> AggExec(Final), reference protobuf + C ABI"},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_stats["h2d"], "d2h_bytes_per_step": e2e_stats["d2h"],
                 "rows_per_gpu": e2e_rows, "host_batch_rows": e2e_batch, "steps": e2e_steps, "host_numa_node": numa},
         "gpu_launches": stats["launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -60,8 +60,8 @@ v = torch.randint(-10**6, 10**6, (rows,), dtype=torch.int64, device=dev, generat
 s1 = T.Schema([T.Field("k", T.int64, False), T.Field("v", T.int64, False)])
 aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], s1, T.int64)), E.AggExpr("c", E.PARTIAL, PL.create_agg(E.AGG_COUNT, [E.Column("v")], s1, T.int64))]
 m1 = PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs, True, PL.MemoryExec(s1))
-run("M1 dense (lean)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20))
-run("M1 hash (gang, paired REDs)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0))
+run("M1 dense (lean, global table)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20))
+run("M1 hash (lean, compacted probes; first pass incl. 1M inserts)", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0))
 run("M1 hash", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
 for ig in (1 << 21, 1 << 22):
     run("M1 hash initial_groups=%d" % ig, m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=ig, agg_dense_keys=0), reps=1, steady=True)
