@@ -66,6 +66,16 @@ __device__ __forceinline__ unsigned long long* warp_sink(const FastSpec& fs, lon
   return fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + (m & 3);
 }
 
+// dense entry index of a row; false: outside the dense range (the row goes to a hashed slot)
+template <int NK>
+__device__ __forceinline__ bool dense_index(const FastSpec& fs, long long k0, long long k1, unsigned long long& idx) {
+  const unsigned long long d0 = (unsigned long long)(k0 - fs.dense_base);
+  if (NK == 1) { idx = d0; return d0 < fs.dense_cap; }
+  const unsigned long long d1 = (unsigned long long)(k1 - fs.dense_base1);
+  idx = d0 * fs.dense_r1 + d1;
+  return d0 < fs.dense_cap0 && d1 < fs.dense_r1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // typed DENSE gang kernel: any integer widths, validity bitmaps; DG = dense gang width (2 or 4 words per entry).
 // (The hashed form of typed inputs is agg_lean_hash_kernel<.., TYPED = true> below.)
@@ -125,8 +135,8 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTabl
         ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; need[s] = false; ins[s] = false; h[s] = 0; idx[s] = 0;
         if (!alive[s]) continue;
         if (DENSE) {
-          const unsigned long long di = (unsigned long long)(key0[s] - fs.dense_base);
-          if (knull[s] == 0 && di < fs.dense_cap) { ptr[s] = fs.dense_tab + di * G + m; continue; }
+          unsigned long long di;
+          if (dense_index<NK>(fs, key0[s], key1[s], di) && knull[s] == 0) { ptr[s] = fs.dense_tab + di * G + m; continue; }
         }
         h[s] = agg_hash2((uint64_t)key0[s], NK == 2 ? (uint64_t)key1[s] : 0ULL, knull[s]);
         idx[s] = agg_first_slot(h[s], tab.capacity); need[s] = true;
@@ -217,7 +227,7 @@ __device__ __forceinline__ i64xG<G> ld_rows(const long long* col, long long rel0
   return r;
 }
 
-template <int NACC, int G>
+template <int NACC, int G, int NK>
 __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                   long long row_begin, long long n) {
   constexpr int U = G == 2 ? 4 : 2;                             // 32-row units in flight per warp
@@ -225,21 +235,22 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const long long* kcol = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
+  const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
   const int src = fs.dense_word_src[m];                         // -1: row counter (+1), -2: padding (+0), j: accumulator j, 2+j: valid arguments of j (+1: inputs are non-null here)
   const bool has_acc = src >= 0 && src < NACC;
   const bool is_add = has_acc && fs.acc[has_acc ? src : 0].kind == FAST_ACC_ADD;
   const long long* vcol = is_add ? (const long long*)cols.col[fs.acc[src].col].values + row_begin : nullptr;
   const long long cst = src == -2 ? 0 : 1;
   unsigned long long* const sink = warp_sink(fs, gwarp, m);
-  const long long base = fs.dense_base; const unsigned long long cap = fs.dense_cap;
   unsigned long long* const dtab = fs.dense_tab + m;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    i64xG<G> k[U], v[U]; bool alive[U][G];
+    i64xG<G> k[U], k1[NK == 2 ? U : 1], v[U]; bool alive[U][G];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long rel0 = (unit0 + u) * 32 + gl;
       k[u] = ld_rows<G>(kcol, rel0, n);
+      if (NK == 2) k1[u] = ld_rows<G>(kcol1, rel0, n);
       if (is_add) v[u] = ld_rows<G>(vcol, rel0, n);
       else {
 #pragma unroll
@@ -262,8 +273,8 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
     for (int u = 0; u < U; u++) {
 #pragma unroll
       for (int s = 0; s < G; s++) {
-        const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
-        const bool in = alive[u][s] && idx < cap;
+        unsigned long long idx;
+        const bool in = dense_index<NK>(fs, k[u].v[s], NK == 2 ? k1[NK == 2 ? u : 0].v[s] : 0, idx) && alive[u][s];
         oor |= alive[u][s] && !in;
         red_add_u64(in ? dtab + idx * G : sink, in ? (unsigned long long)v[u].v[s] : 0ULL);     // G lanes -> 1 sector
       }
@@ -274,13 +285,14 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
       for (int u = 0; u < U; u++) {
 #pragma unroll
         for (int s = 0; s < G; s++) {
-          const unsigned long long idx = (unsigned long long)(k[u].v[s] - base);
+          unsigned long long idx;
+          const bool in = dense_index<NK>(fs, k[u].v[s], NK == 2 ? k1[NK == 2 ? u : 0].v[s] : 0, idx);
           bool inserted = false;
-          if (alive[u][s] && idx >= cap && m == 0) {
+          if (alive[u][s] && !in && m == 0) {
             const long long rel = (unit0 + u) * 32 + gl + s;
-            uint64_t kw[2] = {(uint64_t)k[u].v[s], 0};
+            uint64_t kw[2] = {(uint64_t)k[u].v[s], NK == 2 ? (uint64_t)k1[NK == 2 ? u : 0].v[s] : 0ULL};
             unsigned fl;
-            const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash_words(kw, 1, 0), &fl, &inserted);
+            const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash_words(kw, NK, 0), &fl, &inserted);
             if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
             else {
               unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
@@ -295,6 +307,93 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
           const unsigned b = __ballot_sync(0xffffffffu, inserted);
           if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b));
         }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LEAN dense kernel, one row per lane (2-word entries): for plans with fused filters and/or two keys.  The gang
+// form above evaluates every row redundantly in the G lanes of its gang — free for the bare M1 shape, but with
+// two conjuncts and a composite index the kernel became issue-bound (M2: 5.2e10 rows/s).  Here every lane owns
+// one row; the two words of an entry are still updated by ONE instruction: neighbouring lanes exchange entry
+// index / second operand with a shuffle pair (step 1: rows of even lanes, step 2: rows of odd lanes).
+// ---------------------------------------------------------------------------------------------------
+template <int NACC, int NK>
+__global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_row_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                      long long row_begin, long long n) {
+  constexpr int U = 4;
+  constexpr unsigned NONE = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31; const bool odd = lane & 1;
+  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const long long nunits = (n + 31) / 32;
+  const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
+  const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
+  // per entry word: the column added to it (SUM) or the constant 1 (row counter, COUNT, valid-argument counter) / 0 (padding)
+  const long long* wcol[2]; unsigned long long wcst[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const int src = fs.dense_word_src[m];
+    const bool add = src >= 0 && src < NACC && fs.acc[src].kind == FAST_ACC_ADD;
+    wcol[m] = add ? (const long long*)cols.col[fs.acc[src].col].values + row_begin : nullptr;
+    wcst[m] = src == -2 ? 0ULL : 1ULL;
+  }
+  unsigned long long* const sink = warp_sink(fs, gwarp, lane);
+
+  for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
+    long long k0[U], k1[U]; unsigned long long a[U], b[U]; bool alive[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long rel = (unit0 + u) * 32 + lane;
+      alive[u] = rel < n;
+      k0[u] = alive[u] ? ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      k1[u] = (NK == 2 && alive[u]) ? ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
+      a[u] = (wcol[0] && alive[u]) ? (unsigned long long)ld_stream_vec(wcol[0] + rel, (i64xG<1>*)nullptr).v[0] : wcst[0];
+      b[u] = (wcol[1] && alive[u]) ? (unsigned long long)ld_stream_vec(wcol[1] + rel, (i64xG<1>*)nullptr).v[0] : wcst[1];
+    }
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
+      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long rel = (unit0 + u) * 32 + lane;
+        const long long x = rel < n ? ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0] : 0;
+        alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      unsigned long long di;
+      const bool in = dense_index<NK>(fs, k0[u], k1[u], di) && alive[u];
+      const unsigned mi = in ? (unsigned)di : NONE;
+      const unsigned pi = __shfl_xor_sync(0xffffffffu, mi, 1);                                     // neighbour's entry
+      const unsigned long long pb = wcol[1] ? __shfl_xor_sync(0xffffffffu, b[u], 1) : wcst[1];
+      unsigned long long* const mine = mi != NONE ? fs.dense_tab + (uint64_t)mi * 2 : sink;
+      unsigned long long* const theirs = pi != NONE ? fs.dense_tab + (uint64_t)pi * 2 + 1 : sink;
+      const unsigned long long mv = mi != NONE ? a[u] : 0ULL, tv = pi != NONE ? pb : 0ULL;
+      red_add_u64(odd ? theirs : mine, odd ? tv : mv);          // step 1: rows of even lanes: {word 0 by the owner, word 1 by its odd neighbour}
+      red_add_u64(odd ? mine : theirs, odd ? mv : tv);          // step 2: rows of odd lanes
+      // keys outside the dense range (rare): straight to the hashed slots
+      const bool fb = alive[u] && !in;
+      if (__any_sync(0xffffffffu, fb)) {
+        bool inserted = false;
+        if (fb) {
+          const long long rel = (unit0 + u) * 32 + lane;
+          uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
+          unsigned fl = 0;
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash2(kw[0], kw[1], 0), &fl, &inserted);
+          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
+          else {
+            unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
+#pragma unroll
+            for (int j = 0; j < NACC; j++) {
+              const unsigned long long x = fs.acc[j].kind == FAST_ACC_ADD ? (unsigned long long)__ldg((const long long*)cols.col[fs.acc[j].col].values + row_begin + rel) : 1ULL;
+              red_add_u64(p + fs.acc[j].word, x);
+              slot_mark(tab.keys + si * (uint64_t)lay.kstride, fl, fs.acc[j].vbit);
+            }
+          }
+        }
+        const unsigned bl = __ballot_sync(0xffffffffu, inserted);
+        if (lane == 0 && bl) atomicAdd(tab.counters, (unsigned long long)__popc(bl));
       }
     }
   }
@@ -500,7 +599,7 @@ __device__ __forceinline__ void smem_add64(unsigned* w, unsigned long long v) {
   if (lo) { const unsigned old = atomicAdd(w, lo); carry = old + lo < old; }
   if (hi + carry) atomicAdd(w + 1, hi + carry);
 }
-template <int NACC, bool TYPED>
+template <int NACC, bool TYPED, int NK>
 __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                   long long row_begin, long long n) {
   constexpr int U = 4;
@@ -513,21 +612,22 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
   const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
-  const long long base = fs.dense_base; const unsigned long long cap = fs.dense_cap;
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    long long k[U]; unsigned long long v0[U], v1[U]; bool alive[U]; unsigned meta[U];       // meta: bit0 key NULL, bit2/3 argument valid
+    long long k[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U]; unsigned meta[U];       // meta: bit0/1 key NULL, bit2/3 argument valid
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long rel = (unit0 + u) * 32 + lane, row = row_begin + rel;
-      alive[u] = rel < n; meta[u] = 0xC; k[u] = 0; v0[u] = 1; v1[u] = 1;
+      alive[u] = rel < n; meta[u] = 0xC; k[u] = 0; k1[u] = 0; v0[u] = 1; v1[u] = 1;
       if (!alive[u]) continue;
       if (!TYPED) {
         k[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[0]].values + row, (i64xG<1>*)nullptr).v[0];
+        if (NK == 2) k1[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[1]].values + row, (i64xG<1>*)nullptr).v[0];
         if (add0) v0[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[0].col].values + row, (i64xG<1>*)nullptr).v[0];
         if (add1) v1[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[1].col].values + row, (i64xG<1>*)nullptr).v[0];
       } else {
         { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) k[u] = col_load_int(c, fs.key_phys[0], row); else meta[u] |= 1u; }
+        if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) k1[u] = col_load_int(c, fs.key_phys[1], row); else meta[u] |= 2u; }
         if (fs.acc[0].col >= 0) {
           const DevCol& c = cols.col[fs.acc[0].col];
           if (!col_valid(c, row)) { meta[u] &= ~4u; v0[u] = 0; } else if (add0) v0[u] = (unsigned long long)col_load_int(c, fs.acc[0].phys, row);
@@ -550,8 +650,8 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const unsigned long long idx = (unsigned long long)(k[u] - base);
-      const bool in = alive[u] && !(meta[u] & 1u) && idx < cap;
+      unsigned long long idx;
+      const bool in = dense_index<NK>(fs, k[u], k1[u], idx) && alive[u] && !(meta[u] & 3u);
       if (in) {
         unsigned* const e = s_tab + 2 * (unsigned)idx * G;
 #pragma unroll
@@ -569,10 +669,10 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable
       if (__any_sync(0xffffffffu, fb)) {
         bool inserted = false;
         if (fb) {
-          uint64_t kw[2] = {(uint64_t)k[u], 0};
-          const unsigned knull = meta[u] & 1u;
+          uint64_t kw[2] = {(uint64_t)k[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
+          const unsigned knull = meta[u] & 3u;
           unsigned fl = 0;
-          const uint64_t si = agg_find_or_insert(lay, tab, kw, knull, agg_hash2(kw[0], 0ULL, knull), &fl, &inserted);
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, knull, agg_hash2(kw[0], kw[1], knull), &fl, &inserted);
           if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); }
           else {
             unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
@@ -611,15 +711,32 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
   if (dg && fs.dense_cap * (unsigned long long)dg <= (unsigned long long)DS_MAX_WORDS) {
     // persistent CTAs, 3 per SM (32 KB of shared memory each); every CTA flushes its private table once
     const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + FA_BLOCK * 4 - 1) / (FA_BLOCK * 4), (int64_t)fast_grid(1 << 30) / 8 * 3));
-    if (fs.lean) { if (fs.nacc == 2) agg_dense_smem_kernel<2, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_dense_smem_kernel<1, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
-    else { if (fs.nacc == 2) agg_dense_smem_kernel<2, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_dense_smem_kernel<1, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+#define B200Q_DS(NACC, TYPED, NK) agg_dense_smem_kernel<NACC, TYPED, NK><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.nkeys == 1) {
+      if (fs.lean) { if (fs.nacc == 2) B200Q_DS(2, false, 1); else B200Q_DS(1, false, 1); } else { if (fs.nacc == 2) B200Q_DS(2, true, 1); else B200Q_DS(1, true, 1); }
+    } else {
+      if (fs.lean) { if (fs.nacc == 2) B200Q_DS(2, false, 2); else B200Q_DS(1, false, 2); } else { if (fs.nacc == 2) B200Q_DS(2, true, 2); else B200Q_DS(1, true, 2); }
+    }
+#undef B200Q_DS
+    return 1;
+  }
+  if (dg == 2 && fs.lean && (fs.nkeys == 2 || fs.nfilt > 0)) {
+    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
+#define B200Q_LR(NACC, NK) agg_lean_dense_row_kernel<NACC, NK><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.nkeys == 1) { if (fs.nacc == 2) B200Q_LR(2, 1); else B200Q_LR(1, 1); } else { if (fs.nacc == 2) B200Q_LR(2, 2); else B200Q_LR(1, 2); }
+#undef B200Q_LR
     return 1;
   }
   if (dg && fs.lean) {
     const int u = dg == 2 ? 4 : 2;
     const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
-    if (fs.nacc == 2) { if (dg == 2) agg_lean_dense_kernel<2, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<2, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
-    else { if (dg == 2) agg_lean_dense_kernel<1, 2><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); else agg_lean_dense_kernel<1, 4><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); }
+#define B200Q_LD(NACC, G, NK) agg_lean_dense_kernel<NACC, G, NK><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.nkeys == 1) {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_LD(2, 2, 1); else B200Q_LD(2, 4, 1); } else { if (dg == 2) B200Q_LD(1, 2, 1); else B200Q_LD(1, 4, 1); }
+    } else {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_LD(2, 2, 2); else B200Q_LD(2, 4, 2); } else { if (dg == 2) B200Q_LD(1, 2, 2); else B200Q_LD(1, 4, 2); }
+    }
+#undef B200Q_LD
     return 1;
   }
   if (!dg) {
@@ -632,8 +749,9 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
     return 1;
   }
   const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);
-  // typed dense table (one key): rows outside the dense range / NULL keys fall through to the hashed slots inside the kernel
-  if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n);
+  // typed dense table: rows outside the dense range / NULL keys fall through to the hashed slots inside the kernel
+  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
+  else { if (fs.nacc == 2) launch_gang<2, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
   return 1;
 }
 
@@ -689,7 +807,11 @@ __global__ void __launch_bounds__(256) agg_emit_dense_kernel(const FastSpec fs, 
     const unsigned long long at = base + __popc(m & lanemask_lt());
     for (int c = 0; c < emit.ncols; c++) {
       const EmitCol ec = emit.col[c];
-      if (ec.kind == EMIT_KEY) dense_store(ec, at, (uint64_t)(fs.dense_base + (long long)i), true);
+      if (ec.kind == EMIT_KEY) {
+        const long long kv = fs.nkeys == 1 ? fs.dense_base + (long long)i
+                           : ec.key == 0 ? fs.dense_base + (long long)(i / fs.dense_r1) : fs.dense_base1 + (long long)(i % fs.dense_r1);
+        dense_store(ec, at, (uint64_t)kv, true);
+      }
       else {
         const int w = map.word[c], vw = map.valid_word[c];
         const bool valid = vw == 0xFF ? true : e[vw] != 0;

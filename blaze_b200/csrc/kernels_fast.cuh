@@ -12,8 +12,10 @@ struct FastSpec {
   int8_t key_col[2]; uint8_t key_phys[2];                 // program column slots / physical kinds of the key columns
   struct { uint8_t kind; int8_t col; uint8_t phys; uint8_t vbit; uint8_t word; uint8_t _pad[3]; } acc[2];
   struct { int8_t col; uint8_t phys; uint8_t op; uint8_t _pad[5]; long long lit; } filt[4];
-  long long dense_base;                                   // DENSE: slot index = key - dense_base
+  long long dense_base;                                   // DENSE: entry index = key0 - dense_base                      (one key)
   unsigned long long dense_cap;                           // entries of dense_stride words
+  long long dense_base1;                                  //        entry index = (key0 - dense_base) * dense_r1 + (key1 - dense_base1)   (two keys)
+  unsigned long long dense_r1, dense_cap0;                // key1 - dense_base1 < dense_r1, key0 - dense_base < dense_cap0; dense_cap = dense_cap0 * dense_r1
   unsigned long long* dense_tab;
   int8_t dense_stride;                                    // 2 or 4 words per entry (= gang width)
   int8_t dense_word_src[4];                               // per entry word: -1 row counter (+1), -2 padding (+0), j accumulator j, 2+j valid arguments of accumulator j

@@ -258,6 +258,7 @@ class AggStage : public Stage {
 
   // specialised kernels (kernels_fast.cu)
   bool fast_ok_ = false, dense_possible_ = false, dense_decided_ = false;
+  bool acc_arg_nullable_[2] = {true, true};
   FastSpec fs_{};
   DenseEmitMap dmap_{};
   DevMemP dense_tab_, sink_;
@@ -486,6 +487,7 @@ class AggStage : public Stage {
         if (e->kind != E_COLUMN || !int_phys(e->type)) return;
         const int s = prog_col_slot(e->col_index); if (s < 0 || s > 127) return;
         fs.acc[j].kind = FAST_ACC_ADD; fs.acc[j].col = (int8_t)s; fs.acc[j].phys = phys_of(e->type);
+        acc_arg_nullable_[j] = e->nullable;
       } else if (a.kind == ACC_COUNT && a.nargs <= 1) {
         fs.acc[j].kind = FAST_ACC_COUNT;
         if (a.nargs == 1) {
@@ -510,8 +512,8 @@ class AggStage : public Stage {
     sink_ = DevMem::alloc((size_t)FAST_SINK_WARPS * 32, cx.stream, true);
     fs.sink = (unsigned long long*)sink_->ptr;
     fs_ = fs; fast_ok_ = true;
-    // DENSE mode needs: one key and an entry of at most 4 words (dense_layout)
-    dense_possible_ = lay_.nkeys == 1 && cx.conf.agg_dense_keys != 0;
+    // DENSE mode needs: integer keys with small value ranges (decided on the first batch) and an entry of at most 4 words
+    dense_possible_ = cx.conf.agg_dense_keys != 0;
     if (dense_possible_) {
       for (size_t c = 0; c < emit_.size(); c++) {
         const EmitCol& ec = emit_[c].ec;
@@ -536,6 +538,8 @@ class AggStage : public Stage {
     for (int j = 0; j < lay_.nacc; j++) {
       if (fs_.acc[j].kind != FAST_ACC_ADD || fs_.acc[j].vbit == 0xFF) continue;
       for (int i = 0; i < lay_.nacc; i++) if (i != j && fs_.acc[i].kind == FAST_ACC_COUNT && fs_.acc[i].col == fs_.acc[j].col) valid_word_of_acc[j] = word_of_acc[i];
+      // a never-NULL argument: the SUM has a value as soon as the entry holds a row
+      if (valid_word_of_acc[j] == 0xFF && !acc_arg_nullable_[j]) valid_word_of_acc[j] = star >= 0 ? word_of_acc[star] : 0;
       if (valid_word_of_acc[j] == 0xFF) { valid_word_of_acc[j] = w; src[w++] = (int8_t)(2 + j); }
     }
     if (w > 4) return false;
@@ -558,20 +562,30 @@ class AggStage : public Stage {
     dense_decided_ = true;
     if (!fast_ok_ || !dense_possible_ || n == 0) return;
     const int64_t sample = std::min<int64_t>(n, 1 << 22);
-    DevMemP d = DevMem::alloc(24, cx.stream);
-    const long long init[3] = {INT64_MAX, INT64_MIN, 0};
-    B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 24, cudaMemcpyHostToDevice, cx.stream));
-    cx.m.launches += launch_key_range(ct.col[fs_.key_col[0]], fs_.key_phys[0], sample, (long long*)d->ptr, cx.stream);
-    long long h[3];
-    B200Q_CUDA(cudaMemcpyAsync(h, d->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
-    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-    if (h[2] <= 0 || h[1] < h[0]) return;
-    const unsigned __int128 range = (unsigned __int128)((__int128)h[1] - (__int128)h[0]) + 1;
-    const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(h[2], cx.conf.agg_initial_groups), 1 << 16);
-    if (range > budget || range > ((uint64_t)1 << 26)) return;          // sparse keys: stay on the hash table
-    const uint64_t r = (uint64_t)range, margin = r / 8 + 64;
-    fs_.dense_base = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
-    fs_.dense_cap = r + 2 * margin;
+    // padded value range of every key column: [min - margin, max + margin] of the sample
+    long long base[2] = {0, 0}; uint64_t span[2] = {1, 1}; long long nonnull = 0;
+    for (int k = 0; k < fs_.nkeys; k++) {
+      DevMemP d = DevMem::alloc(24, cx.stream);
+      const long long init[3] = {INT64_MAX, INT64_MIN, 0};
+      B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 24, cudaMemcpyHostToDevice, cx.stream));
+      cx.m.launches += launch_key_range(ct.col[fs_.key_col[k]], fs_.key_phys[k], sample, (long long*)d->ptr, cx.stream);
+      long long h[3];
+      B200Q_CUDA(cudaMemcpyAsync(h, d->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      if (h[2] <= 0 || h[1] < h[0]) return;
+      const unsigned __int128 range = (unsigned __int128)((__int128)h[1] - (__int128)h[0]) + 1;
+      if (range > ((uint64_t)1 << 26)) return;
+      const uint64_t r = (uint64_t)range, margin = r / 8 + std::min<uint64_t>(64, r / 2 + 1);
+      base[k] = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
+      span[k] = r + 2 * margin;
+      nonnull = std::max(nonnull, h[2]);
+    }
+    const unsigned __int128 entries = (unsigned __int128)span[0] * span[1];
+    const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(nonnull, cx.conf.agg_initial_groups), 1 << 16);
+    if (entries > budget || entries > ((uint64_t)1 << 26)) return;             // sparse keys: stay on the hash table
+    fs_.dense_base = base[0]; fs_.dense_cap0 = span[0];
+    fs_.dense_base1 = base[1]; fs_.dense_r1 = span[1];
+    fs_.dense_cap = (uint64_t)entries;
     dense_layout();
     dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * fs_.dense_stride * 8, cx.stream, true);
     fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;

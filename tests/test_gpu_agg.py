@@ -208,3 +208,50 @@ def test_large_batch_against_c_port():
     ref = cpu_ref.hashagg_sum_count(k, v, nthreads=8, max_groups=1 << 21)
     order_g, order_r = np.argsort(gk), np.argsort(ref["k"])
     assert np.array_equal(gk[order_g], ref["k"][order_r]) and np.array_equal(gs[order_g], ref["sum"][order_r]) and np.array_equal(gc[order_g], ref["count"][order_r])
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("shape", ["lean-global", "lean-smem", "typed", "sum-only-notnull"])
+def test_two_key_composite_dense_index(mode, shape):
+    """two small-range integer keys are mapped onto ONE dense index (k0-b0)*r1 + (k1-b1); later batches bring keys
+    outside the range decided on the first batch (-> hashed slots) — every form must agree with the oracle"""
+    n = 300_000
+    rng = np.random.default_rng(77)
+    r0 = 40 if shape == "lean-smem" else 6000
+    k0 = rng.integers(100, 100 + r0, n, dtype=np.int64); k0[200_000:] += rng.integers(0, 3 * r0, n - 200_000)     # range grows after batch 1
+    k1 = rng.integers(-3, 4, n, dtype=np.int64); k1[250_000:] = rng.integers(-40, 40, n - 250_000)
+    v = rng.integers(-10**9, 10**9, n, dtype=np.int64)
+    if shape == "typed":
+        cols = [with_nulls(rng, k0.astype(np.int32), 0.01, pa.int32()), with_nulls(rng, k1.astype(np.int16), 0.02, pa.int16()), with_nulls(rng, v, 0.2)]
+        rb = rb_from_cols(["k0", "k1", "v"], cols)
+    else:
+        notnull = shape == "sum-only-notnull"
+        schema = pa.schema([pa.field("k0", pa.int64(), nullable=not notnull), pa.field("k1", pa.int64(), nullable=not notnull), pa.field("v", pa.int64(), nullable=not notnull)])
+        rb = pa.RecordBatch.from_arrays([pa.array(k0), pa.array(k1), pa.array(v)], schema=schema)
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64)] if shape == "sum-only-notnull" else \
+            [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64)]
+    conf = native.default_conf(staging_rows=0, **MODES[mode])
+    got, plan = run_partial_final(rb, ["k0", "k1"], specs, batch_rows=100_000, conf=conf)
+    assert (plan.last_metrics["fast_path_launches"] > 0) == (mode != "generic")
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_one_key_fused_filter_lean_dense_row_form(mode):
+    """non-null int64 inputs + fused conjuncts + {SUM, COUNT(*)}: 2-word dense entries updated by lane pairs (one row per lane)"""
+    n = 250_001
+    rng = np.random.default_rng(78)
+    schema = pa.schema([pa.field(c, pa.int64(), nullable=False) for c in ("k", "f", "v")])
+    k = rng.integers(-500, 70_000, n, dtype=np.int64); k[1::2] = k[::2][: n // 2]          # neighbouring rows often share a group
+    rb = pa.RecordBatch.from_arrays([pa.array(k), pa.array(rng.integers(0, 100, n, dtype=np.int64)), pa.array(rng.integers(-2**40, 2**40, n, dtype=np.int64))], schema=schema)
+    batches = split_batches(rb, 100_000)
+    leaf = PL.MemoryExec.from_arrow(batches, rb.schema)
+    ins = leaf.schema()
+    preds = [E.BinaryExpr(E.Column("f"), "GtEq", E.Literal(20, T.int64)), E.BinaryExpr(E.Column("f"), "Lt", E.Literal(55, T.int64))]
+    groupings = [E.GroupingExpr("k", E.Column("k"))]
+    aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], ins, T.int64)),
+            E.AggExpr("n", E.PARTIAL, PL.create_agg(E.AGG_COUNT, [E.Literal(1, T.int64)], ins, T.int64))]
+    plan = PL.AggExec(PL.HashAgg, groupings, aggs, True, PL.FilterExec(preds, leaf))
+    got = PL.collect(plan, native.default_conf(staging_rows=0, **MODES[mode]))
+    exp = O.AggExec(E.HASH_AGG, groupings, aggs, False, ins).execute(O.FilterExec(preds, ins).execute(oracle_batches(batches)))
+    assert_multiset_equal(got, exp)
+    assert (plan.last_metrics["fast_path_launches"] > 0) == (mode != "generic")
