@@ -3,22 +3,21 @@
 //   * up to 4 fused `column <cmp> literal` conjuncts (the FilterExec below the agg),
 //   * 1-2 accumulators of the "64-bit add" class: SUM(int column), COUNT(column), COUNT(*).
 //
-// What bounds them (profiles/r01_microbench_atomics_*.txt, measured on B200): the input stream runs at
-// HBM speed (6.5 TB/s) but every row also needs a random read-modify-write into the L2-resident group
-// table, and the chip retires ~1.55e11 scattered 32-byte sector operations per second.  So the design
-// goal is ONE sector operation per row:
-//   - hashed: slot = one 32-byte sector {hdr, key, acc0, acc1}: the probe is a single 16-byte load and the
-//     two accumulators of a row are updated by the SAME red.add.u64 instruction from two adjacent lanes,
-//     which the memory system coalesces into one sector operation;
-//   - DENSE (single integer key whose values span a small range, e.g. TPC-DS surrogate keys): the entry
-//     index is key - base, no probe at all; an entry is 2 or 4 words ({sum,count} / {rows,acc0,acc1,-})
-//     updated by a gang of 2 or 4 lanes in one instruction.  Keys outside the range and NULL keys take
-//     the hash table.
-//
-// Lane organisation ("gang"): G adjacent lanes own G consecutive rows; EVERY lane of the gang loads the
-// gang's G rows itself (the lanes read the same addresses: one access for the LSU), computes the G entry
-// addresses redundantly, and in step s = 0..G-1 the gang's lanes update word 0..G-1 of row s.  No shuffles,
-// no per-thread arrays with dynamic indices.
+// What bounds them (profiles/r01_microbench_*.txt, measured on B200): the input stream runs at HBM speed
+// (6.5 TB/s) but every row also needs a random read-modify-write into the L2-resident group table, and the chip
+// retires ~1.55e11 scattered 32-byte RED sector operations per second.  So the design goal is ONE RED sector per row:
+//   - hashed (agg_lean_hash_kernel): key entries {hdr,key..} and accumulator entries live in two arrays (a RED on a
+//     sector that was just probed costs 2x: the read copies must be invalidated); the probe is a single 16-byte
+//     load, collided rows are re-probed 32 at a time from a per-warp stack, and the two accumulators of a row are
+//     updated by the SAME red.add.u64 instruction from two adjacent lanes (one sector operation);
+//   - DENSE (integer keys whose values span a small range, e.g. TPC-DS surrogate keys; two keys are mapped onto
+//     one composite index): no probe at all; an entry is 2 or 4 words updated by 2 or 4 adjacent lanes in one
+//     instruction.  Keys outside the range and NULL keys take the hash table.
+//       agg_lean_dense_kernel  bare M1 shape: "gangs" of G lanes own G consecutive rows and load them with one wide
+//                              load each (same addresses: one LSU access); in step s the gang updates row s
+//       agg_dense_row_kernel   filters / two keys / typed inputs: one row per lane, operands handed to the G lanes
+//                              of a group by shuffle
+//       agg_dense_smem_kernel  few groups: CTA-private table in shared memory, flushed once
 //
 // REDs are issued UNCONDITIONALLY: ptxas if-converts a predicated `red` into `@P ATOMG ... RZ` (an atomic
 // with a return path); lanes with nothing to add send +0 to their warp's private sink sector instead.
@@ -33,8 +32,6 @@
 namespace b200q {
 
 constexpr int FA_BLOCK = 256;
-constexpr int FA_UNITS = 4;                   // 32-row units per warp per tile (generic gang kernel)
-constexpr int FA_TILE = FA_BLOCK * FA_UNITS;
 
 // streaming load: bypass L1 and mark the line evict-first in L2 so the input stream does not push the
 // group table out of L2
@@ -74,125 +71,6 @@ __device__ __forceinline__ bool dense_index(const FastSpec& fs, long long k0, lo
   const unsigned long long d1 = (unsigned long long)(k1 - fs.dense_base1);
   idx = d0 * fs.dense_r1 + d1;
   return d0 < fs.dense_cap0 && d1 < fs.dense_r1;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// typed DENSE gang kernel: any integer widths, validity bitmaps; DG = dense gang width (2 or 4 words per entry).
-// (The hashed form of typed inputs is agg_lean_hash_kernel<.., TYPED = true> below.)
-// ---------------------------------------------------------------------------------------------------
-template <int NK, int NACC, int DG>
-__global__ void __launch_bounds__(FA_BLOCK) agg_gang_update_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
-                                                                   long long row_begin, long long n) {
-  constexpr bool DENSE = DG != 0;
-  constexpr int G = DENSE ? DG : (NACC == 2 ? 2 : 1);
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned m = lane % G, gl = lane - m;                   // my word index inside the gang, first lane of my gang
-  const long long ntiles = (n + FA_TILE - 1) / FA_TILE;
-  // which accumulator (if any) this lane updates: dense entries follow fs.dense_word_src, hashed slots acc m
-  const int src = DENSE ? fs.dense_word_src[m] : (int)m;        // -1: row counter (+1), -2: padding (+0), j: accumulator j, 2+j: valid arguments of j (+1)
-  const bool has_acc = src >= 0 && src < NACC;
-  const int vsrc_col = src >= 2 ? fs.acc[src - 2].col : -1;     // valid counter: counts the rows whose argument is not NULL
-  const int acc_col = has_acc ? fs.acc[src].col : -1;
-  const int acc_kind = has_acc ? fs.acc[src].kind : FAST_ACC_COUNT;
-  const int acc_phys = has_acc ? fs.acc[src].phys : PH_I64;
-  const int acc_word = has_acc ? fs.acc[src].word : 0;
-  const int acc_vbit = has_acc ? fs.acc[src].vbit : 0xFF;
-  unsigned long long* const sink = warp_sink(fs, (long long)blockIdx.x * (FA_BLOCK / 32) + warp, m);
-
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll 1
-    for (int u = 0; u < FA_UNITS; u++) {
-      const long long rel0 = tile * FA_TILE + (long long)(u * (FA_BLOCK / 32) + warp) * 32 + gl;   // first row of my gang (relative)
-      long long key0[G], key1[G]; bool alive[G]; unsigned knull[G];
-      unsigned long long val[G]; bool act[G];
-#pragma unroll
-      for (int s = 0; s < G; s++) {
-        const long long rel = rel0 + s, row = row_begin + rel;
-        alive[s] = rel < n; knull[s] = 0; key0[s] = 0; key1[s] = 0; val[s] = src == -2 ? 0 : 1; act[s] = alive[s];
-        if (!alive[s]) continue;
-        { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) key0[s] = col_load_int(c, fs.key_phys[0], row); else knull[s] |= 1u; }
-        if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) key1[s] = col_load_int(c, fs.key_phys[1], row); else knull[s] |= 2u; }
-        if (has_acc && acc_col >= 0) {
-          const DevCol& c = cols.col[acc_col];
-          act[s] = col_valid(c, row);
-          if (acc_kind == FAST_ACC_ADD) val[s] = act[s] ? (unsigned long long)col_load_int(c, acc_phys, row) : 0ULL;
-        }
-        if (vsrc_col >= 0) act[s] = col_valid(cols.col[vsrc_col], row);
-      }
-      // fused FilterExec conjuncts (null -> false, cached_exprs_evaluator.rs:518-520)
-      for (int f = 0; f < fs.nfilt; f++) {
-        const DevCol& c = cols.col[fs.filt[f].col];
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-          const long long row = row_begin + rel0 + s;
-          if (alive[s]) alive[s] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
-        }
-      }
-      // entry / slot of every row of the gang (computed redundantly by each lane of the gang)
-      unsigned long long* ptr[G]; unsigned long long* slot[G] /* key entry of a hashed row */; unsigned flags[G]; bool need[G], ins[G]; uint64_t h[G], idx[G];
-#pragma unroll
-      for (int s = 0; s < G; s++) {
-        ptr[s] = nullptr; slot[s] = nullptr; flags[s] = 0; need[s] = false; ins[s] = false; h[s] = 0; idx[s] = 0;
-        if (!alive[s]) continue;
-        if (DENSE) {
-          unsigned long long di;
-          if (dense_index<NK>(fs, key0[s], key1[s], di) && knull[s] == 0) { ptr[s] = fs.dense_tab + di * G + m; continue; }
-        }
-        h[s] = agg_hash2((uint64_t)key0[s], NK == 2 ? (uint64_t)key1[s] : 0ULL, knull[s]);
-        idx[s] = agg_first_slot(h[s], tab.capacity); need[s] = true;
-      }
-      // probe walk: all pending rows advance one slot per round, the lanes of a gang in lockstep (collisions are
-      // common at load 0.5, so they must not serialise the warp); only NEW keys go to the insert section
-      while (true) {
-        ulonglong2 hk[G];
-#pragma unroll
-        for (int s = 0; s < G; s++) if (need[s]) hk[s] = ld_relaxed_v2u64(tab.keys + idx[s] * (uint64_t)lay.kstride);   // {hdr, key0}
-        bool pending = false;
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-          if (!need[s]) continue;
-          const unsigned tag = agg_tag(h[s]), t = (unsigned)hk[s].x;
-          unsigned long long* sp = tab.keys + idx[s] * (uint64_t)lay.kstride;
-          if (t == tag) {
-            bool hit = (unsigned)(hk[s].x >> 48) == knull[s] && hk[s].y == (uint64_t)key0[s];
-            if (NK == 2 && hit) hit = ld_relaxed_u64(sp + 2) == (uint64_t)key1[s];
-            if (hit) { slot[s] = sp; flags[s] = (unsigned)(hk[s].x >> 32); need[s] = false; }
-            else idx[s] = agg_next_slot(idx[s], tab.capacity);
-          } else if (t == TAG_EMPTY) { need[s] = false; ins[s] = true; }
-          else if (t != TAG_LOCKED) idx[s] = agg_next_slot(idx[s], tab.capacity);
-          pending |= need[s];
-        }
-        if (!__any_sync(0xffffffffu, pending)) break;
-      }
-      bool any_ins = false;
-#pragma unroll
-      for (int s = 0; s < G; s++) any_ins |= ins[s];
-      if (__any_sync(0xffffffffu, any_ins)) {                  // new keys: lane 0 of the gang inserts, then broadcasts
-#pragma unroll
-        for (int s = 0; s < G; s++) {
-          unsigned long long si = idx[s]; unsigned fl = flags[s]; bool inserted = false;
-          if (ins[s] && m == 0) {
-            uint64_t kw[2] = {(uint64_t)key0[s], (uint64_t)key1[s]};
-            si = agg_find_or_insert(lay, tab, kw, knull[s], h[s], &fl, &inserted);
-            if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + s); }
-          }
-          { const unsigned b = __ballot_sync(0xffffffffu, inserted); if (lane == 0 && b) atomicAdd(tab.counters, (unsigned long long)__popc(b)); }   // one counter update per warp step
-          if (G > 1) { si = __shfl_sync(0xffffffffu, si, gl); fl = __shfl_sync(0xffffffffu, fl, gl); }
-          if (ins[s]) { idx[s] = si; flags[s] = fl; slot[s] = si == AGG_NO_SLOT ? nullptr : tab.keys + si * (uint64_t)lay.kstride; if (si == AGG_NO_SLOT) alive[s] = false; }
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < G; s++)
-        if (alive[s] && slot[s] && has_acc) ptr[s] = tab.accs + idx[s] * (uint64_t)lay.astride + acc_word;   // hashed row: this lane's accumulator word
-      // accumulate: step s updates row s; the gang's lanes hit adjacent words of ONE sector in ONE instruction
-#pragma unroll
-      for (int s = 0; s < G; s++) {
-        const bool pred = alive[s] && ptr[s] != nullptr;
-        red_add_u64(pred ? ptr[s] : sink, (pred && act[s]) ? val[s] : 0ULL);
-        if (pred && act[s] && slot[s]) slot_mark(slot[s], flags[s], acc_vbit);
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -313,83 +191,107 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_kernel(const ColTable
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LEAN dense kernel, one row per lane (2-word entries): for plans with fused filters and/or two keys.  The gang
-// form above evaluates every row redundantly in the G lanes of its gang — free for the bare M1 shape, but with
-// two conjuncts and a composite index the kernel became issue-bound (M2: 5.2e10 rows/s).  Here every lane owns
-// one row; the two words of an entry are still updated by ONE instruction: neighbouring lanes exchange entry
-// index / second operand with a shuffle pair (step 1: rows of even lanes, step 2: rows of odd lanes).
+// Dense kernel, one row per lane: fused filters, two keys, 4-word entries, typed / nullable inputs.  The gang form
+// above evaluates every row redundantly in the G lanes of its gang — free for the bare M1 shape, but with conjuncts,
+// a composite index or typed loads the kernel becomes issue-bound (M2: 5.2e10 rows/s; typed M1: 2.2e10).  Here every
+// lane owns one row, and the G words of an entry are still updated by ONE instruction: in step t the G lanes of a
+// group receive the entry index, validity flags and operands of the group's t-th row by shuffle and lane q adds
+// the value of word q.
+// TYPED = false: non-null 8-byte-aligned int64 columns; TYPED = true: any integer width + validity bitmaps.
 // ---------------------------------------------------------------------------------------------------
-template <int NACC, int NK>
-__global__ void __launch_bounds__(FA_BLOCK) agg_lean_dense_row_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
-                                                                      long long row_begin, long long n) {
+enum { DW_ZERO = 0, DW_ONE, DW_ADD0, DW_ADD1, DW_VALID0, DW_VALID1 };     // what an entry word accumulates
+template <int NACC, int NK, int G, bool TYPED>
+__global__ void __launch_bounds__(FA_BLOCK) agg_dense_row_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                 long long row_begin, long long n) {
   constexpr int U = 4;
-  constexpr unsigned NONE = 0xFFFFFFFFu;
-  const unsigned lane = threadIdx.x & 31; const bool odd = lane & 1;
+  constexpr unsigned IDX_MASK = 0x0FFFFFFFu;                    // dense_cap <= 2^26; bits 28/29: argument 0/1 is not NULL
+  const unsigned lane = threadIdx.x & 31, q = lane & (G - 1);
   const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
   const long long nunits = (n + 31) / 32;
-  const long long* kcol0 = (const long long*)cols.col[fs.key_col[0]].values + row_begin;
-  const long long* kcol1 = NK == 2 ? (const long long*)cols.col[fs.key_col[1]].values + row_begin : nullptr;
-  // per entry word: the column added to it (SUM) or the constant 1 (row counter, COUNT, valid-argument counter) / 0 (padding)
-  const long long* wcol[2]; unsigned long long wcst[2];
-#pragma unroll
-  for (int m = 0; m < 2; m++) {
-    const int src = fs.dense_word_src[m];
-    const bool add = src >= 0 && src < NACC && fs.acc[src].kind == FAST_ACC_ADD;
-    wcol[m] = add ? (const long long*)cols.col[fs.acc[src].col].values + row_begin : nullptr;
-    wcst[m] = src == -2 ? 0ULL : 1ULL;
+  const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
+  // this lane's entry word
+  int wkind;
+  {
+    const int src = fs.dense_word_src[q];
+    if (src == -1) wkind = DW_ONE; else if (src == -2) wkind = DW_ZERO;
+    else if (src >= 2) wkind = src == 2 ? DW_VALID0 : DW_VALID1;
+    else if (src == 0) wkind = add0 ? DW_ADD0 : DW_VALID0;
+    else wkind = add1 ? DW_ADD1 : DW_VALID1;
   }
   unsigned long long* const sink = warp_sink(fs, gwarp, lane);
 
   for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
-    long long k0[U], k1[U]; unsigned long long a[U], b[U]; bool alive[U];
+    long long k0[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U]; unsigned meta[U];     // meta: bit0/1 key NULL, bit2/3 argument valid
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const long long rel = (unit0 + u) * 32 + lane;
-      alive[u] = rel < n;
-      k0[u] = alive[u] ? ld_stream_vec(kcol0 + rel, (i64xG<1>*)nullptr).v[0] : 0;
-      k1[u] = (NK == 2 && alive[u]) ? ld_stream_vec(kcol1 + rel, (i64xG<1>*)nullptr).v[0] : 0;
-      a[u] = (wcol[0] && alive[u]) ? (unsigned long long)ld_stream_vec(wcol[0] + rel, (i64xG<1>*)nullptr).v[0] : wcst[0];
-      b[u] = (wcol[1] && alive[u]) ? (unsigned long long)ld_stream_vec(wcol[1] + rel, (i64xG<1>*)nullptr).v[0] : wcst[1];
+      const long long rel = (unit0 + u) * 32 + lane, row = row_begin + rel;
+      alive[u] = rel < n; meta[u] = 0xC; k0[u] = 0; k1[u] = 0; v0[u] = 0; v1[u] = 0;
+      if (!alive[u]) continue;
+      if (!TYPED) {
+        k0[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[0]].values + row, (i64xG<1>*)nullptr).v[0];
+        if (NK == 2) k1[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[1]].values + row, (i64xG<1>*)nullptr).v[0];
+        if (add0) v0[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[0].col].values + row, (i64xG<1>*)nullptr).v[0];
+        if (add1) v1[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[1].col].values + row, (i64xG<1>*)nullptr).v[0];
+      } else {
+        { const DevCol& c = cols.col[fs.key_col[0]]; if (col_valid(c, row)) k0[u] = col_load_int(c, fs.key_phys[0], row); else meta[u] |= 1u; }
+        if (NK == 2) { const DevCol& c = cols.col[fs.key_col[1]]; if (col_valid(c, row)) k1[u] = col_load_int(c, fs.key_phys[1], row); else meta[u] |= 2u; }
+        if (fs.acc[0].col >= 0) {
+          const DevCol& c = cols.col[fs.acc[0].col];
+          if (!col_valid(c, row)) meta[u] &= ~4u; else if (add0) v0[u] = (unsigned long long)col_load_int(c, fs.acc[0].phys, row);
+        }
+        if (NACC == 2 && fs.acc[1].col >= 0) {
+          const DevCol& c = cols.col[fs.acc[1].col];
+          if (!col_valid(c, row)) meta[u] &= ~8u; else if (add1) v1[u] = (unsigned long long)col_load_int(c, fs.acc[1].phys, row);
+        }
+      }
     }
-    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
-      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts (NULL -> row dropped)
+      const DevCol& c = cols.col[fs.filt[f].col];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const long long rel = (unit0 + u) * 32 + lane;
-        const long long x = rel < n ? ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0] : 0;
-        alive[u] = alive[u] && cmp_apply(fs.filt[f].op, x, fs.filt[f].lit);
+        const long long row = row_begin + (unit0 + u) * 32 + lane;
+        if (!alive[u]) continue;
+        if (!TYPED) alive[u] = cmp_apply(fs.filt[f].op, ld_stream_vec((const long long*)c.values + row, (i64xG<1>*)nullptr).v[0], fs.filt[f].lit);
+        else alive[u] = col_valid(c, row) && cmp_apply(fs.filt[f].op, col_load_int(c, fs.filt[f].phys, row), fs.filt[f].lit);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       unsigned long long di;
-      const bool in = dense_index<NK>(fs, k0[u], k1[u], di) && alive[u];
-      const unsigned mi = in ? (unsigned)di : NONE;
-      const unsigned pi = __shfl_xor_sync(0xffffffffu, mi, 1);                                     // neighbour's entry
-      const unsigned long long pb = wcol[1] ? __shfl_xor_sync(0xffffffffu, b[u], 1) : wcst[1];
-      unsigned long long* const mine = mi != NONE ? fs.dense_tab + (uint64_t)mi * 2 : sink;
-      unsigned long long* const theirs = pi != NONE ? fs.dense_tab + (uint64_t)pi * 2 + 1 : sink;
-      const unsigned long long mv = mi != NONE ? a[u] : 0ULL, tv = pi != NONE ? pb : 0ULL;
-      red_add_u64(odd ? theirs : mine, odd ? tv : mv);          // step 1: rows of even lanes: {word 0 by the owner, word 1 by its odd neighbour}
-      red_add_u64(odd ? mine : theirs, odd ? mv : tv);          // step 2: rows of odd lanes
-      // keys outside the dense range (rare): straight to the hashed slots
+      const bool in = dense_index<NK>(fs, k0[u], k1[u], di) && alive[u] && !(meta[u] & 3u);
+      const unsigned pk = in ? ((unsigned)di | ((meta[u] & 0xCu) << 26)) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int t = 0; t < G; t++) {                             // step t: the G lanes of a group update the G words of the group's t-th row
+        const unsigned opk = __shfl_sync(0xffffffffu, pk, t, G);
+        const unsigned long long ov0 = add0 ? __shfl_sync(0xffffffffu, v0[u], t, G) : 0ULL;
+        const unsigned long long ov1 = add1 ? __shfl_sync(0xffffffffu, v1[u], t, G) : 0ULL;
+        const bool live = opk != 0xFFFFFFFFu;
+        unsigned long long val;
+        switch (wkind) {
+          case DW_ONE: val = 1; break;
+          case DW_ADD0: val = ov0; break;                       // a NULL argument was loaded as 0
+          case DW_ADD1: val = ov1; break;
+          case DW_VALID0: val = (opk >> 28) & 1u; break;
+          case DW_VALID1: val = (opk >> 29) & 1u; break;
+          default: val = 0; break;
+        }
+        red_add_u64(live ? fs.dense_tab + (uint64_t)(opk & IDX_MASK) * G + q : sink, live ? val : 0ULL);
+      }
+      // keys outside the dense range / NULL keys (rare): straight to the hashed slots
       const bool fb = alive[u] && !in;
       if (__any_sync(0xffffffffu, fb)) {
         bool inserted = false;
         if (fb) {
-          const long long rel = (unit0 + u) * 32 + lane;
           uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
+          const unsigned knull = meta[u] & 3u;
           unsigned fl = 0;
-          const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash2(kw[0], kw[1], 0), &fl, &inserted);
-          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)rel; }
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, knull, agg_hash2(kw[0], kw[1], knull), &fl, &inserted);
+          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); }
           else {
             unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
-#pragma unroll
-            for (int j = 0; j < NACC; j++) {
-              const unsigned long long x = fs.acc[j].kind == FAST_ACC_ADD ? (unsigned long long)__ldg((const long long*)cols.col[fs.acc[j].col].values + row_begin + rel) : 1ULL;
-              red_add_u64(p + fs.acc[j].word, x);
-              slot_mark(tab.keys + si * (uint64_t)lay.kstride, fl, fs.acc[j].vbit);
-            }
+            unsigned long long* const ke = tab.keys + si * (uint64_t)lay.kstride;
+            if (meta[u] & 4u) { red_add_u64(p + fs.acc[0].word, add0 ? v0[u] : 1ULL); slot_mark(ke, fl, fs.acc[0].vbit); }
+            if (NACC == 2 && (meta[u] & 8u)) { red_add_u64(p + fs.acc[1].word, add1 ? v1[u] : 1ULL); slot_mark(ke, fl, fs.acc[1].vbit); }
           }
         }
         const unsigned bl = __ballot_sync(0xffffffffu, inserted);
@@ -699,12 +601,6 @@ static int fast_grid(int64_t ntiles) {
   return (int)(ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap);
 }
 
-template <int NK, int NACC>
-static void launch_gang(int dg, int grid, cudaStream_t s, const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n) {
-  if (dg == 4) agg_gang_update_kernel<NK, NACC, 4><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-  else agg_gang_update_kernel<NK, NACC, 2><<<grid, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n);
-}
-
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
   const int dg = fs.dense ? fs.dense_stride : 0;
@@ -720,23 +616,24 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
 #undef B200Q_DS
     return 1;
   }
-  if (dg == 2 && fs.lean && (fs.nkeys == 2 || fs.nfilt > 0)) {
-    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
-#define B200Q_LR(NACC, NK) agg_lean_dense_row_kernel<NACC, NK><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
-    if (fs.nkeys == 1) { if (fs.nacc == 2) B200Q_LR(2, 1); else B200Q_LR(1, 1); } else { if (fs.nacc == 2) B200Q_LR(2, 2); else B200Q_LR(1, 2); }
-#undef B200Q_LR
-    return 1;
-  }
-  if (dg && fs.lean) {
+  if (dg && fs.lean && fs.nkeys == 1 && fs.nfilt == 0) {        // the bare M1 shape: gang form, wide loads
     const int u = dg == 2 ? 4 : 2;
     const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
-#define B200Q_LD(NACC, G, NK) agg_lean_dense_kernel<NACC, G, NK><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
-    if (fs.nkeys == 1) {
-      if (fs.nacc == 2) { if (dg == 2) B200Q_LD(2, 2, 1); else B200Q_LD(2, 4, 1); } else { if (dg == 2) B200Q_LD(1, 2, 1); else B200Q_LD(1, 4, 1); }
-    } else {
-      if (fs.nacc == 2) { if (dg == 2) B200Q_LD(2, 2, 2); else B200Q_LD(2, 4, 2); } else { if (dg == 2) B200Q_LD(1, 2, 2); else B200Q_LD(1, 4, 2); }
-    }
+#define B200Q_LD(NACC, G) agg_lean_dense_kernel<NACC, G, 1><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.nacc == 2) { if (dg == 2) B200Q_LD(2, 2); else B200Q_LD(2, 4); } else { if (dg == 2) B200Q_LD(1, 2); else B200Q_LD(1, 4); }
 #undef B200Q_LD
+    return 1;
+  }
+  if (dg) {                                                     // filters / two keys / typed inputs: one row per lane
+    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
+#define B200Q_DR(NACC, NK, G) do { if (fs.lean) agg_dense_row_kernel<NACC, NK, G, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); \
+                                   else agg_dense_row_kernel<NACC, NK, G, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); } while (0)
+    if (fs.nkeys == 1) {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_DR(2, 1, 2); else B200Q_DR(2, 1, 4); } else { if (dg == 2) B200Q_DR(1, 1, 2); else B200Q_DR(1, 1, 4); }
+    } else {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_DR(2, 2, 2); else B200Q_DR(2, 2, 4); } else { if (dg == 2) B200Q_DR(1, 2, 2); else B200Q_DR(1, 2, 4); }
+    }
+#undef B200Q_DR
     return 1;
   }
   if (!dg) {
@@ -748,11 +645,7 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
 #undef B200Q_LH
     return 1;
   }
-  const int grid = fast_grid((n + FA_TILE - 1) / FA_TILE);
-  // typed dense table: rows outside the dense range / NULL keys fall through to the hashed slots inside the kernel
-  if (fs.nkeys == 1) { if (fs.nacc == 2) launch_gang<1, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<1, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
-  else { if (fs.nacc == 2) launch_gang<2, 2>(dg, grid, s, cols, fs, lay, tab, row_begin, n); else launch_gang<2, 1>(dg, grid, s, cols, fs, lay, tab, row_begin, n); }
-  return 1;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
