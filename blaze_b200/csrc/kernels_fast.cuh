@@ -17,7 +17,7 @@ struct FastSpec {
   long long dense_base1;                                  //        entry index = (key0 - dense_base) * dense_r1 + (key1 - dense_base1)   (two keys)
   unsigned long long dense_r1, dense_cap0;                // key1 - dense_base1 < dense_r1, key0 - dense_base < dense_cap0; dense_cap = dense_cap0 * dense_r1
   unsigned long long* dense_tab;
-  int8_t dense_stride;                                    // 2 or 4 words per entry (= gang width)
+  int8_t dense_stride;                                    // 2 or 4 words per entry (= lanes that update one entry in one instruction)
   int8_t dense_word_src[4];                               // per entry word: -1 row counter (+1), -2 padding (+0), j accumulator j, 2+j valid arguments of accumulator j
   uint8_t dense_presence_word;                            // word that is non-zero iff the entry holds a group
   uint8_t _pad1[2];
