@@ -79,6 +79,15 @@ klow = torch.randint(0, 64, (rows,), dtype=torch.int64, device=dev, generator=g)
 run("M1 low cardinality (64 groups) dense", m1.plan_bytes(), [klow, v], 16.0, native.default_conf())
 run("M1 low cardinality (64 groups) hash", m1.plan_bytes(), [klow, v], 16.0, native.default_conf(agg_dense_keys=0), reps=1, steady=True)
 del klow
+# skewed keys: Zipf(1.1) ranks over 2^20 keys (continuous inverse-CDF approximation), rank r -> key (r * 2654435761) mod 2^20
+u = torch.rand(rows, device=dev, generator=g, dtype=torch.float64)
+nk, sz = float(1 << 20), 1.1
+ranks = torch.clamp(((u * (nk ** (1 - sz) - 1) + 1) ** (1 / (1 - sz))).floor().to(torch.int64), 1, 1 << 20) - 1
+kz = (ranks * 2654435761) % (1 << 20)
+del u, ranks
+run("M1 Zipf(1.1) keys, dense", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20), reps=1)
+run("M1 Zipf(1.1) keys, hash", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
+del kz
 run("M1 generic VM kernel", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
 del k
 # M2: q1-shaped: f BETWEEN lo AND hi (s = 0.2), keys (k1 ~ U[0,2^17), k2 ~ U[0,8)), SUM(v)   (32 B/row)
