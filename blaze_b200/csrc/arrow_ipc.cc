@@ -150,7 +150,7 @@ ExprP decode_ipc_literal(const uint8_t* bytes, size_t n) {
       auto buf_at = [&](uint32_t i, int64_t& off, int64_t& len) {
         if (i >= bufs.len) throw PlanError(B200Q_ERR_INVALID_PLAN, "literal: missing buffer");
         off = m.meta.rd<int64_t>(bufs.pos + 16 * (size_t)i); len = m.meta.rd<int64_t>(bufs.pos + 16 * (size_t)i + 8);
-        if (off < 0 || len < 0 || off + len > m.body_len) throw PlanError(B200Q_ERR_INVALID_PLAN, "literal: buffer out of body");
+        if (off < 0 || len < 0 || len > (int64_t)m.body_len || off > (int64_t)m.body_len - len) throw PlanError(B200Q_ERR_INVALID_PLAN, "literal: buffer out of body");
       };
       const uint8_t* body = bytes + m.body_off;
       if (e->type.id == T_NULL) { e->lit_null = true; have_batch = true; break; }
