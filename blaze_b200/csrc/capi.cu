@@ -451,6 +451,7 @@ static void conf_defaults(b200q_conf* c) {
   c->partial_state_columnar = 0;
   c->force_generic_kernels = 0;
   c->agg_dense_keys = 1;
+  c->agg_hot_key_cache = 0;
 }
 
 }  // namespace b200q

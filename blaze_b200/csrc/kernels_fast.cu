@@ -63,6 +63,15 @@ __device__ __forceinline__ unsigned long long* warp_sink(const FastSpec& fs, lon
   return fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + (m & 3);
 }
 
+// 64-bit wrapping add on shared memory made of native 32-bit shared atomics: low half with the old value returned,
+// high half plus the carry.  Exact mod 2^64 in any order (every carry is observed exactly once).
+__device__ __forceinline__ void smem_add64(unsigned* w, unsigned long long v) {
+  const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  unsigned carry = 0;
+  if (lo) { const unsigned old = atomicAdd(w, lo); carry = old + lo < old; }
+  if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
 // dense entry index of a row; false: outside the dense range (the row goes to a hashed slot)
 template <int NK>
 __device__ __forceinline__ bool dense_index(const FastSpec& fs, long long k0, long long k1, unsigned long long& idx) {
@@ -302,6 +311,138 @@ __global__ void __launch_bounds__(FA_BLOCK) agg_dense_row_kernel(const ColTable 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (b200q_conf.agg_hot_key_cache, off by default; validated on the CPU build only so far): dense kernel
+// for SKEWED keys.  Every RED on a hot key serialises in the L2 (Zipf 1.1 over 2^20 keys: 1.5e10 rows/s instead of
+// 1.5e11).  Each CTA keeps a direct-mapped write-combining cache of 1024 entries in shared memory: the first key that
+// claims a line keeps it for the CTA's lifetime (hot keys show up early and often), its rows are accumulated with
+// shared-memory atomics; every other row takes the global RED path of agg_dense_row_kernel.  Lines are added to the
+// global table once, at the end.  Non-null 8-byte-aligned int64 inputs only.
+// ---------------------------------------------------------------------------------------------------
+constexpr int HC_LINES = 1024;
+template <int NACC, int NK, int G>
+__global__ void __launch_bounds__(FA_BLOCK) agg_dense_hot_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                 long long row_begin, long long n) {
+  constexpr int U = 4;
+  constexpr unsigned IDX_MASK = 0x0FFFFFFFu;
+  __shared__ unsigned long long c_key[HC_LINES];                // dense entry index + 1 (0: free line)
+  __shared__ unsigned c_acc[HC_LINES * G * 2];                  // the entry's words as 32-bit halves (smem_add64)
+  for (int i = threadIdx.x; i < HC_LINES; i += FA_BLOCK) c_key[i] = 0;
+  for (int i = threadIdx.x; i < HC_LINES * G * 2; i += FA_BLOCK) c_acc[i] = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, q = lane & (G - 1);
+  const long long gwarp = (long long)blockIdx.x * (FA_BLOCK / 32) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (FA_BLOCK / 32);
+  const long long nunits = (n + 31) / 32;
+  const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
+  auto word_kind = [&](int m) {                                 // what word m of an entry accumulates (non-null inputs: every argument counts)
+    const int src = fs.dense_word_src[m];
+    return src == -1 ? DW_ONE : src == -2 ? DW_ZERO : src >= 2 ? DW_ONE : src == 0 ? (add0 ? DW_ADD0 : DW_ONE) : (add1 ? DW_ADD1 : DW_ONE);
+  };
+  int wk[G];
+#pragma unroll
+  for (int m = 0; m < G; m++) wk[m] = word_kind(m);
+  const int wkind = word_kind((int)q);
+  unsigned long long* const sink = warp_sink(fs, gwarp, lane);
+
+  for (long long unit0 = gwarp * U; unit0 < nunits; unit0 += nwarps * U) {
+    long long k0[U], k1[U]; unsigned long long v0[U], v1[U]; bool alive[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long rel = (unit0 + u) * 32 + lane, row = row_begin + rel;
+      alive[u] = rel < n; k0[u] = 0; k1[u] = 0; v0[u] = 0; v1[u] = 0;
+      if (!alive[u]) continue;
+      k0[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[0]].values + row, (i64xG<1>*)nullptr).v[0];
+      if (NK == 2) k1[u] = ld_stream_vec((const long long*)cols.col[fs.key_col[1]].values + row, (i64xG<1>*)nullptr).v[0];
+      if (add0) v0[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[0].col].values + row, (i64xG<1>*)nullptr).v[0];
+      if (add1) v1[u] = (unsigned long long)ld_stream_vec((const long long*)cols.col[fs.acc[1].col].values + row, (i64xG<1>*)nullptr).v[0];
+    }
+    for (int f = 0; f < fs.nfilt; f++) {                        // fused FilterExec conjuncts
+      const long long* fcol = (const long long*)cols.col[fs.filt[f].col].values + row_begin;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long rel = (unit0 + u) * 32 + lane;
+        if (alive[u]) alive[u] = cmp_apply(fs.filt[f].op, ld_stream_vec(fcol + rel, (i64xG<1>*)nullptr).v[0], fs.filt[f].lit);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      unsigned long long di;
+      const bool in = dense_index<NK>(fs, k0[u], k1[u], di) && alive[u];
+      bool cached = false;
+      if (in) {
+        const unsigned line = (unsigned)((di * 0x9E3779B97F4A7C15ULL) >> 54);                     // 1024 lines
+        const unsigned long long mine = di + 1;
+        unsigned long long cur = *(volatile unsigned long long*)&c_key[line];
+        if (cur == 0) { cur = atomicCAS(&c_key[line], 0ULL, mine); if (cur == 0) cur = mine; }
+        if (cur == mine) {
+          cached = true;
+          unsigned* const e = c_acc + line * (G * 2);
+#pragma unroll
+          for (int m = 0; m < G; m++) {
+            if (wk[m] == DW_ONE) smem_add64(e + 2 * m, 1ULL);
+            else if (wk[m] == DW_ADD0) smem_add64(e + 2 * m, v0[u]);
+            else if (wk[m] == DW_ADD1) smem_add64(e + 2 * m, v1[u]);
+          }
+        }
+      }
+      const unsigned pk = (in && !cached) ? (unsigned)di : 0xFFFFFFFFu;
+#pragma unroll
+      for (int t = 0; t < G; t++) {                             // the global path: see agg_dense_row_kernel
+        const unsigned opk = __shfl_sync(0xffffffffu, pk, t, G);
+        const unsigned long long ov0 = add0 ? __shfl_sync(0xffffffffu, v0[u], t, G) : 0ULL;
+        const unsigned long long ov1 = add1 ? __shfl_sync(0xffffffffu, v1[u], t, G) : 0ULL;
+        const bool live = opk != 0xFFFFFFFFu;
+        const unsigned long long val = wkind == DW_ONE ? 1ULL : wkind == DW_ADD0 ? ov0 : wkind == DW_ADD1 ? ov1 : 0ULL;
+        red_add_u64(live ? fs.dense_tab + (uint64_t)(opk & IDX_MASK) * G + q : sink, live ? val : 0ULL);
+      }
+      const bool fb = alive[u] && !in;                          // outside the dense range (rare): hashed slots
+      if (__any_sync(0xffffffffu, fb)) {
+        bool inserted = false;
+        if (fb) {
+          uint64_t kw[2] = {(uint64_t)k0[u], NK == 2 ? (uint64_t)k1[u] : 0ULL};
+          unsigned fl = 0;
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, 0, agg_hash2(kw[0], kw[1], 0), &fl, &inserted);
+          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)((unit0 + u) * 32 + lane); }
+          else {
+            unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
+            unsigned long long* const ke = tab.keys + si * (uint64_t)lay.kstride;
+            red_add_u64(p + fs.acc[0].word, add0 ? v0[u] : 1ULL); slot_mark(ke, fl, fs.acc[0].vbit);
+            if (NACC == 2) { red_add_u64(p + fs.acc[1].word, add1 ? v1[u] : 1ULL); slot_mark(ke, fl, fs.acc[1].vbit); }
+          }
+        }
+        const unsigned bl = __ballot_sync(0xffffffffu, inserted);
+        if (lane == 0 && bl) atomicAdd(tab.counters, (unsigned long long)__popc(bl));
+      }
+    }
+  }
+  __syncthreads();
+  for (int line = threadIdx.x; line < HC_LINES; line += FA_BLOCK) {
+    const unsigned long long key = c_key[line];
+    if (!key) continue;
+#pragma unroll
+    for (int m = 0; m < G; m++) {
+      const unsigned long long val = (unsigned long long)c_acc[(line * G + m) * 2] | ((unsigned long long)c_acc[(line * G + m) * 2 + 1] << 32);
+      if (val) red_add_u64(fs.dense_tab + (key - 1) * G + m, val);
+    }
+  }
+}
+
+// skew probe: 65536-bucket histogram of the key hashes of a sample, then its maximum -> hist[65536]
+__global__ void __launch_bounds__(256) key_skew_hist_kernel(const DevCol c0, const DevCol c1, int phys0, int phys1, int nkeys, long long n, unsigned* hist) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!col_valid(c0, i) || (nkeys == 2 && !col_valid(c1, i))) continue;
+    const uint64_t h = agg_hash2((uint64_t)col_load_int(c0, phys0, i), nkeys == 2 ? (uint64_t)col_load_int(c1, phys1, i) : 0ULL, 0);
+    atomicAdd(hist + (h >> 48), 1u);
+  }
+}
+__global__ void __launch_bounds__(256) key_skew_max_kernel(unsigned* hist) {
+  unsigned mx = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 65536; i += gridDim.x * blockDim.x) mx = max(mx, hist[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0) atomicMax(hist + 65536, mx);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // LEAN hashed kernel: 1-2 non-null int64 keys, non-null int64 accumulator/filter columns (same preconditions as
 // the lean dense kernel), one row per lane, compacted probe rounds.  A lane-parallel probe walk waits, per warp
 // step, for the LONGEST collision chain among its rows (a dependent L2 round trip per extra slot with most lanes
@@ -495,12 +636,6 @@ __global__ void __launch_bounds__(LH_BLOCK, TYPED ? 4 : 6) agg_lean_hash_kernel(
 // TYPED = false: non-null int64 columns; TYPED = true: any integer width + validity bitmaps (NULL key -> hashed slot).
 // ---------------------------------------------------------------------------------------------------
 constexpr int DS_MAX_WORDS = 4096;
-__device__ __forceinline__ void smem_add64(unsigned* w, unsigned long long v) {
-  const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
-  unsigned carry = 0;
-  if (lo) { const unsigned old = atomicAdd(w, lo); carry = old + lo < old; }
-  if (hi + carry) atomicAdd(w + 1, hi + carry);
-}
 template <int NACC, bool TYPED, int NK>
 __global__ void __launch_bounds__(FA_BLOCK) agg_dense_smem_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
                                                                   long long row_begin, long long n) {
@@ -616,6 +751,17 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
 #undef B200Q_DS
     return 1;
   }
+  if (dg && fs.lean && fs.hot_cache) {                          // EXPERIMENTAL: skewed keys (b200q_conf.agg_hot_key_cache)
+    const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
+#define B200Q_HC(NACC, NK, G) agg_dense_hot_kernel<NACC, NK, G><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+    if (fs.nkeys == 1) {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_HC(2, 1, 2); else B200Q_HC(2, 1, 4); } else { if (dg == 2) B200Q_HC(1, 1, 2); else B200Q_HC(1, 1, 4); }
+    } else {
+      if (fs.nacc == 2) { if (dg == 2) B200Q_HC(2, 2, 2); else B200Q_HC(2, 2, 4); } else { if (dg == 2) B200Q_HC(1, 2, 2); else B200Q_HC(1, 2, 4); }
+    }
+#undef B200Q_HC
+    return 1;
+  }
   if (dg && fs.lean && fs.nkeys == 1 && fs.nfilt == 0) {        // the bare M1 shape: gang form, wide loads
     const int u = dg == 2 ? 4 : 2;
     const int g = fast_grid((n + 32 * 8 * u - 1) / (32 * 8 * u));
@@ -664,6 +810,11 @@ __global__ void __launch_bounds__(256) key_range_kernel(const DevCol col, int ph
     mn = a < mn ? a : mn; mx = b > mx ? b : mx; cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
   }
   if ((threadIdx.x & 31) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); atomicAdd((unsigned long long*)out + 2, cnt); }
+}
+int launch_key_skew_probe(const DevCol* key_cols, const uint8_t* phys, int nkeys, int64_t n, unsigned* d_hist, cudaStream_t s) {
+  key_skew_hist_kernel<<<fast_grid((n + 2047) / 2048), 256, 0, s>>>(key_cols[0], key_cols[nkeys == 2 ? 1 : 0], phys[0], phys[nkeys == 2 ? 1 : 0], nkeys, n, d_hist);
+  key_skew_max_kernel<<<32, 256, 0, s>>>(d_hist);
+  return 2;
 }
 int launch_key_range(const DevCol& col, int phys, int64_t n, long long* d_out, cudaStream_t s) {
   key_range_kernel<<<fast_grid((n + 2047) / 2048), 256, 0, s>>>(col, phys, n, d_out);

@@ -8,7 +8,7 @@ enum FastAccKind : uint8_t { FAST_ACC_ADD = 0, FAST_ACC_COUNT = 1 };   // COUNT 
 
 struct FastSpec {
   int32_t nkeys, nacc, nfilt, dense;
-  int32_t lean, _pad0;                                    // lean: all referenced columns are aligned non-null int64 (set per launch)
+  int32_t lean, hot_cache;                                // lean: all referenced columns are aligned non-null int64 (set per launch); hot_cache: skewed keys (experimental)
   int8_t key_col[2]; uint8_t key_phys[2];                 // program column slots / physical kinds of the key columns
   struct { uint8_t kind; int8_t col; uint8_t phys; uint8_t vbit; uint8_t word; uint8_t _pad[3]; } acc[2];
   struct { int8_t col; uint8_t phys; uint8_t op; uint8_t _pad[5]; long long lit; } filt[4];
@@ -29,6 +29,7 @@ constexpr int FAST_SINK_WARPS = 4096;
 struct DenseEmitMap { uint8_t word[EMIT_MAX_COLS]; uint8_t valid_word[EMIT_MAX_COLS]; };
 
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
+int launch_key_skew_probe(const DevCol* key_cols, const uint8_t* phys, int nkeys, int64_t n, unsigned* d_hist /* 65536 + 1 words, zeroed */, cudaStream_t s);
 int launch_key_range(const DevCol& col, int phys, int64_t n, long long* d_out, cudaStream_t s);
 int launch_agg_emit_dense(const FastSpec& fs, const EmitTable& emit, const DenseEmitMap& map, unsigned long long* d_out_count, cudaStream_t s);
 int launch_dense_count(const FastSpec& fs, unsigned long long* d_out, cudaStream_t s);

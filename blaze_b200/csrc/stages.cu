@@ -590,6 +590,15 @@ class AggStage : public Stage {
     dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * fs_.dense_stride * 8, cx.stream, true);
     fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;
     fs_.dense = 1;
+    if (cx.conf.agg_hot_key_cache && fs_.dense_cap * fs_.dense_stride > 4096) {     // EXPERIMENTAL: do a few keys dominate the sample?
+      DevMemP hist = DevMem::alloc((65536 + 1) * 4, cx.stream, true);
+      DevCol kc[2] = {ct.col[fs_.key_col[0]], ct.col[fs_.key_col[fs_.nkeys == 2 ? 1 : 0]]};
+      cx.m.launches += launch_key_skew_probe(kc, fs_.key_phys, fs_.nkeys, sample, (unsigned*)hist->ptr, cx.stream);
+      unsigned mx = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&mx, (unsigned*)hist->ptr + 65536, 4, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      fs_.hot_cache = (uint64_t)mx * 256 > (uint64_t)sample ? 1 : 0;          // one hash bucket holds > 0.4 % of the rows
+    }
   }
 
   // LEAN kernels: every referenced column is a non-null, 32-byte aligned int64 column

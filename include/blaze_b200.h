@@ -132,6 +132,9 @@ typedef struct b200q_conf {
   int32_t force_generic_kernels;      /* 1: disable the specialised fast kernels (testing)        */
   int32_t agg_dense_keys;             /* 1 (default): single integer keys spanning a small range
                                          are direct-indexed (no probe); 0: always hash           */
+  int32_t agg_hot_key_cache;          /* EXPERIMENTAL (default 0): probe the first batch for key skew and, when a
+                                         few keys dominate, combine their updates in a CTA-private
+                                         shared-memory cache before the global table */
 } b200q_conf;
 
 typedef struct b200q_metrics {
