@@ -120,8 +120,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rows = env_int("B200Q_BENCH_ROWS", 1_000_000_000)
-    e2e_rows = env_int("B200Q_BENCH_E2E_ROWS", rows)
     e2e_batch = env_int("B200Q_BENCH_E2E_BATCH_ROWS", 1 << 24)
+    # the e2e leg keeps its input in PINNED host memory (16 B/row): all ranks of the node together stay below
+    # min(64 GB, 35 % of MemAvailable) so that an 8-rank run cannot drive the box out of memory
+    e2e_rows = env_int("B200Q_BENCH_E2E_ROWS", 0)
+    if e2e_rows <= 0:
+        budget = min(64e9, 0.35 * mem_available_bytes())
+        e2e_rows = int(min(rows, max(e2e_batch, budget / (16 * world) // e2e_batch * e2e_batch)))
     plans = m1_plans()
     gen = torch.Generator(device=dev); gen.manual_seed(44 + rank)
     k = torch.randint(0, CARD, (rows,), dtype=torch.int64, device=dev, generator=gen)
@@ -289,6 +294,16 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64e9
 
 
 def bind_to_gpu_numa(torch, local):
