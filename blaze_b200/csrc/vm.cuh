@@ -2,7 +2,7 @@
 // program counter and stack pointer are warp-uniform: instruction fetches are shared-memory
 // broadcasts and the (local-memory) stack accesses are perfectly coalesced.
 //
-// Semantics follow the oracle (oracle/blaze_oracle.py), which restates DataFusion 49 / arrow-rs 55.2
+// Semantics follow the reference (DataFusion 49 / arrow-rs 55.2 as the reference pins them), restated for the tests in oracle/blaze_oracle.py:
 // expression evaluation as used by CachedExprsEvaluator (cached_exprs_evaluator.rs:90-166).
 #pragma once
 #include <cuda_runtime.h>

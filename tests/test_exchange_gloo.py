@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the partial->final exchange plumbing (CPU): partition ids follow the
+"""world_size-2/4/8 gloo tests of the partial->final exchange plumbing (CPU): partition ids follow the
 reference's murmur3(seed 42) pmod rule (oracle), every group ends up on exactly one owner rank, and
 merging what each rank received reproduces the single-process aggregate."""
 import os
@@ -38,15 +38,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_exchange_two_ranks_gloo():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() * 8 + world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
