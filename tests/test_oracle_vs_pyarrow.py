@@ -102,3 +102,55 @@ def test_group_by_matches_pyarrow(seed, n, nf):
         # pyarrow's hash sum is checked-free wrapping like the reference's; all-null groups are NULL on both sides
         assert gc == ec and gmn == emn and gmx == emx
         assert gs == (None if es is None else ((es + 2**63) % 2**64) - 2**63)
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 200), p=st.integers(10, 30), s=st.integers(0, 6), to_p=st.integers(5, 30), to_s=st.integers(0, 8))
+def test_decimal_helpers_match_python_decimal(seed, n, p, s, to_p, to_s):
+    """CheckOverflow (round half up, NULL on overflow; spark_check_overflow.rs:84-124), UnscaledValue / MakeDecimal
+    (spark_unscaled_value.rs:24-42, spark_make_decimal.rs:24-58) and decimal SUM/AVG (avg.rs:158-165: i128
+    checked_div_euclid at the result scale) against Python's arbitrary-precision `decimal` / `int`"""
+    import decimal as D
+    rng = np.random.default_rng(seed)
+    raw = [int(rng.integers(-10**(min(p, 18)) + 1, 10**(min(p, 18)))) for _ in range(n)]
+    mask = rng.random(n) < 0.2
+    arr = pa.array([None if m else D.Decimal(r).scaleb(-s) for r, m in zip(raw, mask)], type=pa.decimal128(p, s))
+    keys = rng.integers(0, 5, n, dtype=np.int64)
+    rb = pa.RecordBatch.from_arrays([pa.array(keys), arr], names=["k", "d"])
+    ob = O.batch_from_arrow(rb)
+    X = E.Column("d")
+    # CheckOverflow
+    got = O.evaluate(E.ScalarFunction("CheckOverflow", [X, E.Literal(to_p, T.int32), E.Literal(to_s, T.int32)], T.decimal128(to_p, to_s)), ob).broadcast(n)
+    ctx = D.Context(prec=80)
+    for i in range(n):
+        if mask[i]:
+            assert not got.valid[i]
+            continue
+        q = D.Decimal(raw[i]).scaleb(-s).quantize(D.Decimal(1).scaleb(-to_s), rounding=D.ROUND_HALF_UP, context=ctx)
+        unscaled = int(q.scaleb(to_s))
+        if abs(unscaled) >= 10**to_p:
+            assert not got.valid[i]
+        else:
+            assert got.valid[i] and int(got.values[i]) == unscaled
+    # UnscaledValue -> MakeDecimal round trip (values fit i64 here)
+    u = O.evaluate(E.ScalarFunction("UnscaledValue", [X], T.int64), ob).broadcast(n)
+    assert all((not u.valid[i]) if mask[i] else int(u.values[i]) == raw[i] for i in range(n))
+    # decimal SUM (result precision p+10) and AVG (precision p+4, scale s+4) per key
+    rt_sum, rt_avg = T.decimal128(min(38, p + 10), s), T.decimal128(min(38, p + 4), min(38, s + 4))
+    g = [E.GroupingExpr("k", E.Column("k"))]
+    from blaze_b200 import plans as PL
+    mk = lambda mode, ch: [E.AggExpr("s", mode, PL.create_agg(E.AGG_SUM, ch, ob.schema, rt_sum)), E.AggExpr("a", mode, PL.create_agg(E.AGG_AVG, ch, ob.schema, rt_avg))]
+    part = O.AggExec(E.HASH_AGG, g, mk(E.PARTIAL, [X]), False, ob.schema)
+    fin = O.AggExec(E.HASH_AGG, g, mk(E.FINAL, [E.placeholder(T.decimal128(p, s))]), False, part.schema)
+    out = O.concat_batches(fin.schema, fin.execute(part.execute([ob])))
+    for i in range(out.num_rows):
+        k = int(out.cols[0].values[i])
+        vals = [raw[j] for j in range(n) if keys[j] == k and not mask[j]]
+        if not vals:
+            assert not out.cols[1].valid[i] and not out.cols[2].valid[i]
+            continue
+        assert int(out.cols[1].values[i]) == sum(vals)
+        num = sum(vals) * 10 ** (rt_avg.scale - s)                    # the sum rescaled to the AVG scale, then euclidean division by the count
+        cnt = len(vals)
+        qe = num // cnt if num >= 0 else -((-num + cnt - 1) // cnt)    # i128::div_euclid with a positive divisor = floor division
+        assert out.cols[2].valid[i] and int(out.cols[2].values[i]) == qe
