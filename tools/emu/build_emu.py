@@ -1,13 +1,15 @@
 """Prepare host-compilable copies of the HashAgg kernel sources for the thread-per-lane emulator (tools/emu):
 copies blaze_b200/csrc/{vm.h,kernels.cuh,kernels_fast.cuh,agg_device.cuh,kernels_fast.cu} into <out>/, rewrites every
-inline-PTX statement into the host helper of tools/emu/include/cuda_runtime.h, and cuts kernels_fast.cu before its
-launchers (`<<<...>>>` is not C++).  The product sources are not modified."""
+inline-PTX statement into the host helper of tools/emu/include/cuda_runtime.h, and rewrites every
+`kernel<<<grid, block, smem, stream>>>(args)` into `emu::Launcher(grid, block, smem, stream).run(...)`, so that the
+real launchers / dispatcher run too.  The product sources are not modified."""
 import os, re, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 SRC = os.path.join(ROOT, "blaze_b200", "csrc")
 
 ASM = re.compile(r'asm\s*(?:volatile)?\s*\(\s*"((?:[^"\\]|\\.)*)"\s*(.*?)\)\s*;', re.S)
+LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)<<<([^>]*)>>>\(([^;{}]*?)\)(?=\s*(?:;|\\|$|\}|else))", re.M)
 OPERAND = re.compile(r'"[^"]*"\s*\(([^()]*(?:\([^()]*\)[^()]*)*)\)')
 
 
@@ -37,14 +39,12 @@ def main(out):
     for fn in ("vm.h", "kernels.cuh", "kernels_fast.cuh", "agg_device.cuh", "kernels_fast.cu"):
         s = open(os.path.join(SRC, fn)).read()
         s, n = ASM.subn(translate, s)
-        if fn == "kernels_fast.cu":
-            cut = s.index("static int fast_grid(")
-            s = s[:cut] + "\n}  // namespace b200q (launchers cut by tools/emu/build_emu.py)\n"
+        s, nl = LAUNCH.subn(r"emu::Launcher(\2).run([&] { (\1)(\3); })", s)     # kernel<<<grid, block, smem, stream>>>(args)
         if "asm" in re.sub(r"//.*", "", s).replace("asm_", ""):
             left = [l for l in s.splitlines() if re.search(r"\basm\b", re.sub(r"//.*", "", l))]
             if left: raise SystemExit(f"build_emu: untranslated asm in {fn}: {left[:3]}")
         open(os.path.join(out, fn), "w").write(s)
-        print(f"{fn}: {n} PTX statements translated")
+        print(f"{fn}: {n} PTX statements translated, {nl} launches rewritten")
 
 
 if __name__ == "__main__":

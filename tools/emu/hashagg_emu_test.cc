@@ -11,7 +11,7 @@
 #include <tuple>
 #include <vector>
 
-#include "kernels_fast.cu"   // translated copy produced by build_emu.py (kernels only, launchers cut)
+#include "kernels_fast.cu"   // translated copy produced by build_emu.py (inline PTX -> host helpers, <<<>>> -> emu::Launcher)
 
 using namespace b200q;
 
@@ -62,7 +62,7 @@ struct Config {
 struct Group { long long rows = 0; unsigned long long sum[2] = {0, 0}; long long nvalid[2] = {0, 0}; };
 using Key = std::tuple<unsigned, long long, long long>;       // (key-is-NULL bits, k0, k1)
 
-bool run(const Config& c, unsigned seed) {
+bool run(const Config& c, unsigned seed, bool via_dispatcher) {
   const long long n = 6000;
   Data d = make_data(n, c.r0, c.r1, c.typed, seed);
   // ---- columns: slots 0 k0, 1 k1, 2 v, 3 w, 4 f ----
@@ -114,6 +114,9 @@ bool run(const Config& c, unsigned seed) {
     if (c.form == 4) fs.hot_cache = 1;
   }
   // ---- run ----
+  if (via_dispatcher) {                                          // the product's own dispatcher picks the kernel form
+    if (launch_agg_fast_update(ct, fs, lay, tab, 0, n, nullptr) != 1) { printf("  %s: dispatcher launched nothing\n", c.name.c_str()); return false; }
+  } else {
   const unsigned grid = 3;
 #define RUN(KERNEL, BLOCK) emu::launch(grid, BLOCK, [&] { KERNEL(ct, fs, lay, tab, 0, n); })
   const int nk = c.nkeys;
@@ -138,6 +141,7 @@ bool run(const Config& c, unsigned seed) {
 #define HOT(NACC, NK, GG) RUN((agg_dense_hot_kernel<NACC, NK, GG>), FA_BLOCK)
     if (nk == 1) { if (nacc == 2) { if (G == 2) HOT(2, 1, 2); else HOT(2, 1, 4); } else { if (G == 2) HOT(1, 1, 2); else HOT(1, 1, 4); } }
     else { if (nacc == 2) { if (G == 2) HOT(2, 2, 2); else HOT(2, 2, 4); } else { if (G == 2) HOT(1, 2, 2); else HOT(1, 2, 4); } }
+  }
   }
   // ---- expected ----
   std::map<Key, Group> exp;
@@ -200,7 +204,7 @@ bool run(const Config& c, unsigned seed) {
   if (counters[0] != (unsigned long long)hashed) { printf("  %s: group counter %llu != %lld hashed slots\n", c.name.c_str(), counters[0], hashed); errors++; }
   if (counters[1] != 0) { printf("  %s: %llu rows deferred (table was sized for all groups)\n", c.name.c_str(), counters[1]); errors++; }
   for (auto& kv : exp) if (!got.count(kv.first)) complain("missing group", kv.first);
-  printf("%-58s %s  (%zu groups, %lld hashed)\n", c.name.c_str(), errors ? "FAIL" : "ok", exp.size(), hashed);
+  printf("%-58s %-10s %s  (%zu groups, %lld hashed)\n", c.name.c_str(), via_dispatcher ? "dispatcher" : "forced", errors ? "FAIL" : "ok", exp.size(), hashed);
   return errors == 0;
 }
 
@@ -238,8 +242,28 @@ int main(int argc, char** argv) {
   int failed = 0, ran = 0;
   for (size_t i = 0; i < cs.size(); i++) {
     if (!only.empty() && cs[i].name.find(only) == std::string::npos) continue;
+    ran += 2;
+    if (!run(cs[i], 1000 + (unsigned)i, false)) failed++;
+    if (!run(cs[i], 1000 + (unsigned)i, true)) failed++;
+  }
+  // the key-range and skew-probe launchers (decide_dense's inputs)
+  if (only.empty()) {
     ran++;
-    if (!run(cs[i], 1000 + (unsigned)i)) failed++;
+    Data d = make_data(50000, 700, 6, true, 7);
+    DevCol kc{d.t_k0.data(), d.vb[0].data(), 0, 0};
+    long long out[3] = {INT64_MAX, INT64_MIN, 0};
+    launch_key_range(kc, PH_I32, d.n, out, nullptr);
+    long long mn = INT64_MAX, mx = INT64_MIN, cnt = 0;
+    for (long long i = 0; i < d.n; i++) if (!d.nk0[i]) { mn = std::min(mn, d.k0[i]); mx = std::max(mx, d.k0[i]); cnt++; }
+    std::vector<unsigned> hist(65536 + 1, 0);
+    DevCol kcs[2] = {kc, kc}; const uint8_t ph[2] = {PH_I32, PH_I32};
+    launch_key_skew_probe(kcs, ph, 1, d.n, hist.data(), nullptr);
+    std::map<long long, unsigned> freq; for (long long i = 0; i < d.n; i++) if (!d.nk0[i]) freq[d.k0[i]]++;
+    unsigned top = 0; for (auto& kv : freq) top = std::max(top, kv.second);
+    unsigned long long total = 0; for (int i = 0; i < 65536; i++) total += hist[i];
+    const bool ok = out[0] == mn && out[1] == mx && out[2] == cnt && total == (unsigned long long)cnt && hist[65536] >= top && hist[65536] <= 4 * top + 16;
+    printf("%-58s %-10s %s\n", "key range + skew probe launchers", "", ok ? "ok" : "FAIL");
+    failed += !ok;
   }
   printf("%d configurations, %d failed\n", ran, failed);
   return failed ? 1 : 0;

@@ -92,6 +92,12 @@ inline void emu_red_min_s64(unsigned long long* p, long long v) { atomicMin((lon
 inline void emu_red_max_s64(unsigned long long* p, long long v) { atomicMax((long long*)p, v); }
 inline unsigned emu_lanemask_lt() { return (1u << emu::lane) - 1u; }
 
+// ---- the few runtime calls the launchers make ----
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return cudaSuccess; }   // one "SM": small grids
+
 // ---- launch: one OS thread per CUDA thread, the blocks of the grid one after the other ----
 namespace emu {
 template <class F> void launch(unsigned grid, unsigned block_threads, F&& kernel_body) {
@@ -108,4 +114,9 @@ template <class F> void launch(unsigned grid, unsigned block_threads, F&& kernel
     for (auto& th : ts) th.join();
   }
 }
+struct Launcher {
+  unsigned grid, block;
+  Launcher(long long g, long long b, long long /*smem*/ = 0, cudaStream_t /*stream*/ = nullptr) : grid((unsigned)g), block((unsigned)b) {}
+  template <class F> void run(F&& body) { launch(grid, block, body); }
+};
 }  // namespace emu
