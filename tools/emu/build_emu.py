@@ -1,5 +1,5 @@
 """Prepare host-compilable copies of the HashAgg kernel sources for the thread-per-lane emulator (tools/emu):
-copies blaze_b200/csrc/{vm.h,kernels.cuh,kernels_fast.cuh,agg_device.cuh,kernels_fast.cu} into <out>/, rewrites every
+copies blaze_b200/csrc/{vm.h,vm.cuh,kernels.cuh,kernels_fast.cuh,agg_device.cuh,kernels_fast.cu,kernels.cu} into <out>/, rewrites every
 inline-PTX statement into the host helper of tools/emu/include/cuda_runtime.h, and rewrites every
 `kernel<<<grid, block, smem, stream>>>(args)` into `emu::Launcher(grid, block, smem, stream).run(...)`, so that the
 real launchers / dispatcher run too.  The product sources are not modified."""
@@ -34,9 +34,13 @@ def translate(m):
     raise SystemExit(f"build_emu: no host translation for PTX `{ptx}`")
 
 
-def main(out):
+def main(top):
+    import shutil
+    out = os.path.join(top, "blaze_b200", "csrc")              # same relative layout as the repo: sources include ../../include/blaze_b200.h
     os.makedirs(out, exist_ok=True)
-    for fn in ("vm.h", "kernels.cuh", "kernels_fast.cuh", "agg_device.cuh", "kernels_fast.cu"):
+    os.makedirs(os.path.join(top, "include"), exist_ok=True)
+    shutil.copy(os.path.join(ROOT, "include", "blaze_b200.h"), os.path.join(top, "include", "blaze_b200.h"))
+    for fn in sorted(f for f in os.listdir(SRC) if f.endswith((".h", ".cuh", ".cu", ".cc"))):
         s = open(os.path.join(SRC, fn)).read()
         s, n = ASM.subn(translate, s)
         s, nl = LAUNCH.subn(r"emu::Launcher(\2).run([&] { (\1)(\3); })", s)     # kernel<<<grid, block, smem, stream>>>(args)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Build the WHOLE library (C ABI, host logic, every kernel) against the host stand-in for the CUDA runtime:
+#   tools/emu/build_lib.sh [outdir]  ->  <outdir>/libblaze_b200_emu.so
+# Test infrastructure only (tools/emu/run_gpu_suite.py loads it explicitly); the product library is blaze_b200/libblaze_b200.so.
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd); OUT=${1:-${TMPDIR:-/tmp}/b200q_emu}
+python "$HERE/build_emu.py" "$OUT" > /dev/null
+cd "$OUT/blaze_b200/csrc"
+pids=()
+for f in kernels.cu kernels_fast.cu stages.cu capi.cu plan_decode.cc arrow_ipc.cc compile.cc; do
+  g++ -std=c++20 -O1 -g -fPIC -pthread -w -x c++ -I"$HERE/include" -I. -c "$f" -o "${f%.*}.o" & pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+g++ -shared -pthread -o "$OUT/libblaze_b200_emu.so" kernels.o kernels_fast.o stages.o capi.o plan_decode.o arrow_ipc.o compile.o
+echo "$OUT/libblaze_b200_emu.so"

@@ -3,6 +3,10 @@
 // (dispatch forms, lane exchange, shared-memory tables, insert protocol) can be unit-tested without a GPU.
 // Test infrastructure only: nothing under blaze_b200/ includes this file; it is no CPU fallback of the product.
 #pragma once
+#include <math.h>
+#include <stdlib.h>
+#include <time.h>
+
 #include <atomic>
 #include <barrier>
 #include <cstdint>
@@ -71,10 +75,30 @@ inline long long clock64() { return 0; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+inline double __ull2double_rn(unsigned long long v) { return (double)v; }
+inline double __ll2double_rn(long long v) { return (double)v; }
+inline float __ll2float_rn(long long v) { return (float)v; }
+inline float __double2float_rn(double v) { return (float)v; }
+inline long long __double2ll_rz(double v) { return v != v ? 0 : v >= 9223372036854775807.0 ? INT64_MAX : v <= -9223372036854775808.0 ? INT64_MIN : (long long)v; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= emu_exchange(v, (unsigned)i); return r; }
+
 // ---- atomics (global and "shared" memory alike) ----
 template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T atomicCAS(T* p, T cmp, T val) { __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return cmp; }
 template <class T> inline T atomicMax(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
@@ -92,11 +116,40 @@ inline void emu_red_min_s64(unsigned long long* p, long long v) { atomicMin((lon
 inline void emu_red_max_s64(unsigned long long* p, long long v) { atomicMax((long long*)p, v); }
 inline unsigned emu_lanemask_lt() { return (1u << emu::lane) - 1u; }
 
-// ---- the few runtime calls the launchers make ----
+// ---- CUDA runtime API: the "device" is host memory, streams are synchronous ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16 };
+typedef struct emu_event_s { double t; }* cudaEvent_t;
+typedef void* cudaMemPool_t;
+enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaDevAttrMultiProcessorCount = 16, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
+       cudaMemPoolAttrReleaseThreshold = 4 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated device error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return cudaSuccess; }   // one "SM": small grids
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline double emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event_s{0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu_now_ms(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { if (n) memset(p, v, n); return cudaSuccess; }
 
 // ---- launch: one OS thread per CUDA thread, the blocks of the grid one after the other ----
 namespace emu {
