@@ -1,0 +1,22 @@
+"""The whole pipeline on an EMULATED device, without a GPU: tools/emu/build_lib.sh builds the library (C ABI, plan decode,
+stages, dispatch, every kernel) against a host stand-in for the CUDA runtime — one OS thread per CUDA thread — and
+tools/emu/run_gpu_suite.py runs `-m gpu` parity tests on it.  Here: the committed golden fixtures (VM filter/project
+with NULLs, Partial incl. the frozen Binary column, Final, the typed 2-key fused filter, f64/decimal128 aggregates).
+The full GPU suite can be run the same way (`python tools/emu/run_gpu_suite.py tests -m gpu -k "not large_batch and not murmur3"`,
+about an hour); it checks logic, never performance, and is no CPU path of the product."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
+def test_golden_fixtures_on_the_emulated_device(tmp_path):
+    env = dict(os.environ, B200Q_EMU_DIR=str(tmp_path / "emu"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu", "run_gpu_suite.py"), os.path.join(ROOT, "tests", "test_golden_fixtures.py"),
+                        "-m", "gpu", "-q", "-k", "not murmur3", "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1800, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
