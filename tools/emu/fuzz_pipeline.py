@@ -45,6 +45,7 @@ def main(seed, cases):
                                          pa.array(dec, type=pa.decimal128(17, 2), mask=(rng.random(n) < nf) if nf > 0 and n else None), nulls(f, pa.int64(), nf / 2)],
                                         names=["k", "k2", "v", "w", "x", "d", "f"])
         bs = int(rng.choice([1, 100, 1000, 10000]))
+        bs = max(bs, (n + 63) // 64)                                   # at most 64 pushes per case: every emulated launch spawns OS threads
         batches = H.split_batches(rb, max(1, min(bs, max(n, 1)))) if n else [rb]
         leaf = PL.MemoryExec.from_arrow(batches, rb.schema); ins = leaf.schema()
         preds = []
