@@ -191,6 +191,14 @@ static void validate_host_batch(b200q_op* op, const ArrowArray* batch) {
     if (!c) throw ExecError(B200Q_ERR_INVALID_ARG, "push: null child array");
     if (c->length + c->offset < batch->length + batch->offset) throw ExecError(B200Q_ERR_INVALID_ARG, "push: child array shorter than the struct");
     if (c->dictionary) throw ExecError(B200Q_ERR_UNSUPPORTED, "push: dictionary-encoded columns are not on the hot path");
+    // the import paths dereference buffers[1] (and buffers[2] of Binary columns): a malformed / foreign batch must not crash the host process
+    const DType& t = op->in_schema.fields[(size_t)i].type;
+    if (t.id == T_NULL || batch->length == 0) continue;
+    const int need = t.id == T_BINARY ? 3 : 2;
+    if (c->n_buffers < need || !c->buffers) throw ExecError(B200Q_ERR_INVALID_ARG, "push: column " + std::to_string(i) + " has " + std::to_string(c->n_buffers) + " buffers, its type needs " + std::to_string(need));
+    if (!c->buffers[1]) throw ExecError(B200Q_ERR_INVALID_ARG, "push: column " + std::to_string(i) + " has a null " + (t.id == T_BINARY ? "offsets" : "values") + " buffer");
+    if (t.id == T_BINARY && !c->buffers[2] && ((const int32_t*)c->buffers[1])[c->offset + batch->offset + batch->length] != ((const int32_t*)c->buffers[1])[c->offset + batch->offset])
+      throw ExecError(B200Q_ERR_INVALID_ARG, "push: binary column " + std::to_string(i) + " has a null data buffer");
   }
 }
 
@@ -578,11 +586,15 @@ b200q_status b200q_op_push_device(b200q_op* op, struct ArrowDeviceArray* dbatch)
       if (dc.type.id == T_BINARY) { dc.offsets = DevMem::borrow(c->buffers[1], huge, nullptr); dc.values = DevMem::borrow(c->buffers[2], huge, nullptr); }
       else if (c->n_buffers > 1 && c->buffers[1]) dc.values = DevMem::borrow(c->buffers[1], huge, nullptr);
     }
-    PendingRelease pr; pr.arr = *batch; batch->release = nullptr;
+    // queued BEFORE the stages run: if a stage throws, the array is still released (poll_pending) and the event destroyed;
+    // in both cases the event is recorded behind the last kernel that reads the caller's buffers.
+    PendingRelease pr; pr.arr = *batch;
     B200Q_CUDA(cudaEventCreateWithFlags(&pr.ev, cudaEventDisableTiming));
-    run_stages(op, db, 0);
-    B200Q_CUDA(cudaEventRecord(pr.ev, op->cx.stream));
+    batch->release = nullptr;
     op->pending.push_back(pr);
+    const cudaEvent_t ev = pr.ev;
+    try { run_stages(op, db, 0); } catch (...) { cudaEventRecord(ev, op->cx.stream); throw; }
+    B200Q_CUDA(cudaEventRecord(ev, op->cx.stream));
   });
   if (dbatch && dbatch->array.release) dbatch->array.release(&dbatch->array);
   return st;

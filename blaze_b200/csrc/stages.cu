@@ -357,7 +357,9 @@ class AggStage : public Stage {
         if (partial) { arg = agg_args[ai][0]; }
         else { arg = state_col_expr(state_columns_of(a).fields[0]); }
         const int o = add_out(arg);
-        const bool nullable_arg = can_be_null(arg);
+        // no-grouping aggregates always emit one (pre-seeded) row: with no valid input the accumulator stays NULL
+        // (AccPrimColumn valids stay false, agg_exec.rs:280-323), so it needs a validity bit even for never-NULL arguments
+        const bool nullable_arg = can_be_null(arg) || lay_.nkeys == 0;
         const uint8_t vbit = nullable_arg ? new_vbit() : (uint8_t)0xFF;
         AccKind kind; int nwords = 1; uint64_t ilo = 0, ihi = 0;
         if (a.fn == AGG_SUM || a.fn == AGG_AVG) {

@@ -144,9 +144,11 @@ def col_to_arrow(c: Col):
     at = T.to_arrow_type(c.dtype)
     mask = ~c.valid
     if c.dtype.id == T.DECIMAL128:
-        ctx = decimal.Context(prec=60)
-        py = [None if not ok else decimal.Decimal(int(v)).scaleb(-c.dtype.scale, ctx) for v, ok in zip(c.values, c.valid)]
-        return pa.array(py, type=at)
+        # raw 128-bit little-endian words, no precision validation: MakeDecimal / Decimal128Array::from(..)
+        # .with_precision_and_scale keep out-of-precision unscaled values as they are (spark_make_decimal.rs:24-58)
+        data = b"".join((int(v) if ok else 0).to_bytes(16, "little", signed=True) for v, ok in zip(c.values, c.valid))
+        bits = np.packbits(np.asarray(c.valid, dtype=np.uint8), bitorder="little").tobytes()
+        return pa.Array.from_buffers(at, len(c), [pa.py_buffer(bits), pa.py_buffer(data)], null_count=int(mask.sum()))
     if c.dtype.id == T.BINARY:
         return pa.array([None if not ok else bytes(v) for v, ok in zip(c.values, c.valid)], type=at)
     if c.dtype.id == T.NULLTYPE:

@@ -126,6 +126,35 @@ def test_no_grouping_and_empty_input():
     assert PL.collect(PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs, False, empty)) == []
 
 
+def test_no_grouping_over_non_nullable_arguments_yields_null_without_rows():
+    """execute_agg_no_grouping (agg_exec.rs:280-323) always emits one row; with no row reaching the accumulators
+    their valids stay false: SUM/MIN/MAX/AVG = NULL, COUNT = 0 — also when the argument column is declared non-null."""
+    n = 3000
+    rng = np.random.default_rng(77)
+    schema = pa.schema([pa.field("f", pa.int64(), nullable=False), pa.field("v", pa.int64(), nullable=False)])
+    rb = pa.RecordBatch.from_arrays([pa.array(rng.integers(0, 100, n, dtype=np.int64)), pa.array(rng.integers(-50, 50, n, dtype=np.int64))], schema=schema)
+    specs = [("s", E.AGG_SUM, T.int64), ("mn", E.AGG_MIN, T.int64), ("mx", E.AGG_MAX, T.int64), ("a", E.AGG_AVG, T.float64), ("c", E.AGG_COUNT, T.int64)]
+    for batches, preds in (([], []), (split_batches(rb, 1000), [E.BinaryExpr(E.Column("f"), "Lt", E.Literal(-1, T.int64))]),
+                           (split_batches(rb, 1000), [E.BinaryExpr(E.Column("f"), "Lt", E.Literal(50, T.int64))])):
+        leaf = PL.MemoryExec.from_arrow(batches, schema)
+        ins = leaf.schema()
+        mk = lambda mode, ch: [E.AggExpr(nm, mode, PL.create_agg(fn, ch(fn, rt), ins, rt)) for nm, fn, rt in specs]
+        child = PL.FilterExec(preds, leaf) if preds else leaf
+        partial = PL.AggExec(PL.HashAgg, [], mk(E.PARTIAL, lambda fn, rt: [E.Column("v")]), False, child)
+        final = PL.AggExec(PL.HashAgg, [], mk(E.FINAL, lambda fn, rt: [E.placeholder(rt)]), False, partial)
+        got_p = PL.collect(partial)
+        got = PL.collect(final)
+        ob = oracle_batches(batches)
+        op = O.AggExec(E.HASH_AGG, [], mk(E.PARTIAL, lambda fn, rt: [E.Column("v")]), False, ins)
+        of = O.AggExec(E.HASH_AGG, [], mk(E.FINAL, lambda fn, rt: [E.placeholder(rt)]), False, op.schema)
+        exp_p = op.execute(O.FilterExec(preds, ins).execute(ob) if preds else ob)
+        assert_multiset_equal(got_p, exp_p)                           # the frozen state bytes carry valid = 0
+        assert_multiset_equal(got, of.execute(exp_p), float_cols=(3,))
+        if not batches or preds[0].right.value == -1:
+            row = got[0].to_pylist()[0]
+            assert [row[k] for k in ("s", "mn", "mx", "a", "c")] == [None, None, None, None, 0]
+
+
 def test_f64_and_decimal_sums():
     import decimal
     n = 120_000

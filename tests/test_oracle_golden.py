@@ -132,3 +132,16 @@ def test_partial_skipping_passthrough_keeps_the_final_result():
         final = O.AggExec(E.HASH_AGG, g, mk(E.FINAL), False, partial.schema)
         outs[skipping] = O.rows_multiset(final.execute(mid))
     assert outs[False] == outs[True] and len(outs[True]) == 50000
+
+
+def test_cast_and_decimal_helper_kats():
+    """Every cast / Spark-decimal known-answer vector the reference's own unit tests hold for the hot path
+    (tests/kat_cases.py: arrow/cast.rs test_float_to_int / test_int_to_float / test_int_to_decimal, TryCastExpr
+    test_ok_1, spark_make_decimal test_decimal, spark_unscaled_value array + scalar, spark_check_overflow)."""
+    import kat_cases as K
+    for name, ref, inp, expr, exp in K.cases():
+        rb = pa.RecordBatch.from_arrays([inp], names=["x"])
+        b = O.batch_from_arrow(rb)
+        out = O.ProjectExec([(expr, "y")], b.schema, []).execute([b])
+        got = O.batch_to_arrow(O.concat_batches(O.ProjectExec([(expr, "y")], b.schema, []).schema, out)).column(0)
+        assert K.same_column(got, exp), f"{name} ({ref}): oracle gives {got.to_pylist()}, the reference test expects {exp.to_pylist()}"
