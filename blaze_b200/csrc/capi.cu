@@ -459,7 +459,7 @@ static void conf_defaults(b200q_conf* c) {
   c->partial_state_columnar = 0;
   c->force_generic_kernels = 0;
   c->agg_dense_keys = 1;
-  c->agg_hot_key_cache = 0;
+  c->agg_hot_key_cache = 1;                            // skew probe on the first batch -> CTA-private hot-key cache (validated on B200 in round 2)
 }
 
 }  // namespace b200q

@@ -72,15 +72,8 @@ __device__ __forceinline__ void smem_add64(unsigned* w, unsigned long long v) {
   if (hi + carry) atomicAdd(w + 1, hi + carry);
 }
 
-// dense entry index of a row; false: outside the dense range (the row goes to a hashed slot)
 template <int NK>
-__device__ __forceinline__ bool dense_index(const FastSpec& fs, long long k0, long long k1, unsigned long long& idx) {
-  const unsigned long long d0 = (unsigned long long)(k0 - fs.dense_base);
-  if (NK == 1) { idx = d0; return d0 < fs.dense_cap; }
-  const unsigned long long d1 = (unsigned long long)(k1 - fs.dense_base1);
-  idx = d0 * fs.dense_r1 + d1;
-  return d0 < fs.dense_cap0 && d1 < fs.dense_r1;
-}
+__device__ __forceinline__ bool dense_index(const FastSpec& fs, long long k0, long long k1, unsigned long long& idx) { return dense_index_of<NK>(fs, k0, k1, idx); }
 
 // ---------------------------------------------------------------------------------------------------
 // LEAN dense kernel: the hot loop of the M1 shape with everything resolved at compile time.
@@ -770,7 +763,11 @@ int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLa
 #undef B200Q_LD
     return 1;
   }
-  if (dg) {                                                     // filters / two keys / typed inputs: one row per lane
+  if (dg && fs.nfcol >= 0 && !fs.row_kernels) {                 // filters / two keys / typed inputs: 128-row tiles, 4 rows per lane (kernels_tile.cu)
+    if (fs.filt_never) return 0;
+    return launch_agg_tile_dense(cols, fs, lay, tab, row_begin, n, s);
+  }
+  if (dg) {                                                     // conjuncts that do not merge into intervals: one row per lane
     const int g = fast_grid((n + 32 * 8 * 4 - 1) / (32 * 8 * 4));
 #define B200Q_DR(NACC, NK, G) do { if (fs.lean) agg_dense_row_kernel<NACC, NK, G, false><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); \
                                    else agg_dense_row_kernel<NACC, NK, G, true><<<g, FA_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n); } while (0)

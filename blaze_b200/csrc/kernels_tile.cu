@@ -1,0 +1,245 @@
+// TILE form of the specialised HashAgg update kernels (round 2): the streaming front end of every shape that has
+// fused FilterExec conjuncts, typed (int8..int64) or nullable inputs, or two keys.
+//
+// Why: the one-row-per-lane kernels of kernels_fast.cu issue one 8-byte (or narrower) load per row per column plus one
+// validity-byte load per row, re-read a filter column once per conjunct, and run G shuffle + RED steps per 32 rows
+// whether or not the rows survived the filter (profiles/r02_ncu_baseline_*.txt: M2 0.44 of HBM peak, typed 0.12).
+// Here a warp owns a TILE of 128 consecutive rows and every lane 4 consecutive rows of it:
+//   * one vector load per column per lane (256-bit for int64, 128-bit for int32, 64/32-bit for int16/int8) and ONE
+//     validity nibble per column per lane (a 32-lane load covers 128 validity bits);
+//   * the conjuncts on one column are merged on the host into one closed interval [lo, hi] (FilterExec conjuncts are
+//     pre-split `col cmp literal` terms, NativeFilterBase.scala:66-87), tested with one subtract + one unsigned compare;
+//   * rows that survive are COMPACTED into a per-warp shared-memory queue (ballot + popc, no atomics), and the dense
+//     table is updated from the queue G lanes per entry: one RED instruction updates the G words of 32/G rows, so a
+//     selectivity of 0.2 costs 0.2 x the RED issue slots and sector operations instead of 1.0 x.
+// Semantics are those of agg_dense_row_kernel (same table, same entry layout, same fall-back of NULL / out-of-range
+// keys to the hashed slots, same deferred-row protocol), so the emit / grow / replay code is shared.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "agg_device.cuh"
+#include "kernels_fast.cuh"
+
+namespace b200q {
+
+constexpr int TL_BLOCK = 256, TL_WARPS = TL_BLOCK / 32, TL_ROWS = 128;
+
+__device__ __forceinline__ uint64_t tl_policy_evict_first() {
+  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ void tl_ld_v4b64(const long long* p, long long (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ long long tl_ld_b64(const long long* p, uint64_t pol) {
+  long long v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ void tl_ld_v4b32(const int* p, uint64_t pol, int (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void tl_ld_v2b32(const int* p, uint64_t pol, int (&v)[2]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(v[0]), "=r"(v[1]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ int tl_ld_b32(const int* p, uint64_t pol) {
+  int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+
+// 4 bits starting at bit `bi` of a bitmap; bits of rows >= nrow are not touched in memory
+__device__ __forceinline__ unsigned tl_nibble(const uint8_t* bits, unsigned long long bi, int nrow) {
+  const unsigned sh = (unsigned)bi & 7u;
+  unsigned w = __ldg(bits + (bi >> 3));
+  if (sh + (unsigned)nrow > 8u) w |= (unsigned)__ldg(bits + (bi >> 3) + 1) << 8;
+  return (w >> sh) & 0xFu;
+}
+
+// the 4 rows [row0, row0 + 4) of one column as sign-extended int64 + their validity bits; rows >= nrow read as 0 / invalid.
+// `want_values` = false: only the validity (COUNT(col) never looks at the values).
+__device__ __forceinline__ void tl_load4(const DevCol& c, int phys, long long row0, int nrow, bool want_values, uint64_t pol, long long (&v)[4], unsigned& valid) {
+  valid = (1u << nrow) - 1u;
+  if (c.validity && nrow > 0) valid &= tl_nibble(c.validity, (unsigned long long)row0 + c.bit_offset, nrow);
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[j] = 0;
+  if (!want_values || nrow <= 0) return;
+  switch (phys) {
+    case PH_I64: {
+      const long long* p = (const long long*)c.values + row0;
+      if (nrow == 4 && ((uintptr_t)p & 31) == 0) tl_ld_v4b64(p, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < nrow) v[j] = tl_ld_b64(p + j, pol);
+      }
+      break;
+    }
+    case PH_I32: {
+      const int* p = (const int*)c.values + row0;
+      if (nrow == 4 && ((uintptr_t)p & 15) == 0) { int t[4]; tl_ld_v4b32(p, pol, t); v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; v[3] = t[3]; }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < nrow) v[j] = tl_ld_b32(p + j, pol);
+      }
+      break;
+    }
+    case PH_I16: {
+      const int16_t* p = (const int16_t*)c.values + row0;
+      if (nrow == 4 && ((uintptr_t)p & 7) == 0) { int t[2]; tl_ld_v2b32((const int*)p, pol, t); v[0] = (int16_t)t[0]; v[1] = (int16_t)(t[0] >> 16); v[2] = (int16_t)t[1]; v[3] = (int16_t)(t[1] >> 16); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < nrow) v[j] = __ldg(p + j);
+      }
+      break;
+    }
+    case PH_I8: {
+      const int8_t* p = (const int8_t*)c.values + row0;
+      if (nrow == 4 && ((uintptr_t)p & 3) == 0) { const int t = tl_ld_b32((const int*)p, pol); v[0] = (int8_t)t; v[1] = (int8_t)(t >> 8); v[2] = (int8_t)(t >> 16); v[3] = (int8_t)(t >> 24); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < nrow) v[j] = __ldg(p + j);
+      }
+      break;
+    }
+    default: {                                                    // PH_BOOL: bit-packed values
+      const unsigned b = tl_nibble((const uint8_t*)c.values, (unsigned long long)row0 + c.bit_offset, nrow);
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = (b >> j) & 1u;
+      break;
+    }
+  }
+}
+
+enum { TW_ZERO = 0, TW_ONE, TW_ADD0, TW_ADD1, TW_VALID0, TW_VALID1 };     // what an entry word accumulates
+
+struct TileQueue {                                                  // per warp: the surviving rows of one tile
+  unsigned idx[TL_ROWS];                                            // dense entry index | argument-valid bits << 28
+  unsigned long long v0[TL_ROWS], v1[TL_ROWS];
+};
+
+template <int NK, int NACC, int G, int NF>
+__global__ void __launch_bounds__(TL_BLOCK) agg_tile_dense_kernel(const ColTable cols, const FastSpec fs, const AggLayout lay, const AggTable tab,
+                                                                  long long row_begin, long long n) {
+  constexpr unsigned IDX_MASK = 0x0FFFFFFFu;                        // dense_cap <= 2^26
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ TileQueue queues[TL_WARPS];
+  TileQueue& q = queues[threadIdx.x >> 5];
+  const unsigned lane = threadIdx.x & 31, qw = lane & (G - 1);
+  const long long gwarp = (long long)blockIdx.x * TL_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * TL_WARPS;
+  const long long ntiles = (n + TL_ROWS - 1) / TL_ROWS;
+  const bool add0 = fs.acc[0].kind == FAST_ACC_ADD, add1 = NACC == 2 && fs.acc[1].kind == FAST_ACC_ADD;
+  int wkind;                                                        // this lane's entry word
+  {
+    const int src = fs.dense_word_src[qw];
+    if (src == -1) wkind = TW_ONE; else if (src == -2) wkind = TW_ZERO;
+    else if (src >= 2) wkind = src == 2 ? TW_VALID0 : TW_VALID1;
+    else if (src == 0) wkind = add0 ? TW_ADD0 : TW_VALID0;
+    else wkind = add1 ? TW_ADD1 : TW_VALID1;
+  }
+  unsigned long long* const sink = fs.sink + ((gwarp & (FAST_SINK_WARPS - 1)) << 2) + (lane & 3);
+  const uint64_t pol = tl_policy_evict_first();
+
+  for (long long tile = gwarp; tile < ntiles; tile += nwarps) {
+    const long long rel0 = tile * TL_ROWS + lane * 4, row0 = row_begin + rel0;
+    const int nrow = (int)(n - rel0 >= 4 ? 4 : (n - rel0 > 0 ? n - rel0 : 0));
+    // ---- loads: everything this tile needs is in flight before the first use
+    long long f[NF > 0 ? NF : 1][4]; unsigned fv[NF > 0 ? NF : 1];
+    long long k0[4], k1[4], a0[4], a1[4]; unsigned kv0, kv1 = 0xF, av0 = 0xF, av1 = 0xF;
+#pragma unroll
+    for (int c = 0; c < NF; c++) tl_load4(cols.col[fs.frange[c].col], fs.frange[c].phys, row0, nrow, true, pol, f[c], fv[c]);
+    tl_load4(cols.col[fs.key_col[0]], fs.key_phys[0], row0, nrow, true, pol, k0, kv0);
+    if (NK == 2) tl_load4(cols.col[fs.key_col[1]], fs.key_phys[1], row0, nrow, true, pol, k1, kv1);
+    else { k1[0] = k1[1] = k1[2] = k1[3] = 0; }
+    if (fs.acc[0].col >= 0) tl_load4(cols.col[fs.acc[0].col], fs.acc[0].phys, row0, nrow, add0, pol, a0, av0);
+    else { a0[0] = a0[1] = a0[2] = a0[3] = 0; }
+    if (NACC == 2 && fs.acc[1].col >= 0) tl_load4(cols.col[fs.acc[1].col], fs.acc[1].phys, row0, nrow, add1, pol, a1, av1);
+    else { a1[0] = a1[1] = a1[2] = a1[3] = 0; }
+    // ---- fused FilterExec conjuncts: NULL -> row dropped (cached_exprs_evaluator.rs:518-520)
+    unsigned alive = (1u << nrow) - 1u;
+#pragma unroll
+    for (int c = 0; c < NF; c++) {
+      unsigned pass = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) pass |= (unsigned)((unsigned long long)(f[c][j] - fs.frange[c].lo) <= fs.frange[c].span) << j;
+      alive &= pass & fv[c];
+    }
+    // ---- compaction of the surviving rows with an in-range, non-NULL key
+    const unsigned knull = (~kv0 | (NK == 2 ? ~kv1 : 0u)) & 0xFu;
+    int total = 0; unsigned fb = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      unsigned long long di;
+      const bool live = (alive >> j) & 1u;
+      const bool in = dense_index_of<NK>(fs, k0[j], k1[j], di) && live && !((knull >> j) & 1u);
+      fb |= (unsigned)(live && !in) << j;
+      const unsigned m = __ballot_sync(FULL, in);
+      if (in) {
+        const int at = total + __popc(m & lanemask_lt());
+        q.idx[at] = (unsigned)di | (((av0 >> j) & 1u) << 28) | (((av1 >> j) & 1u) << 29);
+        if (add0) q.v0[at] = ((av0 >> j) & 1u) ? (unsigned long long)a0[j] : 0ULL;
+        if (add1) q.v1[at] = ((av1 >> j) & 1u) ? (unsigned long long)a1[j] : 0ULL;
+      }
+      total += __popc(m);
+    }
+    __syncwarp();
+    // ---- the G lanes of a group update the G words of one queued row with ONE instruction (one sector operation)
+    for (int e0 = 0; e0 < total; e0 += 32 / G) {
+      const int e = e0 + (int)(lane / G);
+      const bool live = e < total;
+      const unsigned pk = live ? q.idx[e] : 0u;
+      unsigned long long val;
+      switch (wkind) {
+        case TW_ONE: val = 1; break;
+        case TW_ADD0: val = live ? q.v0[e] : 0ULL; break;
+        case TW_ADD1: val = live ? q.v1[e] : 0ULL; break;
+        case TW_VALID0: val = (pk >> 28) & 1u; break;
+        case TW_VALID1: val = (pk >> 29) & 1u; break;
+        default: val = 0; break;
+      }
+      red_add_u64(live ? fs.dense_tab + (uint64_t)(pk & IDX_MASK) * G + qw : sink, live ? val : 0ULL);
+    }
+    __syncwarp();                                                   // the queue is rewritten by the next tile
+    // ---- keys outside the dense range / NULL keys (rare): straight to the hashed slots
+    if (__any_sync(FULL, fb != 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        bool inserted = false;
+        if ((fb >> j) & 1u) {
+          const unsigned kn = ((~kv0 >> j) & 1u) | (NK == 2 ? (((~kv1 >> j) & 1u) << 1) : 0u);
+          uint64_t kw[2] = {(kn & 1u) ? 0ULL : (uint64_t)k0[j], (NK == 2 && !(kn & 2u)) ? (uint64_t)k1[j] : 0ULL};
+          unsigned fl = 0;
+          const uint64_t si = agg_find_or_insert(lay, tab, kw, kn, agg_hash2(kw[0], kw[1], kn), &fl, &inserted);
+          if (si == AGG_NO_SLOT) { const unsigned long long at = atomicAdd(tab.counters + 1, 1ULL); tab.deferred[at] = (uint32_t)(rel0 + j); }
+          else {
+            unsigned long long* const p = tab.accs + si * (uint64_t)lay.astride;
+            unsigned long long* const ke = tab.keys + si * (uint64_t)lay.kstride;
+            if ((av0 >> j) & 1u) { red_add_u64(p + fs.acc[0].word, add0 ? (unsigned long long)a0[j] : 1ULL); slot_mark(ke, fl, fs.acc[0].vbit); }
+            if (NACC == 2 && ((av1 >> j) & 1u)) { red_add_u64(p + fs.acc[1].word, add1 ? (unsigned long long)a1[j] : 1ULL); slot_mark(ke, fl, fs.acc[1].vbit); }
+          }
+        }
+        const unsigned bl = __ballot_sync(FULL, inserted);
+        if (lane == 0 && bl) atomicAdd(tab.counters, (unsigned long long)__popc(bl));
+      }
+    }
+  }
+}
+
+static int tile_grid(int64_t ntiles, int ctas_per_sm) {
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (ntiles + TL_WARPS - 1) / TL_WARPS, cap = (int64_t)sms * ctas_per_sm;      // persistent grid: a multiple of the SM count
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+int launch_agg_tile_dense(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int g = tile_grid((n + TL_ROWS - 1) / TL_ROWS, 4);
+  const int G = fs.dense_stride;
+#define B200Q_TD(NK, NACC, G_, NF) agg_tile_dense_kernel<NK, NACC, G_, NF><<<g, TL_BLOCK, 0, s>>>(cols, fs, lay, tab, row_begin, n)
+#define B200Q_TD_NF(NK, NACC, G_) do { if (fs.nfcol == 0) B200Q_TD(NK, NACC, G_, 0); else if (fs.nfcol == 1) B200Q_TD(NK, NACC, G_, 1); else B200Q_TD(NK, NACC, G_, 2); } while (0)
+#define B200Q_TD_G(NK, NACC) do { if (G == 2) B200Q_TD_NF(NK, NACC, 2); else B200Q_TD_NF(NK, NACC, 4); } while (0)
+  if (fs.nkeys == 1) { if (fs.nacc == 2) B200Q_TD_G(1, 2); else B200Q_TD_G(1, 1); }
+  else { if (fs.nacc == 2) B200Q_TD_G(2, 2); else B200Q_TD_G(2, 1); }
+#undef B200Q_TD_G
+#undef B200Q_TD_NF
+#undef B200Q_TD
+  return 1;
+}
+
+}  // namespace b200q

@@ -1,5 +1,6 @@
 // Stage implementations: FilterProjectStage and AggStage (see runtime.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -39,7 +40,16 @@ DevMemP DevMem::alloc(size_t bytes, cudaStream_t s, bool zero) {
   auto m = std::make_shared<DevMem>();
   m->bytes = bytes; m->stream = s; m->owned = true; m->stream_keep = stream_ref_lookup(s);
   if (bytes == 0) bytes = 16;
-  B200Q_CUDA(cudaMallocAsync(&m->ptr, bytes, s));
+  {
+    // HBM exhaustion is not a CUDA failure of the handle: the reference spills / skips under memory pressure
+    // (agg_table.rs:108-120,540-588); here the op reports UNSUPPORTED so the host re-runs the task on its CPU operators
+    const cudaError_t e = cudaMallocAsync(&m->ptr, bytes, s);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError(); m->ptr = nullptr; m->owned = false;
+      throw ExecError(B200Q_ERR_UNSUPPORTED, "out of HBM: a device allocation of " + std::to_string(bytes) + " bytes failed; this task must fall back to the host path");
+    }
+    B200Q_CUDA(e);
+  }
   if (zero) B200Q_CUDA(cudaMemsetAsync(m->ptr, 0, bytes, s));
   return m;
 }
@@ -511,6 +521,8 @@ class AggStage : public Stage {
       const int s = prog_col_slot(l->col_index); if (s < 0 || s > 127) return;
       fs.filt[f].col = (int8_t)s; fs.filt[f].phys = phys_of(l->type); fs.filt[f].op = (uint8_t)op; fs.filt[f].lit = (long long)r->lit_lo;
     }
+    merge_conjuncts(fs);
+    { const char* e = getenv("B200Q_ROW_KERNELS"); fs.row_kernels = e && *e == '1'; }
     sink_ = DevMem::alloc((size_t)FAST_SINK_WARPS * 32, cx.stream, true);
     fs.sink = (unsigned long long*)sink_->ptr;
     fs_ = fs; fast_ok_ = true;
@@ -525,6 +537,33 @@ class AggStage : public Stage {
       }
     }
     if (dense_possible_) dense_possible_ = dense_layout();
+  }
+
+  // FilterExec conjuncts arrive pre-split as `col cmp literal` terms (NativeFilterBase.scala:66-87): all terms on one
+  // column intersect to one closed interval [lo, lo + span], tested by the tile kernels with one subtract + one
+  // unsigned compare.  `!=` terms or more than two filter columns keep the per-conjunct kernels (nfcol = -1).
+  static void merge_conjuncts(FastSpec& fs) {
+    fs.nfcol = 0; fs.filt_never = 0;
+    long long lo[2] = {INT64_MIN, INT64_MIN}, hi[2] = {INT64_MAX, INT64_MAX}; bool never = false;
+    for (int f = 0; f < fs.nfilt; f++) {
+      int c = -1;
+      for (int i = 0; i < fs.nfcol; i++) if (fs.frange[i].col == fs.filt[f].col) c = i;
+      if (c < 0) { if (fs.nfcol == 2) { fs.nfcol = -1; return; } c = fs.nfcol++; fs.frange[c].col = fs.filt[f].col; fs.frange[c].phys = fs.filt[f].phys; }
+      const long long lit = fs.filt[f].lit;
+      switch (fs.filt[f].op) {
+        case CMP_EQ: lo[c] = std::max(lo[c], lit); hi[c] = std::min(hi[c], lit); break;
+        case CMP_LT: if (lit == INT64_MIN) never = true; else hi[c] = std::min(hi[c], lit - 1); break;
+        case CMP_LE: hi[c] = std::min(hi[c], lit); break;
+        case CMP_GT: if (lit == INT64_MAX) never = true; else lo[c] = std::max(lo[c], lit + 1); break;
+        case CMP_GE: lo[c] = std::max(lo[c], lit); break;
+        default: fs.nfcol = -1; return;                              // CMP_NE
+      }
+    }
+    for (int c = 0; c < fs.nfcol; c++) {
+      if (lo[c] > hi[c]) never = true;
+      fs.frange[c].lo = lo[c]; fs.frange[c].span = (unsigned long long)hi[c] - (unsigned long long)lo[c];
+    }
+    fs.filt_never = never ? 1 : 0;
   }
 
   // dense entry layout (2 or 4 words): [row counter unless a COUNT(*) accumulator doubles as the presence marker]
@@ -589,6 +628,7 @@ class AggStage : public Stage {
     fs_.dense_base1 = base[1]; fs_.dense_r1 = span[1];
     fs_.dense_cap = (uint64_t)entries;
     dense_layout();
+    if (cx.conf.agg_max_table_bytes > 0 && (unsigned __int128)fs_.dense_cap * fs_.dense_stride * 8 > (unsigned __int128)cx.conf.agg_max_table_bytes) return;   // over budget: stay hashed
     dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * fs_.dense_stride * 8, cx.stream, true);
     fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;
     fs_.dense = 1;
@@ -631,7 +671,16 @@ class AggStage : public Stage {
     return launch_agg_update((const VmProgram*)d_prog_->ptr, ct, lay_, t, begin, m, list, cx.stream);
   }
 
+  // A12: the GPU table never spills; when it would outgrow its HBM budget (b200q_conf.agg_max_table_bytes, or the
+  // device itself) the op returns B200Q_ERR_UNSUPPORTED and the host falls back
+  void check_table_budget(OpContext& cx, unsigned __int128 bytes, const char* what) const {
+    const int64_t budget = cx.conf.agg_max_table_bytes;
+    if (budget > 0 && bytes > (unsigned __int128)budget)
+      throw ExecError(B200Q_ERR_UNSUPPORTED, std::string("aggregate ") + what + " of " + std::to_string((unsigned long long)bytes) + " bytes exceeds the HBM budget (agg_max_table_bytes = " +
+                                                 std::to_string(budget) + "): the table cannot spill on the GPU, fall back to the host path (agg_table.rs:540-588)");
+  }
   void alloc_table(OpContext& cx, uint64_t cap, DevMemP& keys, DevMemP& accs, DevMemP& counters) {
+    check_table_budget(cx, (unsigned __int128)cap * (lay_.kstride + lay_.astride) * 8, "hash table");
     keys = DevMem::alloc((size_t)cap * lay_.kstride * 8, cx.stream, true);
     accs = DevMem::alloc((size_t)cap * lay_.astride * 8, cx.stream);       // initialised at insertion
     counters = DevMem::alloc(64, cx.stream, true);

@@ -55,7 +55,8 @@ class Conf(C.Structure):
                 ("partial_agg_skipping_enable", C.c_int32), ("partial_agg_skipping_ratio", C.c_double),
                 ("partial_agg_skipping_min_rows", C.c_int64), ("staging_rows", C.c_int64),
                 ("agg_initial_groups", C.c_int64), ("max_launch_rows", C.c_int64),
-                ("partial_state_columnar", C.c_int32), ("force_generic_kernels", C.c_int32), ("agg_dense_keys", C.c_int32), ("agg_hot_key_cache", C.c_int32)]
+                ("partial_state_columnar", C.c_int32), ("force_generic_kernels", C.c_int32), ("agg_dense_keys", C.c_int32), ("agg_hot_key_cache", C.c_int32),
+                ("agg_max_table_bytes", C.c_int64)]
 
 
 class Metrics(C.Structure):

@@ -132,9 +132,15 @@ typedef struct b200q_conf {
   int32_t force_generic_kernels;      /* 1: disable the specialised fast kernels (testing)        */
   int32_t agg_dense_keys;             /* 1 (default): single integer keys spanning a small range
                                          are direct-indexed (no probe); 0: always hash           */
-  int32_t agg_hot_key_cache;          /* EXPERIMENTAL (default 0): probe the first batch for key skew and, when a
+  int32_t agg_hot_key_cache;          /* 1 (default): probe the first batch for key skew and, when a
                                          few keys dominate, combine their updates in a CTA-private
-                                         shared-memory cache before the global table (DESIGN.md §6) */
+                                         shared-memory cache before the global table (DESIGN.md §3) */
+  int64_t agg_max_table_bytes;        /* HBM budget of one aggregate's group table (0 = whatever the
+                                         device can allocate).  The GPU table never spills: growing
+                                         past the budget, or a failed device allocation, returns
+                                         B200Q_ERR_UNSUPPORTED so the host falls back to its CPU
+                                         operators (replaces spill / partial skipping,
+                                         agg/agg_table.rs:108-120,540-588)                       */
 } b200q_conf;
 
 typedef struct b200q_metrics {

@@ -155,6 +155,28 @@ def test_no_grouping_over_non_nullable_arguments_yields_null_without_rows():
             assert [row[k] for k in ("s", "mn", "mx", "a", "c")] == [None, None, None, None, 0]
 
 
+def test_table_over_the_hbm_budget_is_unsupported_not_a_cuda_failure():
+    """A12 (agg_table.rs:108-120,540-588 is what the reference does under memory pressure): the GPU table cannot
+    spill, so outgrowing b200q_conf.agg_max_table_bytes is B200Q_ERR_UNSUPPORTED (host falls back, INTEGRATION.md §4);
+    the handle stays usable for teardown and the same plan runs when the budget allows it."""
+    n = 600_000
+    rng = np.random.default_rng(5)
+    k = rng.integers(0, 2**40, n, dtype=np.int64)                    # ~600k sparse groups: hashed table, must grow past 2^20 slots
+    rb = rb_from_cols(["k", "v"], [pa.array(k), pa.array(rng.integers(-9, 9, n, dtype=np.int64))])
+    batches = split_batches(rb, 100_000)
+    leaf = PL.MemoryExec.from_arrow(batches, rb.schema)
+    ins = leaf.schema()
+    aggs = [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], ins, T.int64))]
+    plan = PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))], aggs, False, leaf)
+    with pytest.raises(native.NativeError) as ei:
+        PL.collect(plan, native.default_conf(staging_rows=0, agg_initial_groups=1 << 10, agg_max_table_bytes=40 << 20))   # 2^20 slots x 24 B fit, 2^21 do not
+    assert ei.value.code == native.ERR_UNSUPPORTED and "HBM budget" in str(ei.value)
+    got = PL.collect(plan, native.default_conf(staging_rows=0, agg_initial_groups=1 << 10, agg_max_table_bytes=1 << 30))
+    exp = O.AggExec(E.HASH_AGG, [E.GroupingExpr("k", E.Column("k"))], aggs, False, ins).execute(oracle_batches(batches))
+    assert_multiset_equal(got, exp)
+    assert plan.last_metrics["table_grow_count"] >= 1
+
+
 def test_f64_and_decimal_sums():
     import decimal
     n = 120_000

@@ -85,8 +85,8 @@ nk, sz = float(1 << 20), 1.1
 ranks = torch.clamp(((u * (nk ** (1 - sz) - 1) + 1) ** (1 / (1 - sz))).floor().to(torch.int64), 1, 1 << 20) - 1
 kz = (ranks * 2654435761) % (1 << 20)
 del u, ranks
-run("M1 Zipf(1.1) keys, dense", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20), reps=1)
-run("M1 Zipf(1.1) keys, dense + hot-key cache (experimental)", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_hot_key_cache=1), reps=1)
+run("M1 Zipf(1.1) keys, dense, hot-key cache off", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_hot_key_cache=0), reps=1)
+run("M1 Zipf(1.1) keys, dense + hot-key cache", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_hot_key_cache=1), reps=1)
 run("M1 Zipf(1.1) keys, hash", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
 del kz
 run("M1 generic VM kernel", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)

@@ -120,7 +120,7 @@ inline unsigned emu_lanemask_lt() { return (1u << emu::lane) - 1u; }
 typedef int cudaError_t;
 typedef struct emu_event_s { double t; }* cudaEvent_t;
 typedef void* cudaMemPool_t;
-enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaDevAttrMultiProcessorCount = 16, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600, cudaDevAttrMultiProcessorCount = 16, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
        cudaMemPoolAttrReleaseThreshold = 4 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated device error"; }
