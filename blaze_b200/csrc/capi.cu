@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 
 #include "runtime.h"
@@ -24,7 +25,7 @@ static std::string format_of(const DType& t) {
     case T_BINARY: return "z"; default: return "n";
   }
 }
-static DType type_of_format(const char* f) {
+DType type_of_format(const char* f) {
   DType d; std::string s(f ? f : "");
   if (s == "b") d.id = T_BOOL; else if (s == "c") d.id = T_INT8; else if (s == "s") d.id = T_INT16; else if (s == "i") d.id = T_INT32;
   else if (s == "l") d.id = T_INT64; else if (s == "f") d.id = T_FLOAT32; else if (s == "g") d.id = T_FLOAT64; else if (s == "tdD") d.id = T_DATE32;
@@ -100,7 +101,7 @@ struct b200q_op {
 
 namespace b200q {
 
-static b200q_status fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+b200q_status fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 
 template <class F>
 static b200q_status guarded(b200q_op* op, F&& f) {
@@ -117,6 +118,7 @@ static b200q_status guarded(b200q_op* op, F&& f) {
     return fail(B200Q_ERR_CUDA, e.what());
   } catch (const std::exception& e) { return fail(B200Q_ERR_EXECUTION, e.what()); }
 }
+b200q_status guarded_call(const std::function<void()>& f) { return guarded(nullptr, f); }
 
 // ---- pipeline construction ----------------------------------------------------------------------------
 static std::vector<ExprP> identity_cols(const SchemaDef& s) {
@@ -419,7 +421,7 @@ static void export_host_slice(const HostBatch& hb, int64_t off, int64_t len, Arr
   out->n_children = (int64_t)hb.cols.size(); out->children = top->child_ptrs.data();
   out->release = release_array; out->private_data = top;
 }
-static void export_device(DevBatch& db, int device, ArrowDeviceArray* out) {
+void export_device(DevBatch& db, int device, ArrowDeviceArray* out) {
   auto* top = new ArrayPriv();
   memset(out, 0, sizeof(*out));
   ArrowArray& a = out->array;

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <deque>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -99,6 +100,12 @@ std::unique_ptr<Stage> make_filter_project_stage(OpContext& cx, const SchemaDef&
                                                  const std::vector<ExprP>& outs, const SchemaDef& out_schema);
 std::unique_ptr<Stage> make_agg_stage(OpContext& cx, const SchemaDef& in_schema, const std::vector<ExprP>& filters, const PlanNode& agg,
                                       const std::vector<ExprP>& group_exprs, const std::vector<std::vector<ExprP>>& agg_args);
+
+// helpers of the C ABI layer (capi.cu) shared with exchange.cu
+DType type_of_format(const char* arrow_format);
+void export_device(DevBatch& db, int device, ArrowDeviceArray* out);
+b200q_status fail(int code, const std::string& msg);
+b200q_status guarded_call(const std::function<void()>& f);        // exceptions -> status + b200q_last_error()
 
 // state columns of one aggregate in the columnar partial-state layout
 struct StateCols { std::vector<FieldDef> fields; };

@@ -244,7 +244,9 @@ __device__ __forceinline__ int vm_run(const VmInstr* __restrict__ code, const ui
       case VM_CAST_F_I: {
         FORR {
           const double d = as_f64(st[sp - 1][r]);
-          long long v = __double2ll_rz(d);           // truncates, saturates at i64, NaN -> 0 (== Rust `as i64`)
+          // Rust `as i64`: truncates, saturates, NaN -> 0 (arrow/cast.rs:442-470 test_float_to_int).  cvt.rzi.s64.f64 saturates
+          // too but maps NaN to 0x8000000000000000, so NaN is handled here (found by the reference KAT on hardware).
+          long long v = d != d ? 0LL : __double2ll_rz(d);
           if (in.a < 64) { const long long mx = (1LL << (in.a - 1)) - 1, mn = -(1LL << (in.a - 1)); v = v > mx ? mx : (v < mn ? mn : v); }
           st[sp - 1][r] = (uint64_t)v;
         }

@@ -70,7 +70,9 @@ class Metrics(C.Structure):
 SYMBOLS = ["b200q_version", "b200q_build_info", "b200q_last_error", "b200q_device_count", "b200q_conf_init",
            "b200q_plan_explain", "b200q_op_create", "b200q_op_input_schema", "b200q_op_output_schema", "b200q_op_push",
            "b200q_op_push_device", "b200q_op_finish", "b200q_op_pull", "b200q_op_pull_device", "b200q_op_sync",
-           "b200q_op_metrics", "b200q_op_destroy", "b200q_murmur3_partition"]
+           "b200q_op_metrics", "b200q_op_destroy", "b200q_murmur3_partition",
+           "b200q_exchange_unique_id", "b200q_exchange_create", "b200q_exchange_shuffle", "b200q_exchange_kernel_launches",
+           "b200q_exchange_destroy"]
 
 
 def _load():
@@ -97,6 +99,13 @@ def _load():
     lib.b200q_op_destroy.argtypes = [C.c_void_p]
     lib.b200q_op_destroy.restype = None
     lib.b200q_murmur3_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.b200q_exchange_unique_id.argtypes = [C.c_void_p]
+    lib.b200q_exchange_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.b200q_exchange_shuffle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.b200q_exchange_kernel_launches.argtypes = [C.c_void_p]
+    lib.b200q_exchange_kernel_launches.restype = C.c_int64
+    lib.b200q_exchange_destroy.argtypes = [C.c_void_p]
+    lib.b200q_exchange_destroy.restype = None
     return lib
 
 
@@ -280,3 +289,51 @@ class NativeOp:
 def release_device_array(d: ArrowDeviceArray):
     if d.array.release:
         C.CFUNCTYPE(None, C.c_void_p)(d.array.release)(C.addressof(d.array))
+
+
+def exchange_unique_id() -> bytes:
+    """rank 0: the 128-byte ncclUniqueId every rank passes to Exchange(...); distribute it over the host's control plane"""
+    buf = C.create_string_buffer(128)
+    check(lib.b200q_exchange_unique_id(buf))
+    return buf.raw
+
+
+class Exchange:
+    """b200q_exchange: murmur3(seed 42) pmod world repartitioning of device batches over NCCL (collective calls)."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self._h = C.c_void_p()
+        self.rank, self.world, self.device = rank, world, device
+        check(lib.b200q_exchange_create(unique_id, rank, world, device, C.byref(self._h)))
+
+    def shuffle(self, schema, dev_array: ArrowDeviceArray, n_key_cols: int) -> ArrowDeviceArray:
+        """schema: pyarrow.Schema of the columns; dev_array is consumed; returns the rows this rank owns (release_device_array when done)"""
+        s = ArrowSchema()
+        schema._export_to_c(C.addressof(s))
+        out = ArrowDeviceArray()
+        try:
+            check(lib.b200q_exchange_shuffle(self._h, C.addressof(s), C.addressof(dev_array), n_key_cols, C.addressof(out)))
+        finally:
+            import pyarrow as pa
+            pa.Schema._import_from_c(C.addressof(s))
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(lib.b200q_exchange_kernel_launches(self._h))
+
+    def close(self):
+        if self._h:
+            lib.b200q_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -220,6 +220,24 @@ b200q_status b200q_murmur3_partition(const struct ArrowSchema* key_schema,
                                      const struct ArrowDeviceArray* keys, int32_t num_partitions,
                                      uint32_t* out_pids_device, void* cuda_stream);
 
+/* ---- multi-GPU repartitioning (replaces the shuffle between the Partial and the Final AggExec) ----------------
+ * Reference: shuffle writer partitioning `evaluate_hashes` + `evaluate_partition_ids`
+ * (datafusion-ext-plans/src/shuffle/mod.rs:163-188) and the reduce side feeding `AggExec` Final
+ * (agg/agg_ctx.rs:276-301).  One process per GPU; rank r owns partition r of `world` partitions, so GPU partitions
+ * equal Spark reduce partitions when world = spark.sql.shuffle.partitions.  Transport: NCCL send/recv over NVLink,
+ * bound at run time (dlopen libnccl.so.2); the 128-byte id is an ncclUniqueId the host's control plane distributes. */
+typedef struct b200q_exchange b200q_exchange;
+b200q_status b200q_exchange_unique_id(uint8_t* out128);               /* rank 0 */
+b200q_status b200q_exchange_create(const uint8_t* unique_id128, int32_t rank, int32_t world, int32_t device,
+                                   b200q_exchange** out);                /* collective: every rank calls it */
+/* Collective.  `in`: struct-typed device array of fixed-width columns (e.g. the columnar partial states), its first
+ * n_key_cols children are the grouping keys; ownership moves to the library.  `out`: the rows whose
+ * pmod(murmur3(keys, seed 42), world) equals this rank, gathered from all ranks; caller releases. */
+b200q_status b200q_exchange_shuffle(b200q_exchange* ex, const struct ArrowSchema* schema,
+                                    struct ArrowDeviceArray* in, int32_t n_key_cols, struct ArrowDeviceArray* out);
+int64_t b200q_exchange_kernel_launches(const b200q_exchange* ex);
+void b200q_exchange_destroy(b200q_exchange* ex);
+
 #ifdef __cplusplus
 }
 #endif

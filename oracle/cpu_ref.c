@@ -270,3 +270,106 @@ int64_t cpu_ref_filter_project(const int64_t* a, const uint8_t* av, const int64_
   free(tasks); free(th);
   return total;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * M2 (TPC-DS q1 shape): FilterExec[f >= lo, f <= hi] -> AggExec SUM(v) GROUP BY k1, k2.
+ * Per 10,000-row batch, as the reference operators do it:
+ *   FilterExec: conjunct 1 over the batch -> mask; conjunct 2 evaluated on the selected rows only and scattered back
+ *   (filter_one_pred / evaluate_selection, cached_exprs_evaluator.rs:495-524); NULL -> false; then the columns the
+ *   parent needs (k1, k2, v — column pruning, column_pruning.rs:68-90) are compacted (filter_record_batch);
+ *   AggExec: two int64 keys row-encoded to 18 bytes (arrow-row), 8-lane hash groups, SUM accumulator (sum.rs:90-115).
+ * Then the same Partial per task -> bucket by key hash -> Final per partition structure as above.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct q1_task_s {
+  const int64_t *f, *k1, *k2, *v; int64_t lo, hi, begin, end; table_t t;
+  int nparts; uint32_t* bucket_off; uint32_t* bucket_idx; struct q1_task_s* all; int self; table_t fin;
+} q1_task_t;
+
+static void* q1_task_main(void* arg) {
+  q1_task_t* ta = (q1_task_t*)arg; table_t* t = &ta->t;
+  table_init(t);
+  uint8_t* mask = malloc(BATCH_SIZE); int32_t* sel = malloc(BATCH_SIZE * 4);
+  int64_t* c1 = malloc(BATCH_SIZE * 8); int64_t* c2 = malloc(BATCH_SIZE * 8); int64_t* cv = malloc(BATCH_SIZE * 8);
+  uint8_t* rows = malloc(BATCH_SIZE * 18); uint32_t* hashes = malloc(BATCH_SIZE * 4); uint32_t* recs = malloc(BATCH_SIZE * 4);
+  for (int64_t base = ta->begin; base < ta->end; base += BATCH_SIZE) {
+    const int n = (int)(ta->end - base < BATCH_SIZE ? ta->end - base : BATCH_SIZE);
+    for (int i = 0; i < n; i++) mask[i] = (uint8_t)(ta->f[base + i] >= ta->lo);                      /* conjunct 1 */
+    int ns = 0; for (int i = 0; i < n; i++) if (mask[i]) sel[ns++] = i;                               /* selection of conjunct 2 */
+    for (int s = 0; s < ns; s++) mask[sel[s]] = (uint8_t)(ta->f[base + sel[s]] <= ta->hi);            /* evaluate_selection + scatter */
+    int m = 0;
+    for (int i = 0; i < n; i++) if (mask[i]) c1[m++] = ta->k1[base + i];                              /* filter_record_batch, one pass per column */
+    m = 0; for (int i = 0; i < n; i++) if (mask[i]) c2[m++] = ta->k2[base + i];
+    m = 0; for (int i = 0; i < n; i++) if (mask[i]) cv[m++] = ta->v[base + i];
+    if (m == 0) continue;                                                                             /* empty batches are dropped (execution_context.rs:713-716) */
+    for (int i = 0; i < m; i++) { encode_key(c1[i], 1, rows + 18 * i); encode_key(c2[i], 1, rows + 18 * i + 9); hashes[i] = key_hash(rows + 18 * i, 18); }
+    table_reserve(t, (uint64_t)m);
+    for (int i = 0; i < m; i++) {
+      if (i + 4 < m) __builtin_prefetch(t->groups + (hashes[i + 4] & t->ngroups_mask) * 16, 1);
+      recs[i] = upsert_one(t, rows + 18 * i, 18, hashes[i]);
+    }
+    for (int i = 0; i < m; i++) {
+      const uint32_t r = recs[i];
+      if (t->sum_valid[r]) t->sums[r] = (int64_t)((uint64_t)t->sums[r] + (uint64_t)cv[i]); else { t->sums[r] = cv[i]; t->sum_valid[r] = 1; }
+    }
+  }
+  free(mask); free(sel); free(c1); free(c2); free(cv); free(rows); free(hashes); free(recs);
+  const int P = ta->nparts;
+  ta->bucket_off = calloc((size_t)P + 1, 4); ta->bucket_idx = malloc((t->nrec ? t->nrec : 1) * 4);
+  for (uint64_t r = 0; r < t->nrec; r++) { const uint8_t* k = t->keys + r * KEY_CELL; ta->bucket_off[1 + (key_hash(k + 1, k[0]) >> 3) % (uint32_t)P]++; }
+  for (int p = 0; p < P; p++) ta->bucket_off[p + 1] += ta->bucket_off[p];
+  uint32_t* cur = malloc((size_t)P * 4); memcpy(cur, ta->bucket_off, (size_t)P * 4);
+  for (uint64_t r = 0; r < t->nrec; r++) { const uint8_t* k = t->keys + r * KEY_CELL; ta->bucket_idx[cur[(key_hash(k + 1, k[0]) >> 3) % (uint32_t)P]++] = (uint32_t)r; }
+  free(cur);
+  return NULL;
+}
+
+static void* q1_final_main(void* arg) {
+  q1_task_t* me = (q1_task_t*)arg; table_t* fin = &me->fin;
+  table_init(fin);
+  for (int i = 0; i < me->nparts; i++) {
+    q1_task_t* src = &me->all[i]; table_t* p = &src->t;
+    const uint32_t lo = src->bucket_off[me->self], hi = src->bucket_off[me->self + 1];
+    table_reserve(fin, hi - lo);
+    for (uint32_t x = lo; x < hi; x++) {
+      const uint64_t r = src->bucket_idx[x];
+      const uint8_t* key = p->keys + r * KEY_CELL;
+      const uint32_t rec = upsert_one(fin, key + 1, key[0], key_hash(key + 1, key[0]));
+      if (p->sum_valid[r]) { if (fin->sum_valid[rec]) fin->sums[rec] = (int64_t)((uint64_t)fin->sums[rec] + (uint64_t)p->sums[r]); else { fin->sums[rec] = p->sums[r]; fin->sum_valid[rec] = 1; } }
+    }
+  }
+  return NULL;
+}
+
+/* returns the number of groups; outputs (capacity out_cap, or NULL to only time): k1, k2, sum per group */
+int64_t cpu_ref_q1_filter_agg(const int64_t* f, const int64_t* k1, const int64_t* k2, const int64_t* v, int64_t n, int64_t lo, int64_t hi, int nthreads,
+                              int64_t* out_k1, int64_t* out_k2, int64_t* out_sum, int64_t out_cap) {
+  if (nthreads < 1) nthreads = 1;
+  q1_task_t* tasks = calloc((size_t)nthreads, sizeof(q1_task_t));
+  pthread_t* th = calloc((size_t)nthreads, sizeof(pthread_t));
+  const int64_t per = ((n + nthreads - 1) / nthreads + BATCH_SIZE - 1) / BATCH_SIZE * BATCH_SIZE;
+  for (int i = 0; i < nthreads; i++) {
+    q1_task_t* t = &tasks[i];
+    t->f = f; t->k1 = k1; t->k2 = k2; t->v = v; t->lo = lo; t->hi = hi; t->nparts = nthreads; t->all = tasks; t->self = i;
+    t->begin = per * i < n ? per * i : n; t->end = per * (i + 1) < n ? per * (i + 1) : n;
+    if (nthreads == 1) q1_task_main(t); else pthread_create(&th[i], NULL, q1_task_main, t);
+  }
+  if (nthreads > 1) for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  for (int i = 0; i < nthreads; i++) { if (nthreads == 1) q1_final_main(&tasks[i]); else pthread_create(&th[i], NULL, q1_final_main, &tasks[i]); }
+  if (nthreads > 1) for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  int64_t g = 0;
+  for (int i = 0; i < nthreads; i++) g += (int64_t)tasks[i].fin.nrec;
+  if (out_k1 && g <= out_cap) {
+    int64_t o = 0;
+    for (int i = 0; i < nthreads; i++) {
+      table_t* fin = &tasks[i].fin;
+      for (uint64_t r = 0; r < fin->nrec; r++, o++) {
+        int valid; const uint8_t* key = fin->keys + r * KEY_CELL + 1;
+        out_k1[o] = decode_key(key, &valid); out_k2[o] = decode_key(key + 9, &valid); out_sum[o] = fin->sums[r];
+      }
+    }
+  }
+  for (int i = 0; i < nthreads; i++) { table_free(&tasks[i].t); table_free(&tasks[i].fin); free(tasks[i].bucket_off); free(tasks[i].bucket_idx); }
+  free(tasks); free(th);
+  return g;
+}

@@ -22,6 +22,8 @@ def _load():
     lib.cpu_ref_hashagg_sum_count.argtypes = [p, p, p, p, C.c_int64, C.c_int, p, p, p, p, p, C.c_int64]
     lib.cpu_ref_filter_project.restype = C.c_int64
     lib.cpu_ref_filter_project.argtypes = [p, p, p, p, C.c_int64, C.c_int64, C.c_int, p, p, p]
+    lib.cpu_ref_q1_filter_agg.restype = C.c_int64
+    lib.cpu_ref_q1_filter_agg.argtypes = [p, p, p, p, C.c_int64, C.c_int64, C.c_int64, C.c_int, p, p, p, C.c_int64]
     return lib
 
 
@@ -71,3 +73,26 @@ def filter_project(a, b, thr, a_valid=None, b_valid=None, nthreads=1):
     oa = np.empty(n, np.int64); oc = np.empty(n, np.int64); ocv = np.empty(n, np.uint8)
     m = lib().cpu_ref_filter_project(_ptr(a), _ptr(_bits(a_valid)), _ptr(b), _ptr(_bits(b_valid)), n, int(thr), nthreads, _ptr(oa), _ptr(oc), _ptr(ocv))
     return oa[:m], oc[:m], ocv[:m].astype(bool)
+
+
+def q1_filter_agg(f, k1, k2, v, lo, hi, nthreads=1, max_groups=None):
+    """Filter[lo <= f <= hi] -> SUM(v) GROUP BY k1, k2 -> dict(k1, k2, sum)"""
+    f, k1, k2, v = (np.ascontiguousarray(a, np.int64) for a in (f, k1, k2, v))
+    n = len(f)
+    cap = int(max_groups if max_groups is not None else n)
+    o1 = np.empty(cap, np.int64); o2 = np.empty(cap, np.int64); os_ = np.empty(cap, np.int64)
+    g = lib().cpu_ref_q1_filter_agg(_ptr(f), _ptr(k1), _ptr(k2), _ptr(v), n, int(lo), int(hi), nthreads, _ptr(o1), _ptr(o2), _ptr(os_), cap)
+    if g > cap:
+        raise ValueError(f"{g} groups exceed max_groups={cap}")
+    return dict(k1=o1[:g], k2=o2[:g], sum=os_[:g])
+
+
+def q1_time_only(f, k1, k2, v, lo, hi, nthreads):
+    return lib().cpu_ref_q1_filter_agg(_ptr(f), _ptr(k1), _ptr(k2), _ptr(v), len(f), int(lo), int(hi), nthreads, None, None, None, 0)
+
+
+def filter_project_time_only(a, b, thr, nthreads, scratch=None):
+    """M0 timing: outputs go to caller-provided (or fresh) scratch arrays"""
+    n = len(a)
+    oa, oc = scratch if scratch is not None else (np.empty(n, np.int64), np.empty(n, np.int64))
+    return lib().cpu_ref_filter_project(_ptr(a), None, _ptr(b), None, n, int(thr), nthreads, _ptr(oa), _ptr(oc), None)

@@ -46,3 +46,27 @@ def test_filter_project_port_matches_numpy_oracle(nthreads):
     out = O.concat_batches(pe.schema, pe.execute([bt.take(np.arange(i, min(i + 10000, n))) for i in range(0, n, 10000)]))
     assert np.array_equal(out.cols[0].values, oa) and np.array_equal(out.cols[1].valid, ocv)
     assert np.array_equal(out.cols[1].values[ocv], oc[ocv])
+
+
+@pytest.mark.parametrize("nthreads", [1, 3])
+@pytest.mark.parametrize("n", [0, 1, 35_000])
+def test_q1_filter_agg_port_matches_numpy_oracle(n, nthreads):
+    """M2 (q1 shape): Filter[f >= lo, f <= hi] -> SUM(v) GROUP BY k1, k2, Partial -> Final"""
+    rng = np.random.default_rng(8)
+    f = rng.integers(0, 1000, n, dtype=np.int64); k1 = rng.integers(0, 500, n, dtype=np.int64)
+    k2 = rng.integers(0, 8, n, dtype=np.int64); v = rng.integers(-10**6, 10**6, n, dtype=np.int64)
+    got = cpu_ref.q1_filter_agg(f, k1, k2, v, 200, 399, nthreads)
+    ins = T.Schema([T.Field(c, T.int64, False) for c in ("f", "k1", "k2", "v")])
+    ones = np.ones(n, bool)
+    b = O.Batch(ins, [O.Col(T.int64, a, ones) for a in (f, k1, k2, v)], n)
+    batches = [b.take(np.arange(i, min(i + 10000, n))) for i in range(0, n, 10000)]
+    preds = [E.BinaryExpr(E.Column("f"), "GtEq", E.Literal(200, T.int64)), E.BinaryExpr(E.Column("f"), "LtEq", E.Literal(399, T.int64))]
+    g = [E.GroupingExpr("k1", E.Column("k1")), E.GroupingExpr("k2", E.Column("k2"))]
+    part = O.AggExec(E.HASH_AGG, g, [E.AggExpr("s", E.PARTIAL, E.AggFunctionExpr(E.AGG_SUM, [E.Column("v")], T.int64))], False, ins)
+    fin = O.AggExec(E.HASH_AGG, g, [E.AggExpr("s", E.FINAL, E.AggFunctionExpr(E.AGG_SUM, [E.placeholder(T.int64)], T.int64))], False, part.schema)
+    exp = O.rows_multiset(fin.execute(part.execute(O.FilterExec(preds, ins).execute(batches))))
+    ms = {}
+    for i in range(len(got["k1"])):
+        key = (int(got["k1"][i]), int(got["k2"][i]), int(got["sum"][i]))
+        ms[key] = ms.get(key, 0) + 1
+    assert ms == exp

@@ -12,9 +12,11 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
+#define B200Q_EMULATED_DEVICE 1
 #define __global__
 #define __device__
 #define __host__
@@ -82,7 +84,7 @@ inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 inline double __ll2double_rn(long long v) { return (double)v; }
 inline float __ll2float_rn(long long v) { return (float)v; }
 inline float __double2float_rn(double v) { return (float)v; }
-inline long long __double2ll_rz(double v) { return v != v ? 0 : v >= 9223372036854775807.0 ? INT64_MAX : v <= -9223372036854775808.0 ? INT64_MIN : (long long)v; }
+inline long long __double2ll_rz(double v) { return v != v ? INT64_MIN /* cvt.rzi.s64.f64 maps NaN to 0x8000000000000000 (seen on B200) */ : v >= 9223372036854775807.0 ? INT64_MAX : v <= -9223372036854775808.0 ? INT64_MIN : (long long)v; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
@@ -170,6 +172,8 @@ template <class F> void launch(unsigned grid, unsigned block_threads, F&& kernel
 struct Launcher {
   unsigned grid, block;
   Launcher(long long g, long long b, long long /*smem*/ = 0, cudaStream_t /*stream*/ = nullptr) : grid((unsigned)g), block((unsigned)b) {}
-  template <class F> void run(F&& body) { launch(grid, block, body); }
+  // `__shared__` variables are function-local statics here: launches from different host threads (ranks-as-threads tests) are serialised
+  template <class F> void run(F&& body) { std::lock_guard<std::mutex> l(launch_mutex()); launch(grid, block, body); }
+  static std::mutex& launch_mutex() { static std::mutex m; return m; }
 };
 }  // namespace emu
