@@ -230,6 +230,10 @@ class NativeOp:
     def push_device(self, batch: DeviceBatch):
         check(lib.b200q_op_push_device(self._h, C.addressof(batch.dev)))
 
+    def push_device_array(self, d: ArrowDeviceArray):
+        """an ArrowDeviceArray produced by the library itself (pull_device / Exchange.shuffle); ownership moves to the op"""
+        check(lib.b200q_op_push_device(self._h, C.addressof(d)))
+
     def finish(self):
         check(lib.b200q_op_finish(self._h))
 

