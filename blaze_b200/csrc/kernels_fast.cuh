@@ -43,6 +43,50 @@ __device__ __forceinline__ bool dense_index_of(const FastSpec& fs, long long k0,
   return d0 < fs.dense_cap0 && d1 < fs.dense_r1;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// WIDE tile aggregates (kernels_tile.cu, round 2): the accumulator kinds the specialised family did not cover — f64
+// SUM / AVG, decimal128 SUM / AVG, integer and f64 MIN / MAX, any mix of up to 4 of them over at most two argument
+// columns — on a DENSE table whose entry words all take the SAME RED flavour, so that one instruction still updates the
+// G (2, 4 or 8) words of 32 / G rows:
+//   TF_ADD_U64  SUM(int) | COUNT | decimal128 SUM kept carry-free as three words (low 32 bits, middle 32 bits, high 64
+//               bits: 64-bit wrapping adds of 32-bit pieces cannot lose a carry for 2^31 rows; the host normalises the
+//               pieces before that and before the emit)
+//   TF_ADD_F64  SUM(f64) | SUM(TryCast(int -> f64)) (= Spark AVG(long)) | COUNT kept as an exact f64 integer
+//   TF_MIN_S64  MIN(x) | MAX(x) kept as MIN(~x) | presence / valid-argument marks kept as MIN(0) (identity INT64_MAX);
+//               f64 values enter as IEEE totalOrder keys
+// NULL / out-of-range keys fall back to the hashed table with the generic accumulator updates of AggLayout.
+// ---------------------------------------------------------------------------------------------------
+enum TileFlavour : uint8_t { TF_ADD_U64 = 0, TF_ADD_F64 = 1, TF_MIN_S64 = 2 };
+enum TileArgCvt : uint8_t { TC_NONE = 0, TC_I2F = 1 /* integer -> f64 bits */, TC_ORDER = 2 /* f64 bits -> totalOrder key */ };
+enum TileRecon : uint8_t { TR_COPY = 0 /* slot word = dense word */, TR_NOT = 1 /* ~dense word (a maximum kept as the minimum of the complement) */,
+                           TR_F2I = 2 /* count kept as f64 */, TR_DEC3 = 3 /* three carry-free pieces -> {lo, hi} */ };
+struct TileWord {                                         // value a lane adds to its entry word: (((srcsel ? v1 : v0) >> sh) & msk) ^ inv, or cst; gated by a pk bit
+  uint8_t srcsel;                                         // 0: argument register v0, 1: v1, 2: the constant cst
+  uint8_t sh;                                             // 0 or 32
+  uint8_t gate;                                           // pk bit that must be set: 28 / 29 = argument 0 / 1 is not NULL, 30 = always
+  uint8_t _pad[5];
+  unsigned long long msk, inv, cst;
+};
+struct TileAggSpec {
+  int32_t nkeys, nargs, nfcol, filt_never, nacc, G, flavour, arg_is_dec;
+  int8_t key_col[2]; uint8_t key_phys[2];
+  int8_t arg_col[2]; uint8_t arg_phys[2]; uint8_t arg_cvt[2]; uint8_t arg_values[2];      // arg_values: 0 = only the validity is needed (COUNT(col))
+  struct { int8_t col; uint8_t phys; uint8_t _pad[6]; long long lo; unsigned long long span; } frange[2];
+  long long dense_base, dense_base1;
+  unsigned long long dense_cap, dense_r1, dense_cap0;
+  unsigned long long* dense_tab;
+  unsigned long long* sink;
+  unsigned long long dec_mul;                             // decimal argument: 10^(scale increase) of the TryCast below the SUM / AVG (Spark AVG(decimal(p,s)) accumulates at (p+4, s+4)); 1: none
+  TileWord word[8];
+  uint8_t presence_word, dec_word /* first of the three decimal pieces, 0xFF: none */, _pad2[6];
+  struct { int8_t arg; uint8_t recon; uint8_t w0; uint8_t valid_word; uint8_t lay_acc; uint8_t _pad[3]; } acc[4];
+};
+int launch_agg_tile_wide(const ColTable& cols, const TileAggSpec& ts, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
+int launch_tile_wide_init(const TileAggSpec& ts, cudaStream_t s);                       // identities of the dense entries
+int launch_tile_wide_count(const TileAggSpec& ts, unsigned long long* d_out, cudaStream_t s);
+int launch_tile_wide_normalise(const TileAggSpec& ts, cudaStream_t s);                  // carry the decimal pieces (no-op without a decimal SUM)
+int launch_tile_wide_emit(const TileAggSpec& ts, const AggLayout& lay, const EmitTable& emit, unsigned long long* d_out_count, cudaStream_t s);
+
 int launch_agg_tile_dense(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
 int launch_agg_fast_update(const ColTable& cols, const FastSpec& fs, const AggLayout& lay, const AggTable& tab, int64_t row_begin, int64_t n, cudaStream_t s);
 int launch_key_skew_probe(const DevCol* key_cols, const uint8_t* phys, int nkeys, int64_t n, unsigned* d_hist /* 65536 + 1 words, zeroed */, cudaStream_t s);

@@ -272,6 +272,10 @@ class AggStage : public Stage {
   FastSpec fs_{};
   DenseEmitMap dmap_{};
   DevMemP dense_tab_, sink_;
+  // wide tile aggregates (f64 / decimal / MIN / MAX accumulators over a dense table, kernels_tile.cu)
+  bool wide_possible_ = false;
+  TileAggSpec ws_{};
+  int64_t wide_rows_since_norm_ = 0;
 
   // emit plan (per output/state column)
   struct EmitSpec { EmitCol ec; FieldDef field; bool frozen_count = false; };
@@ -449,6 +453,7 @@ class AggStage : public Stage {
     B200Q_CUDA(cudaMemcpyAsync(d_prog_->ptr, &cp_.prog, sizeof(VmProgram), cudaMemcpyHostToDevice, cx.stream));
 
     detect_fast(cx);
+    if (!fast_ok_) detect_wide(cx);
 
     // ---- frozen-row descriptors of the state columns (non-final output in the reference format)
     if (!final_) {
@@ -566,6 +571,181 @@ class AggStage : public Stage {
     fs.filt_never = never ? 1 : 0;
   }
 
+  // ---- WIDE tile aggregates: everything the FAST_ACC_ADD / FAST_ACC_COUNT family does not cover --------------------
+  // 1-2 integer key columns, mergeable conjuncts, up to 4 accumulators of ONE RED flavour over at most two argument columns
+  // (a decimal128 argument takes both value registers).  Dense keys only (decided on the first batch like DENSE mode).
+  void detect_wide(OpContext& cx) {
+    wide_possible_ = false;
+    if (cx.conf.force_generic_kernels || !cx.conf.agg_dense_keys) return;
+    if (lay_.nkeys < 1 || lay_.nkeys > 2 || lay_.nacc < 1 || lay_.nacc > 4 || filters_.size() > 4) return;
+    TileAggSpec ts{};
+    ts.nkeys = lay_.nkeys; ts.nacc = lay_.nacc; ts.dec_word = 0xFF;
+    for (int k = 0; k < lay_.nkeys; k++) {
+      const ExprP& e = vm_outs_[lay_.key_out[k]];
+      if (e->kind != E_COLUMN || !int_phys(e->type) || lay_.key_nwords[k] != 1) return;
+      const int s = prog_col_slot(e->col_index); if (s < 0 || s > 127) return;
+      ts.key_col[k] = (int8_t)s; ts.key_phys[k] = phys_of(e->type);
+    }
+    {   // conjuncts -> intervals (shares merge_conjuncts with the FastSpec path)
+      FastSpec fs{}; fs.nfilt = (int)filters_.size();
+      for (size_t f = 0; f < filters_.size(); f++) {
+        const ExprP& p = filters_[f];
+        if (p->kind != E_BINARY || p->op < OP_EQ || p->op > OP_GE) return;
+        ExprP l = strip_noop_casts(p->children[0]), r = strip_noop_casts(p->children[1]);
+        int op = p->op - OP_EQ;
+        if (l->kind == E_LITERAL && r->kind == E_COLUMN) { std::swap(l, r); static const int flip[] = {CMP_EQ, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE}; op = flip[op]; }
+        if (l->kind != E_COLUMN || r->kind != E_LITERAL || r->lit_null || !int_phys(l->type) || !int_phys(r->type)) return;
+        const int s = prog_col_slot(l->col_index); if (s < 0 || s > 127) return;
+        fs.filt[f].col = (int8_t)s; fs.filt[f].phys = phys_of(l->type); fs.filt[f].op = (uint8_t)op; fs.filt[f].lit = (long long)r->lit_lo;
+      }
+      merge_conjuncts(fs);
+      if (fs.nfcol < 0) return;
+      ts.nfcol = fs.nfcol; ts.filt_never = fs.filt_never;
+      for (int c = 0; c < fs.nfcol; c++) { ts.frange[c].col = fs.frange[c].col; ts.frange[c].phys = fs.frange[c].phys; ts.frange[c].lo = fs.frange[c].lo; ts.frange[c].span = fs.frange[c].span; }
+    }
+    // flavour
+    bool any_f64 = false, any_min = false, any_int = false;
+    for (int j = 0; j < lay_.nacc; j++) {
+      switch (lay_.acc[j].kind) {
+        case ACC_ADD_F64: any_f64 = true; break;
+        case ACC_MIN_I64: case ACC_MAX_I64: case ACC_MIN_F64: case ACC_MAX_F64: any_min = true; break;
+        case ACC_ADD_I64: case ACC_ADD_DEC: any_int = true; break;
+        case ACC_COUNT: break;
+        default: return;                                               // 128-bit MIN / MAX stay on the generic kernel
+      }
+    }
+    if ((int)any_f64 + (int)any_min + (int)any_int > 1) return;
+    ts.flavour = any_f64 ? TF_ADD_F64 : any_min ? TF_MIN_S64 : TF_ADD_U64;
+    const unsigned long long ONE = ts.flavour == TF_ADD_F64 ? 0x3FF0000000000000ULL : ts.flavour == TF_MIN_S64 ? 0ULL : 1ULL;
+    const unsigned long long NOOP = ts.flavour == TF_MIN_S64 ? 0x7FFFFFFFFFFFFFFFULL : 0ULL;
+    // argument columns
+    struct ArgInfo { int col_index; int cvt; bool nullable; bool values; };
+    std::vector<ArgInfo> args; std::vector<ExprP> arg_cols;
+    unsigned long long dec_mul = 1; bool dec_mul_seen = false;
+    auto arg_of = [&](const ExprP& e0, int want_cvt, bool values, bool dec) -> int {
+      ExprP e = strip_noop_casts(e0); int cvt = TC_NONE;
+      const bool nullable = can_be_null(e0);
+      if ((e->kind == E_CAST || e->kind == E_TRY_CAST)) {
+        const ExprP& c = e->children[0];
+        if (c->kind == E_COLUMN && c->type.is_intlike() && e->type.id == T_FLOAT64) { cvt = TC_I2F; e = c; }                     // Rust `as f64` (arrow/cast.rs test_int_to_float)
+        else if (c->kind == E_COLUMN && c->type.is_decimal() && e->type.is_decimal() && e->type.scale >= c->type.scale && e->type.scale - c->type.scale <= 18 &&
+                 (int)e->type.precision - (int)c->type.precision >= (int)e->type.scale - (int)c->type.scale) {
+          // decimal -> decimal with at least as many extra digits as extra scale: an exact multiplication that cannot overflow
+          unsigned long long mul = 1; for (int i = c->type.scale; i < e->type.scale; i++) mul *= 10ULL;
+          if (dec_mul_seen && dec_mul != mul) return -1;
+          dec_mul = mul; dec_mul_seen = true; e = c;
+        }
+        else return -1;
+      }
+      if (e->kind != E_COLUMN) return -1;
+      if (!values) { for (size_t i = 0; i < args.size(); i++) if (args[i].col_index == e->col_index) { args[i].nullable = args[i].nullable || nullable; return (int)i; } }
+      if (values) {
+        if (dec) { if (!e->type.is_decimal()) return -1; }
+        else if (want_cvt == TC_ORDER) { if (e->type.id != T_FLOAT64 || cvt != TC_NONE) return -1; cvt = TC_ORDER; }
+        else if (ts.flavour == TF_ADD_F64) { if (!(e->type.id == T_FLOAT64 && cvt == TC_NONE) && cvt != TC_I2F) return -1; }
+        else if (!e->type.is_intlike() || cvt != TC_NONE) return -1;
+      }
+      for (size_t i = 0; i < args.size(); i++)
+        if (args[i].col_index == e->col_index && (!values || !args[i].values || args[i].cvt == cvt)) { args[i].nullable = args[i].nullable || nullable; if (values && !args[i].values) { args[i].values = true; args[i].cvt = cvt; } return (int)i; }
+      if (args.size() == 2) return -1;
+      args.push_back(ArgInfo{e->col_index, cvt, nullable, values}); arg_cols.push_back(e);
+      return (int)args.size() - 1;
+    };
+    int acc_arg[4] = {-1, -1, -1, -1};
+    for (int j = 0; j < lay_.nacc; j++) {
+      const AccOp& a = lay_.acc[j];
+      if (a.kind == ACC_COUNT) { if (a.nargs > 1) return; if (a.nargs == 1) { acc_arg[j] = arg_of(vm_outs_[a.arg_out[0]], TC_NONE, false, false); if (acc_arg[j] < 0) return; } continue; }
+      const bool dec = a.kind == ACC_ADD_DEC, order = a.kind == ACC_MIN_F64 || a.kind == ACC_MAX_F64;
+      acc_arg[j] = arg_of(vm_outs_[a.arg_out[0]], order ? TC_ORDER : TC_NONE, true, dec);
+      if (acc_arg[j] < 0) return;
+      if (dec) { if ((ts.arg_is_dec && acc_arg[j] != 0) || acc_arg[j] != 0) return; ts.arg_is_dec = 1; }
+    }
+    if (ts.arg_is_dec && args.size() > 1) return;                       // a decimal argument takes both value registers
+    ts.nargs = (int)args.size(); ts.dec_mul = dec_mul;
+    for (size_t i = 0; i < args.size(); i++) {
+      const int s = prog_col_slot(args[i].col_index); if (s < 0 || s > 127) return;
+      const DType& t = arg_cols[i]->type;
+      if (args[i].values && !ts.arg_is_dec && !(t.is_intlike() || t.id == T_FLOAT64)) return;
+      ts.arg_col[i] = (int8_t)s; ts.arg_phys[i] = t.id == T_FLOAT64 ? (uint8_t)PH_I64 : phys_of(t); ts.arg_cvt[i] = (uint8_t)args[i].cvt; ts.arg_values[i] = args[i].values ? 1 : 0;
+    }
+    // entry words: [presence] [valid-argument mark per nullable argument] [accumulator words]
+    int w = 0;
+    auto constant_word = [&](unsigned long long cst, int gate) { TileWord tw{}; tw.srcsel = 2; tw.gate = (uint8_t)gate; tw.cst = cst; return tw; };
+    ts.presence_word = 0; ts.word[w++] = constant_word(ONE, 30);
+    int valid_word[2] = {-1, -1};
+    for (size_t i = 0; i < args.size(); i++) if (args[i].nullable) { valid_word[i] = w; ts.word[w++] = constant_word(ONE, 28 + (int)i); }
+    for (int j = 0; j < lay_.nacc; j++) {
+      const AccOp& a = lay_.acc[j]; const int arg = acc_arg[j];
+      auto& out = ts.acc[j]; out.arg = (int8_t)arg; out.lay_acc = (uint8_t)j; out.valid_word = 0xFF; out.recon = TR_COPY;
+      if (a.kind == ACC_COUNT) {
+        if (ts.flavour == TF_MIN_S64) return;
+        out.w0 = (uint8_t)(arg >= 0 && valid_word[arg] >= 0 ? valid_word[arg] : 0);
+        out.recon = ts.flavour == TF_ADD_F64 ? TR_F2I : TR_COPY;
+        continue;
+      }
+      if (a.vbit != 0xFF) { if (valid_word[arg] < 0) return; out.valid_word = (uint8_t)valid_word[arg]; }
+      if (w + (a.kind == ACC_ADD_DEC ? 3 : 1) > 8) return;
+      out.w0 = (uint8_t)w;
+      TileWord tw{}; tw.srcsel = (uint8_t)arg; tw.gate = (uint8_t)(28 + arg); tw.msk = ~0ULL;
+      if (a.kind == ACC_ADD_DEC) {
+        ts.dec_word = (uint8_t)w; out.recon = TR_DEC3;
+        TileWord lo = tw; lo.srcsel = 0; lo.msk = 0xFFFFFFFFULL; ts.word[w++] = lo;
+        TileWord mid = lo; mid.sh = 32; ts.word[w++] = mid;
+        TileWord hi = tw; hi.srcsel = 1; ts.word[w++] = hi;
+      } else {
+        if (a.kind == ACC_MAX_I64 || a.kind == ACC_MAX_F64) { tw.inv = ~0ULL; out.recon = TR_NOT; }
+        ts.word[w++] = tw;
+      }
+    }
+    if (w > 8) return;
+    ts.G = w <= 2 ? 2 : w <= 4 ? 4 : 8;
+    for (; w < ts.G; w++) ts.word[w] = constant_word(NOOP, 30);
+    // every emit column must be something the hashed-slot view can produce (always true for these accumulator kinds)
+    sink_ = DevMem::alloc((size_t)FAST_SINK_WARPS * 32, cx.stream);
+    { std::vector<unsigned long long> fill((size_t)FAST_SINK_WARPS * 4, NOOP); B200Q_CUDA(cudaMemcpyAsync(sink_->ptr, fill.data(), fill.size() * 8, cudaMemcpyHostToDevice, cx.stream)); B200Q_CUDA(cudaStreamSynchronize(cx.stream)); }
+    ts.sink = (unsigned long long*)sink_->ptr;
+    ws_ = ts; wide_possible_ = true;
+  }
+
+  // padded value range of the key columns from a sample of the first batch; false: not dense
+  bool sample_key_ranges(OpContext& cx, const ColTable& ct, int64_t n, int nkeys, const int8_t* key_col, const uint8_t* key_phys, int entry_words,
+                         long long (&base)[2], uint64_t (&span)[2]) {
+    const int64_t sample = std::min<int64_t>(n, 1 << 22);
+    base[0] = base[1] = 0; span[0] = span[1] = 1; long long nonnull = 0;
+    for (int k = 0; k < nkeys; k++) {
+      DevMemP d = DevMem::alloc(24, cx.stream);
+      const long long init[3] = {INT64_MAX, INT64_MIN, 0};
+      B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 24, cudaMemcpyHostToDevice, cx.stream));
+      cx.m.launches += launch_key_range(ct.col[key_col[k]], key_phys[k], sample, (long long*)d->ptr, cx.stream);
+      long long h[3];
+      B200Q_CUDA(cudaMemcpyAsync(h, d->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      if (h[2] <= 0 || h[1] < h[0]) return false;
+      const unsigned __int128 range = (unsigned __int128)((__int128)h[1] - (__int128)h[0]) + 1;
+      if (range > ((uint64_t)1 << 26)) return false;
+      const uint64_t r = (uint64_t)range, margin = r / 8 + std::min<uint64_t>(64, r / 2 + 1);
+      base[k] = h[0] > INT64_MIN + (long long)margin ? h[0] - (long long)margin : INT64_MIN;
+      span[k] = r + 2 * margin;
+      nonnull = std::max(nonnull, h[2]);
+    }
+    const unsigned __int128 entries = (unsigned __int128)span[0] * span[1];
+    const uint64_t budget = 8 * (uint64_t)std::max<int64_t>(std::max<int64_t>(nonnull, cx.conf.agg_initial_groups), 1 << 16);
+    if (entries > budget || entries > ((uint64_t)1 << 26)) return false;               // sparse keys: stay on the hash table
+    if (cx.conf.agg_max_table_bytes > 0 && entries * entry_words * 8 > (unsigned __int128)cx.conf.agg_max_table_bytes) return false;
+    return true;
+  }
+
+  void decide_wide(OpContext& cx, const ColTable& ct, int64_t n) {
+    dense_decided_ = true;
+    if (!wide_possible_ || n == 0) { wide_possible_ = false; return; }
+    long long base[2]; uint64_t span[2];
+    if (!sample_key_ranges(cx, ct, n, ws_.nkeys, ws_.key_col, ws_.key_phys, ws_.G, base, span)) { wide_possible_ = false; return; }
+    ws_.dense_base = base[0]; ws_.dense_cap0 = span[0]; ws_.dense_base1 = base[1]; ws_.dense_r1 = span[1]; ws_.dense_cap = span[0] * span[1];
+    dense_tab_ = DevMem::alloc((size_t)ws_.dense_cap * ws_.G * 8, cx.stream);
+    ws_.dense_tab = (unsigned long long*)dense_tab_->ptr;
+    cx.m.launches += launch_tile_wide_init(ws_, cx.stream);
+  }
+
   // dense entry layout (2 or 4 words): [row counter unless a COUNT(*) accumulator doubles as the presence marker]
   // [accumulators] [one "valid arguments" counter per nullable SUM that has no COUNT over the same column beside it]
   bool dense_layout() {
@@ -662,6 +842,14 @@ class AggStage : public Stage {
 
   int launch_update(OpContext& cx, const ColTable& ct, const AggTable& t, int64_t begin, int64_t m, const uint32_t* list) {
     // deferred-row replays (arbitrary row lists, rare) always take the generic kernel: same table, same semantics
+    if (wide_possible_ && ws_.dense_tab && !list) {
+      cx.m.fast_launches++;
+      if (ws_.dec_word != 0xFF) {                                    // carry-free decimal pieces: normalise before 2^31 rows could have met in one entry
+        if (wide_rows_since_norm_ + m > (1LL << 31)) { cx.m.launches += launch_tile_wide_normalise(ws_, cx.stream); wide_rows_since_norm_ = 0; }
+        wide_rows_since_norm_ += m;
+      }
+      return launch_agg_tile_wide(ct, ws_, lay_, t, begin, m, cx.stream);
+    }
     if (fast_ok_ && !list) {
       cx.m.fast_launches++;
       FastSpec fs = fs_;
@@ -777,7 +965,7 @@ class AggStage : public Stage {
       const int c = cp_.used_cols[i];
       ct.col[i] = dev_col_of(c < n_in_ ? in.cols[c] : state_cols[c - n_in_]);
     }
-    if (!dense_decided_) decide_dense(cx, ct, n);
+    if (!dense_decided_) { if (wide_possible_) decide_wide(cx, ct, n); else decide_dense(cx, ct, n); }
     update_rows(cx, ct, n);
   }
 
@@ -818,6 +1006,17 @@ class AggStage : public Stage {
       g += (int64_t)hc;
       cx.m.num_groups = g;
     }
+    const bool wide = wide_possible_ && ws_.dense_tab;
+    if (wide) {
+      cx.m.launches += launch_tile_wide_normalise(ws_, cx.stream);
+      DevMemP dc = DevMem::alloc(8, cx.stream, true);
+      cx.m.launches += launch_tile_wide_count(ws_, (unsigned long long*)dc->ptr, cx.stream);
+      unsigned long long hc = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&hc, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      g += (int64_t)hc;
+      cx.m.num_groups = g;
+    }
     if (g == 0) return;                                             // no records (agg_table.rs:154-156)
     EmitTable et{}; et.ncols = (int)emit_.size();
     if (et.ncols > EMIT_MAX_COLS) throw ExecError(B200Q_ERR_UNSUPPORTED, "too many output columns");
@@ -835,6 +1034,7 @@ class AggStage : public Stage {
     DevMemP out_count = DevMem::alloc(8, cx.stream, true);
     cx.m.launches += launch_agg_emit(lay_, table_view(0), et, (unsigned long long*)out_count->ptr, cx.stream);
     if (fs_.dense) cx.m.launches += launch_agg_emit_dense(fs_, et, dmap_, (unsigned long long*)out_count->ptr, cx.stream);
+    if (wide) cx.m.launches += launch_tile_wide_emit(ws_, lay_, et, (unsigned long long*)out_count->ptr, cx.stream);
     for (size_t i = 0; i < emit_.size(); i++) {
       if (valid_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)valid_bytes[i]->ptr, (uint32_t*)ob.cols[i].validity->ptr, g, cx.stream);
       if (bool_bytes[i]) cx.m.launches += launch_pack_valid((const uint8_t*)bool_bytes[i]->ptr, (uint32_t*)ob.cols[i].values->ptr, g, cx.stream);
