@@ -89,6 +89,21 @@ run("M1 Zipf(1.1) keys, dense, hot-key cache off", m1.plan_bytes(), [kz, v], 16.
 run("M1 Zipf(1.1) keys, dense + hot-key cache", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_hot_key_cache=1), reps=1)
 run("M1 Zipf(1.1) keys, hash", m1.plan_bytes(), [kz, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, agg_dense_keys=0), reps=1, steady=True)
 del kz
+# the "fp64 SUM/AVG", "decimal128(17,2)" and MIN/MAX halves of the north_star target: wide tile kernels (kernels_tile.cu)
+vf = v.to(torch.float64)
+s1f = T.Schema([T.Field("k", T.int64, False), T.Field("v", T.float64, False)])
+mkp = lambda sch, specs: PL.AggExec(PL.HashAgg, [E.GroupingExpr("k", E.Column("k"))],
+                                    [E.AggExpr(nm, E.PARTIAL, PL.create_agg(fn, [E.Column("v")], sch, rt)) for nm, fn, rt in specs], True, PL.MemoryExec(sch))
+run("M1 f64 SUM+COUNT (wide tile)", mkp(s1f, [("s", E.AGG_SUM, T.float64), ("c", E.AGG_COUNT, T.int64)]).plan_bytes(), [k, vf], 16.0, native.default_conf(agg_initial_groups=1 << 20))
+run("M1 f64 AVG (wide tile)", mkp(s1f, [("a", E.AGG_AVG, T.float64)]).plan_bytes(), [k, vf], 16.0, native.default_conf(agg_initial_groups=1 << 20))
+run("M1 f64 SUM+COUNT generic VM", mkp(s1f, [("s", E.AGG_SUM, T.float64), ("c", E.AGG_COUNT, T.int64)]).plan_bytes(), [k, vf], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
+del vf
+run("M1 int64 MIN+MAX (wide tile)", mkp(s1, [("mn", E.AGG_MIN, T.int64), ("mx", E.AGG_MAX, T.int64)]).plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20))
+vd = torch.stack([v, v >> 63], dim=1).contiguous()          # decimal128(17,2): little-endian {lo, hi} pairs, sign-extended
+s1d = T.Schema([T.Field("k", T.int64, False), T.Field("v", T.decimal128(17, 2), False)])
+run("M1 decimal128(17,2) SUM+COUNT (wide tile)", mkp(s1d, [("s", E.AGG_SUM, T.decimal128(27, 2)), ("c", E.AGG_COUNT, T.int64)]).plan_bytes(), [k, vd], 24.0, native.default_conf(agg_initial_groups=1 << 20))
+run("M1 decimal128(17,2) SUM+COUNT generic VM", mkp(s1d, [("s", E.AGG_SUM, T.decimal128(27, 2)), ("c", E.AGG_COUNT, T.int64)]).plan_bytes(), [k, vd], 24.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
+del vd
 run("M1 generic VM kernel", m1.plan_bytes(), [k, v], 16.0, native.default_conf(agg_initial_groups=1 << 20, force_generic_kernels=1), reps=1)
 del k
 # M2: q1-shaped: f BETWEEN lo AND hi (s = 0.2), keys (k1 ~ U[0,2^17), k2 ~ U[0,8)), SUM(v)   (32 B/row)

@@ -11,6 +11,7 @@
 #include <tuple>
 #include <vector>
 
+#include "kernels_tile.cu"   // the tile form the dispatcher of kernels_fast.cu reaches (same translation)
 #include "kernels_fast.cu"   // translated copy produced by build_emu.py (inline PTX -> host helpers, <<<>>> -> emu::Launcher)
 
 using namespace b200q;
@@ -88,6 +89,9 @@ bool run(const Config& c, unsigned seed, bool via_dispatcher) {
   }
   if (c.nfilt >= 1) { fs.filt[0].col = 4; fs.filt[0].phys = c.typed ? PH_I8 : PH_I64; fs.filt[0].op = CMP_GE; fs.filt[0].lit = 2; }
   if (c.nfilt >= 2) { fs.filt[1].col = 4; fs.filt[1].phys = c.typed ? PH_I8 : PH_I64; fs.filt[1].op = CMP_NE; fs.filt[1].lit = 7; }
+  // merged per-column intervals, as stages.cu derives them: a `!=` term keeps the per-conjunct kernels (nfcol = -1)
+  fs.nfcol = c.nfilt >= 2 ? -1 : c.nfilt;
+  if (c.nfilt == 1) { fs.frange[0].col = 4; fs.frange[0].phys = fs.filt[0].phys; fs.frange[0].lo = 2; fs.frange[0].span = (unsigned long long)INT64_MAX - 2ull; }
   std::vector<unsigned long long> sink((size_t)FAST_SINK_WARPS * 4, 0); fs.sink = sink.data();
   // ---- hash table ----
   const uint64_t cap = 1 << 15;
@@ -216,8 +220,8 @@ int main(int argc, char** argv) {
   const long long TINY0 = 12, TINY1 = 3, MID0 = 700, MID1 = 6;
   for (int nk = 1; nk <= 2; nk++)
     for (int typed = 0; typed <= 1; typed++)
-      for (int nf = 0; nf <= 2; nf += 2) {
-        const std::string tag = std::string(nk == 1 ? "1key" : "2keys") + (typed ? " typed" : " lean") + (nf ? " filt" : "");
+      for (int nf = 0; nf <= 2; nf++) {
+        const std::string tag = std::string(nk == 1 ? "1key" : "2keys") + (typed ? " typed" : " lean") + (nf == 2 ? " filt" : nf == 1 ? " filt1" : "");
         cs.push_back({"hash   sum(v),count(v)        " + tag, nk, (bool)typed, {SUM_V, COUNT_V}, nf, 0, {}, typed ? 1LL << 30 : 1LL << 40, 9});     // typed keys are stored as int32
         cs.push_back({"hash   sum(v)                 " + tag, nk, (bool)typed, {SUM_V}, nf, 0, {}, 5000, 9});
         cs.push_back({"smem   {sum,count*}           " + tag, nk, (bool)typed, {SUM_V, COUNT_STAR}, nf, 1, {0, 1}, TINY0, TINY1});
