@@ -8,6 +8,7 @@
 #include <functional>
 #include <mutex>
 
+#include "lz4_frame.h"
 #include "runtime.h"
 
 namespace b200q {
@@ -158,6 +159,13 @@ static void build_pipeline(b200q_op* op) {
       op->stages.push_back(make_agg_stage(op->cx, stage_in, filters, *n, gex, aargs));
       stage_in = op->stages.back()->out_schema;
       cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+    } else if (n->kind == N_SHUFFLE_WRITER) {
+      if (i + 1 != chain.size()) throw PlanError(B200Q_ERR_UNSUPPORTED, "ShuffleWriterExec below another operator");
+      if (pending_tail) {                               // Filter / Project chain below the writer: its own fused stage
+        op->stages.push_back(make_filter_project_stage(op->cx, stage_in, filters, cur_cols, n->input->schema));
+        stage_in = op->stages.back()->out_schema; cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+      }
+      op->stages.push_back(make_shuffle_write_stage(op->cx, stage_in, *n));
     } else throw PlanError(B200Q_ERR_INVALID_PLAN, "leaf in the middle of the plan");
   }
   if (pending_tail) {
@@ -689,6 +697,33 @@ void b200q_op_destroy(b200q_op* op) {
   if (op->cx.ev1) cudaEventDestroy(op->cx.ev1);
   if (op->cx.stream) cudaStreamSynchronize(op->cx.stream);
   delete op;                     // the stream itself goes away with the last allocation that references it
+}
+
+b200q_status b200q_op_shuffle_chunk_count(b200q_op* op, int64_t* out_count) {
+  if (!op || !out_count) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+  return guarded(op, [&] {
+    const ShuffleResult* r = op->stages.empty() ? nullptr : dynamic_cast<const ShuffleResult*>(op->stages.back().get());
+    if (!r) throw ExecError(B200Q_ERR_STATE, "the plan is not rooted at a ShuffleWriterExecNode");
+    *out_count = r->chunk_count();
+  });
+}
+b200q_status b200q_op_shuffle_chunk(b200q_op* op, int64_t index, b200q_shuffle_chunk* out) {
+  if (!op || !out) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+  return guarded(op, [&] {
+    const ShuffleResult* r = op->stages.empty() ? nullptr : dynamic_cast<const ShuffleResult*>(op->stages.back().get());
+    if (!r) throw ExecError(B200Q_ERR_STATE, "the plan is not rooted at a ShuffleWriterExecNode");
+    if (index < 0 || index >= r->chunk_count()) throw ExecError(B200Q_ERR_INVALID_ARG, "shuffle chunk index out of range");
+    r->chunk(index, out);
+  });
+}
+b200q_status b200q_lz4_frame_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len) {
+  if ((!src && n) || !out_len) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+  return guarded(nullptr, [&] {
+    std::vector<uint8_t> v; lz4_frame_append(src, n, v);
+    *out_len = v.size();
+    if (!dst || cap < v.size()) throw ExecError(B200Q_ERR_INVALID_ARG, "lz4 frame needs " + std::to_string(v.size()) + " bytes");
+    memcpy(dst, v.data(), v.size());
+  });
 }
 
 b200q_status b200q_murmur3_partition(const struct ArrowSchema* key_schema, const struct ArrowDeviceArray* keys, int32_t num_partitions,

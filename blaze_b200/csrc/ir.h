@@ -95,7 +95,8 @@ struct AggDef {
   }
 };
 
-enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG };
+enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG, N_SHUFFLE_WRITER };
+enum ShuffleKind : uint8_t { SHUFFLE_SINGLE = 0, SHUFFLE_HASH = 1, SHUFFLE_ROUND_ROBIN = 2, SHUFFLE_RANGE = 3 };   // PhysicalRepartition oneof (auron.proto:629-655)
 
 struct PlanNode {
   NodeKind kind;
@@ -115,6 +116,11 @@ struct PlanNode {
   std::vector<AggDef> aggs;
   bool supports_partial_skipping = false;
   bool need_final_merge = false, need_partial_update = false, need_partial_merge = false;
+  // N_SHUFFLE_WRITER (ShuffleWriterExecNode, auron.proto:524-529)
+  ShuffleKind shuffle_kind = SHUFFLE_SINGLE;
+  uint64_t num_partitions = 1;
+  std::vector<ExprP> hash_exprs;
+  std::string data_file, index_file;
 };
 using PlanP = std::shared_ptr<PlanNode>;
 

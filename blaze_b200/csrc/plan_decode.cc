@@ -493,16 +493,52 @@ PlanP parse_agg(Reader r) {                  // AggExecNode (auron.proto:675-685
   return n;
 }
 
+// PhysicalRepartition (auron.proto:629-655) -> parse_protobuf_partitioning (auron-serde/src/from_proto.rs:1107-1187)
+void parse_repartition(Reader r, PlanNode& n, const SchemaDef& schema) {
+  bool have = false;
+  while (!r.done()) {
+    int wt; uint32_t f = r.tag(wt);
+    if (f < 1 || f > 4 || wt != 2) { r.skip(wt); continue; }
+    Reader b = r.bytes(); have = true;
+    n.shuffle_kind = (ShuffleKind)(f - 1); n.num_partitions = 0; n.hash_exprs.clear();
+    while (!b.done()) {
+      int w2; uint32_t g = b.tag(w2);
+      if (f == 1 || f == 3) { if (g == 1) n.num_partitions = b.varint(); else b.skip(w2); }                    // single / round robin: partition_count = 1
+      else if (f == 2) { if (g == 1) n.hash_exprs.push_back(parse_expr(b.bytes(), schema)); else if (g == 2) n.num_partitions = b.varint(); else b.skip(w2); }
+      else { if (g == 2) n.num_partitions = b.varint(); else b.skip(w2); }                                         // range: sort_expr = 1, partition_count = 2, list_value = 3
+    }
+    if (f == 1) n.num_partitions = 1;                                                                            // SinglePartitioning()
+    if (f == 4 && n.num_partitions == 1) n.shuffle_kind = SHUFFLE_SINGLE;                                        // from_proto.rs:1140-1141
+  }
+  if (!have) bad("partition::from_proto() Unsupported partition");
+}
+
+PlanP parse_shuffle_writer(Reader r) {       // ShuffleWriterExecNode{input=1, output_partitioning=2, output_data_file=3, output_index_file=4}
+  auto n = std::make_shared<PlanNode>(); n->kind = N_SHUFFLE_WRITER;
+  bool have_part = false; Reader part(nullptr, 0);
+  while (!r.done()) {
+    int wt; uint32_t f = r.tag(wt);
+    if (f == 1) n->input = parse_plan(r.bytes()); else if (f == 2) { part = r.bytes(); have_part = true; }
+    else if (f == 3) n->data_file = r.str(); else if (f == 4) n->index_file = r.str(); else r.skip(wt);
+  }
+  if (!n->input) bad("Missing required field in protobuf");
+  if (!have_part) bad("shuffle writer without output_partitioning");        // from_proto.rs:266-270 unwraps it
+  n->schema = n->input->schema;                                               // shuffle_writer_exec.rs:76-78
+  parse_repartition(part, *n, n->schema);
+  return n;
+}
+
 PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.proto:27-55)
   while (!r.done()) {
     int wt; uint32_t f = r.tag(wt);
     switch (f) {
+      case 2: return parse_shuffle_writer(r.bytes());
       case 6: return parse_projection(r.bytes());
       case 8: return parse_filter(r.bytes());
       case 15: return parse_leaf(r.bytes(), false);
       case 16: return parse_agg(r.bytes());
       case 18: return parse_leaf(r.bytes(), true);
-      case 1: case 2: case 3: case 4: case 5: case 7: case 9: case 10: case 11: case 12: case 13: case 14: case 17: case 19: case 20:
+      case 1: case 3: case 4: case 5: case 7: case 9: case 10: case 11: case 12: case 13: case 14: case 17: case 19: case 20:
       case 21: case 22: case 23: case 24: case 25:
         unsupported("plan node #" + std::to_string(f) + " is outside the Filter/Project/Agg hot path (SURVEY.md §8)");
       default: r.skip(wt);
@@ -571,6 +607,12 @@ static void explain_rec(const PlanP& p, int depth, std::ostringstream& o) {
         o << "):" << a.data_type.str() << "/" << md[a.mode] << " AS " << a.field_name;
       }
       o << "] partial_skipping=" << (p->supports_partial_skipping ? "true" : "false") << " schema=" << schema_str(p->schema) << "\n"; break;
+    }
+    case N_SHUFFLE_WRITER: {
+      static const char* kd[] = {"Single", "Hash", "RoundRobin", "Range"};
+      o << ind << "ShuffleWriterExec partitioning=" << kd[p->shuffle_kind] << "([";
+      for (size_t i = 0; i < p->hash_exprs.size(); i++) o << (i ? ", " : "") << explain_expr(p->hash_exprs[i]);
+      o << "], " << p->num_partitions << ") data=" << p->data_file << " index=" << p->index_file << " schema=" << schema_str(p->schema) << "\n"; break;
     }
   }
   if (p->input) explain_rec(p->input, depth + 1, o);

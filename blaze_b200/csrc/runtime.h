@@ -101,6 +101,14 @@ std::unique_ptr<Stage> make_filter_project_stage(OpContext& cx, const SchemaDef&
 std::unique_ptr<Stage> make_agg_stage(OpContext& cx, const SchemaDef& in_schema, const std::vector<ExprP>& filters, const PlanNode& agg,
                                       const std::vector<ExprP>& group_exprs, const std::vector<std::vector<ExprP>>& agg_args);
 
+// ShuffleWriterExec (shuffle_stage.cu): terminal stage; its result is the two shuffle files and/or the encoded chunks
+std::unique_ptr<Stage> make_shuffle_write_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);
+struct ShuffleResult {
+  virtual ~ShuffleResult() {}
+  virtual int64_t chunk_count() const = 0;
+  virtual void chunk(int64_t i, b200q_shuffle_chunk* out) const = 0;
+};
+
 // helpers of the C ABI layer (capi.cu) shared with exchange.cu
 DType type_of_format(const char* arrow_format);
 void export_device(DevBatch& db, int device, ArrowDeviceArray* out);

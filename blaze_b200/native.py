@@ -56,7 +56,12 @@ class Conf(C.Structure):
                 ("partial_agg_skipping_min_rows", C.c_int64), ("staging_rows", C.c_int64),
                 ("agg_initial_groups", C.c_int64), ("max_launch_rows", C.c_int64),
                 ("partial_state_columnar", C.c_int32), ("force_generic_kernels", C.c_int32), ("agg_dense_keys", C.c_int32), ("agg_hot_key_cache", C.c_int32),
-                ("agg_max_table_bytes", C.c_int64)]
+                ("agg_max_table_bytes", C.c_int64), ("shuffle_output_on_device", C.c_int32)]
+
+
+class ShuffleChunk(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("on_device", C.c_int32), ("num_partitions", C.c_int32), ("rows", C.c_int64),
+                ("part_off", C.POINTER(C.c_uint64)), ("part_rows", C.POINTER(C.c_uint64))]
 
 
 class Metrics(C.Structure):
@@ -71,6 +76,7 @@ SYMBOLS = ["b200q_version", "b200q_build_info", "b200q_last_error", "b200q_devic
            "b200q_plan_explain", "b200q_op_create", "b200q_op_input_schema", "b200q_op_output_schema", "b200q_op_push",
            "b200q_op_push_device", "b200q_op_finish", "b200q_op_pull", "b200q_op_pull_device", "b200q_op_sync",
            "b200q_op_metrics", "b200q_op_destroy", "b200q_murmur3_partition",
+           "b200q_op_shuffle_chunk_count", "b200q_op_shuffle_chunk", "b200q_lz4_frame_compress",
            "b200q_exchange_unique_id", "b200q_exchange_create", "b200q_exchange_shuffle", "b200q_exchange_kernel_launches",
            "b200q_exchange_destroy"]
 
@@ -99,6 +105,9 @@ def _load():
     lib.b200q_op_destroy.argtypes = [C.c_void_p]
     lib.b200q_op_destroy.restype = None
     lib.b200q_murmur3_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.b200q_op_shuffle_chunk_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.b200q_op_shuffle_chunk.argtypes = [C.c_void_p, C.c_int64, C.POINTER(ShuffleChunk)]
+    lib.b200q_lz4_frame_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.b200q_exchange_unique_id.argtypes = [C.c_void_p]
     lib.b200q_exchange_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
     lib.b200q_exchange_shuffle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -110,6 +119,15 @@ def _load():
 
 
 lib = _load()
+
+
+def lz4_frame_compress(data: bytes) -> bytes:
+    """the library's own LZ4 frame encoder (host only): the compression blocks of the shuffle files"""
+    need = C.c_size_t(0)
+    cap = len(data) + len(data) // 255 + 64
+    buf = C.create_string_buffer(cap)
+    check(lib.b200q_lz4_frame_compress(data, len(data), buf, cap, C.byref(need)))
+    return buf.raw[: need.value]
 
 
 def last_error() -> str:
@@ -265,6 +283,24 @@ class NativeOp:
         has = C.c_int32(0)
         check(lib.b200q_op_pull_device(self._h, C.addressof(d), C.byref(has)))
         return d if has.value else None
+
+    def shuffle_chunks(self) -> List[dict]:
+        """ShuffleWriterExec plans, after finish(): [{rows, part_off, part_rows, data (bytes, host) | data_ptr (device)}]"""
+        n = C.c_int64(0)
+        check(lib.b200q_op_shuffle_chunk_count(self._h, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            ch = ShuffleChunk()
+            check(lib.b200q_op_shuffle_chunk(self._h, i, C.byref(ch)))
+            P = ch.num_partitions
+            off = [int(ch.part_off[j]) for j in range(P + 1)]
+            d = {"rows": int(ch.rows), "part_off": off, "part_rows": [int(ch.part_rows[j]) for j in range(P)], "on_device": bool(ch.on_device)}
+            if ch.on_device:
+                d["data_ptr"] = int(ch.data or 0)
+            else:
+                d["data"] = C.string_at(ch.data, off[P]) if off[P] else b""
+            out.append(d)
+        return out
 
     def metrics(self) -> dict:
         m = Metrics()

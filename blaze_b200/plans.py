@@ -187,6 +187,40 @@ class AggExec(ExecutionPlan):
         return P.agg_node(self.input.node(), self.exec_mode, self.groupings, self.aggs, self.supports_partial_skipping)
 
 
+class ShuffleWriterExec(ExecutionPlan):
+    """ShuffleWriterExec::try_new(input, partitioning, output_data_file, output_index_file)
+    (datafusion-ext-plans/src/shuffle_writer_exec.rs:180-197).  partitioning: ("single",) | ("hash", [exprs], n) |
+    ("round_robin", n) — the reference's `Partitioning` enum (shuffle/mod.rs:108-132).  execute() yields nothing, like the
+    reference's stream; the result is the two files (and `last_chunks`, the per-partition bytes before compression)."""
+
+    def __init__(self, input: ExecutionPlan, partitioning, output_data_file: str, output_index_file: str):
+        self.input = input
+        self.partitioning = tuple(partitioning)
+        self.output_data_file, self.output_index_file = output_data_file, output_index_file
+        self._validate()
+
+    try_new = classmethod(lambda cls, input, partitioning, data_file, index_file: cls(input, partitioning, data_file, index_file))
+
+    def schema(self):
+        return self.input.schema()                                      # shuffle_writer_exec.rs:76-78
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        return P.shuffle_writer_node(self.input.node(), self.partitioning, self.output_data_file, self.output_index_file)
+
+    def execute(self, conf: Optional[native.Conf] = None, device: int = 0):
+        leaf = self.leaf()
+        with native.NativeOp(self.plan_bytes(), conf, device) as op:
+            for rb in leaf.batches:
+                op.push(rb)
+            op.finish()
+            self.last_chunks = op.shuffle_chunks()
+            self.last_metrics = op.metrics()
+        return iter(())
+
+
 def _agg_data_type(f: AggFunctionExpr, ins: Schema) -> T.DataType:
     if f.function == E.AGG_COUNT:
         return T.int64

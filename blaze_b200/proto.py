@@ -126,8 +126,17 @@ def _build_pool():
         ("agg_expr", 4, "PhysicalExprNode", R), ("mode", 5, "enum:AggMode", R), ("grouping_expr_name", 6, _F.TYPE_STRING, R),
         ("agg_expr_name", 7, _F.TYPE_STRING, R), ("initial_input_buffer_offset", 8, _F.TYPE_UINT64),
         ("supports_partial_skipping", 9, _F.TYPE_BOOL)])
+    _msg(fd, "PhysicalSingleRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
+    _msg(fd, "PhysicalHashRepartition", [("hash_expr", 1, "PhysicalExprNode", R), ("partition_count", 2, _F.TYPE_UINT64)])
+    _msg(fd, "PhysicalRoundRobinRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
+    _msg(fd, "PhysicalRepartition", [
+        ("single_repartition", 1, "PhysicalSingleRepartition", O), ("hash_repartition", 2, "PhysicalHashRepartition", O),
+        ("round_robin_repartition", 3, "PhysicalRoundRobinRepartition", O),
+    ], oneofs=["RepartitionType"])
+    _msg(fd, "ShuffleWriterExecNode", [("input", 1, "PhysicalPlanNode"), ("output_partitioning", 2, "PhysicalRepartition"),
+                                       ("output_data_file", 3, _F.TYPE_STRING), ("output_index_file", 4, _F.TYPE_STRING)])
     _msg(fd, "PhysicalPlanNode", [
-        ("projection", 6, "ProjectionExecNode", O), ("filter", 8, "FilterExecNode", O),
+        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O), ("filter", 8, "FilterExecNode", O),
         ("empty_partitions", 15, "EmptyPartitionsExecNode", O), ("agg", 16, "AggExecNode", O),
         ("ffi_reader", 18, "FFIReaderExecNode", O),
     ], oneofs=["PhysicalPlanType"])
@@ -325,6 +334,26 @@ def agg_node(input_node, exec_mode, groupings, aggs, supports_partial_skipping=F
         a.mode.append(ag.mode)
     a.initial_input_buffer_offset = initial_input_buffer_offset
     a.supports_partial_skipping = supports_partial_skipping
+    return n
+
+
+def shuffle_writer_node(input_node, partitioning, data_file: str, index_file: str):
+    """partitioning: ("single",) | ("hash", [exprs], n) | ("round_robin", n)  (PhysicalRepartition, auron.proto:629-649)"""
+    n = PhysicalPlanNode()
+    w = n.shuffle_writer
+    w.input.CopyFrom(input_node)
+    kind = partitioning[0]
+    if kind == "single":
+        w.output_partitioning.single_repartition.partition_count = 1
+    elif kind == "hash":
+        for e in partitioning[1]:
+            w.output_partitioning.hash_repartition.hash_expr.add().CopyFrom(expr_msg(e))
+        w.output_partitioning.hash_repartition.partition_count = partitioning[2]
+    elif kind == "round_robin":
+        w.output_partitioning.round_robin_repartition.partition_count = partitioning[1]
+    else:
+        raise ValueError(kind)
+    w.output_data_file, w.output_index_file = data_file, index_file
     return n
 
 

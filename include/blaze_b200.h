@@ -30,6 +30,14 @@
  *                           datafusion-ext-plans/src/common/execution_context.rs:569-598
  *   b200q_murmur3_partition evaluate_hashes + evaluate_partition_ids
  *                           datafusion-ext-plans/src/shuffle/mod.rs:163-188 (Spark murmur3 seed 42, pmod)
+ *   ShuffleWriterExecNode plans (b200q_op_create .. b200q_op_finish write <data_file> and <index_file>)
+ *                           ShuffleWriterExec::execute        datafusion-ext-plans/src/shuffle_writer_exec.rs:109-165
+ *                           SortShuffleRepartitioner          datafusion-ext-plans/src/shuffle/sort_repartitioner.rs:121-185
+ *                           BufferedData::write               datafusion-ext-plans/src/shuffle/buffered_data.rs:123-158
+ *                           write_batch (byte planes)         datafusion-ext-commons/src/io/batch_serde.rs:66-77,264-306
+ *                           IpcCompressionWriter              datafusion-ext-plans/src/common/ipc_compression.rs:34-112
+ *   b200q_op_shuffle_chunk  the per-partition encoded bytes before compression — what BufferedData::write_rss
+ *                           hands to an RSS partition writer (buffered_data.rs:160-196)
  *
  * Conventions: every call returns a status (0 = ok) and never unwinds; the message of the last
  * failure on the calling thread is available from b200q_last_error().  A CUDA error is sticky
@@ -141,6 +149,9 @@ typedef struct b200q_conf {
                                          B200Q_ERR_UNSUPPORTED so the host falls back to its CPU
                                          operators (replaces spill / partial skipping,
                                          agg/agg_table.rs:108-120,540-588)                       */
+  int32_t shuffle_output_on_device;   /* ShuffleWriterExec plans: 1 = keep the encoded partition bytes in HBM (no files are
+                                         written; read them with b200q_op_shuffle_chunk), 0 (default) = bring them to the
+                                         host and write <data_file>/<index_file> at finish                          */
 } b200q_conf;
 
 typedef struct b200q_metrics {
@@ -211,6 +222,28 @@ b200q_status b200q_op_sync(b200q_op* op);
 
 b200q_status b200q_op_metrics(b200q_op* op, b200q_metrics* out);
 void b200q_op_destroy(b200q_op* op);
+
+/* ---- ShuffleWriterExec result (plans rooted at ShuffleWriterExecNode) ----------------------------------------
+ * Every pushed batch becomes one CHUNK: the rows of the batch grouped by output partition
+ * (pmod(murmur3(hash exprs, 42), n), shuffle/mod.rs:163-188) and encoded as the reference's `batch_serde`
+ * records (batch_serde.rs:66-77; records of at most conf.batch_size rows).  Bytes [part_off[p], part_off[p+1]) of
+ * `data` are partition p's records of that chunk, UNcompressed.  b200q_op_finish frames them into
+ * `u32 length ‖ LZ4 frame` blocks and writes the .data / .index files (unless conf.shuffle_output_on_device).
+ * Pointers stay valid until b200q_op_destroy. */
+typedef struct b200q_shuffle_chunk {
+  const uint8_t* data;        /* host memory, or device memory when on_device = 1 */
+  int32_t on_device;
+  int32_t num_partitions;
+  int64_t rows;
+  const uint64_t* part_off;   /* host: num_partitions + 1 byte offsets into data */
+  const uint64_t* part_rows;  /* host: rows per partition */
+} b200q_shuffle_chunk;
+b200q_status b200q_op_shuffle_chunk_count(b200q_op* op, int64_t* out_count);
+b200q_status b200q_op_shuffle_chunk(b200q_op* op, int64_t index, b200q_shuffle_chunk* out);
+/* The library's LZ4 frame encoder (the compression blocks of the shuffle files; host only, no GPU needed):
+ * appends one frame holding src[0, n) to dst (capacity cap); *out_len = frame bytes, or the bytes needed when
+ * the call fails with B200Q_ERR_INVALID_ARG because cap is too small. */
+b200q_status b200q_lz4_frame_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len);
 
 /* Spark-compatible partition ids of device-resident key columns:
  * pid[i] = pmod(murmur3_x86_32 chained over the key columns (NULL leaves the hash unchanged), seed 42,

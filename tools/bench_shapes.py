@@ -116,3 +116,8 @@ m2 = PL.AggExec(PL.HashAgg, [E.GroupingExpr("k1", E.Column("k1")), E.GroupingExp
                 [E.AggExpr("s", E.PARTIAL, PL.create_agg(E.AGG_SUM, [E.Column("v")], s2, T.int64))], True, PL.FilterExec(preds, PL.MemoryExec(s2)))
 run("M2 q1-shaped fused filter->agg (2 keys)", m2.plan_bytes(), [f, k1, k2, v], 32.0, native.default_conf(agg_initial_groups=1 << 20))
 run("M2 q1-shaped", m2.plan_bytes(), [f, k1, k2, v], 32.0, native.default_conf(agg_initial_groups=1 << 20), reps=1, steady=True)
+# M3: ShuffleWriterExec 200-way hash partition + batch_serde encode (BASELINE configs[3] map side): 32 B/row read + 32 B/row of byte planes written
+m3 = PL.ShuffleWriterExec(PL.MemoryExec(s2), ("hash", [E.Column("k1")], 200), "", "")
+run("M3 shuffle write 200-way (4 int64 columns, hash on k1)", m3.plan_bytes(), [f, k1, k2, v], 64.0, native.default_conf(shuffle_output_on_device=1), reps=2)
+m3b = PL.ShuffleWriterExec(PL.MemoryExec(s2), ("hash", [E.Column("k1"), E.Column("k2")], 2000), "", "")
+run("M3 shuffle write 2000-way (hash on k1,k2)", m3b.plan_bytes(), [f, k1, k2, v], 64.0, native.default_conf(shuffle_output_on_device=1), reps=2)
