@@ -30,3 +30,14 @@ def test_multi_rank_exchange_on_the_emulated_device(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu", "run_gpu_suite.py"), os.path.join(ROOT, "tests", "test_gpu_exchange_threads.py"),
                         "-m", "gpu", "-q", "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1800, cwd=ROOT)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
+def test_shuffle_writer_on_the_emulated_device(tmp_path):
+    """ShuffleWriterExec (pids + layout + tile-sort scatter/encode kernels, LZ4 framing, .data/.index) without a GPU: a subset of
+    tests/test_gpu_shuffle_writer.py (the whole file passes the same way in ~4 min)."""
+    env = dict(os.environ, B200Q_EMU_DIR=str(tmp_path / "emu"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu", "run_gpu_suite.py"), os.path.join(ROOT, "tests", "test_gpu_shuffle_writer.py"),
+                        "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "chunks_can_stay or empty_input or outside_the_gpu_path or partial_aggregate"],
+                       capture_output=True, text=True, env=env, timeout=1800, cwd=ROOT)
+    assert r.returncode == 0 and "4 passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

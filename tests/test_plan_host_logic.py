@@ -94,3 +94,18 @@ def test_unsupported_is_reported_not_faked():
     with pytest.raises(native.NativeError) as ei:
         native.plan_explain(b"\x42\x05\x0a")          # FilterExecNode with a truncated length-delimited body
     assert ei.value.code == native.ERR_INVALID_PLAN
+
+
+def test_explain_shuffle_writer_and_partitionings():
+    """ShuffleWriterExecNode + PhysicalRepartition decode (auron.proto:524-529,629-655; from_proto.rs:263-277,1107-1187)"""
+    ins = T.Schema([T.Field("k", T.int64, False), T.Field("v", T.float64, True)])
+    leaf = PL.MemoryExec(ins)
+    h = PL.ShuffleWriterExec(PL.FilterExec([E.BinaryExpr(E.Column("k"), "Gt", E.Literal(3, T.int64))], leaf), ("hash", [E.Column("k")], 200), "/x/shuffle_0_0.data", "/x/shuffle_0_0.index")
+    text = h.explain()
+    assert "ShuffleWriterExec partitioning=Hash([k@0], 200) data=/x/shuffle_0_0.data index=/x/shuffle_0_0.index" in text and "FilterExec" in text
+    assert "partitioning=Single([], 1)" in PL.ShuffleWriterExec(leaf, ("single",), "a", "b").explain()
+    assert "partitioning=RoundRobin([], 9)" in PL.ShuffleWriterExec(leaf, ("round_robin", 9), "a", "b").explain()
+    assert h.schema() == leaf.schema()                       # shuffle_writer_exec.rs:76-78
+    with pytest.raises(native.NativeError) as ei:            # hash expressions resolve against the input schema (from_proto.rs:1122-1126)
+        PL.ShuffleWriterExec(leaf, ("hash", [E.Column("nope")], 4), "a", "b")
+    assert ei.value.code == native.ERR_INVALID_PLAN
