@@ -159,6 +159,18 @@ static void build_pipeline(b200q_op* op) {
       op->stages.push_back(make_agg_stage(op->cx, stage_in, filters, *n, gex, aargs));
       stage_in = op->stages.back()->out_schema;
       cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+    } else if (n->kind == N_JOIN_BUILD || n->kind == N_JOIN) {
+      if (pending_tail) {                               // Filter / Project chain below the join side: its own fused stage
+        op->stages.push_back(make_filter_project_stage(op->cx, stage_in, filters, cur_cols, n->input->schema));
+        stage_in = op->stages.back()->out_schema; cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+      }
+      if (n->kind == N_JOIN_BUILD) {
+        if (i + 1 != chain.size()) throw PlanError(B200Q_ERR_UNSUPPORTED, "BroadcastJoinBuildHashMapExec below another operator: build the map side with its own op and attach it (b200q_op_attach_build)");
+        op->stages.push_back(make_join_build_stage(op->cx, stage_in, *n));
+      } else {
+        op->stages.push_back(make_join_probe_stage(op->cx, stage_in, *n));
+        stage_in = op->stages.back()->out_schema; cur_cols = identity_cols(stage_in);
+      }
     } else if (n->kind == N_SHUFFLE_WRITER) {
       if (i + 1 != chain.size()) throw PlanError(B200Q_ERR_UNSUPPORTED, "ShuffleWriterExec below another operator");
       if (pending_tail) {                               // Filter / Project chain below the writer: its own fused stage
@@ -697,6 +709,19 @@ void b200q_op_destroy(b200q_op* op) {
   if (op->cx.ev1) cudaEventDestroy(op->cx.ev1);
   if (op->cx.stream) cudaStreamSynchronize(op->cx.stream);
   delete op;                     // the stream itself goes away with the last allocation that references it
+}
+
+b200q_status b200q_op_attach_build(b200q_op* probe_op, b200q_op* build_op) {
+  if (!probe_op || !build_op) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+  return guarded(probe_op, [&] {
+    const JoinBuildResult* b = build_op->stages.empty() ? nullptr : dynamic_cast<const JoinBuildResult*>(build_op->stages.back().get());
+    if (!b) throw ExecError(B200Q_ERR_STATE, "attach_build: the build op's plan is not rooted at a BroadcastJoinBuildHashMapExecNode");
+    if (!build_op->finished || !b->built()) throw ExecError(B200Q_ERR_STATE, "attach_build: finish the build op first");
+    JoinProbeAttach* a = nullptr;
+    for (auto& st : probe_op->stages) if (auto* j = dynamic_cast<JoinProbeAttach*>(st.get())) a = j;
+    if (!a) throw ExecError(B200Q_ERR_STATE, "attach_build: the probe op's plan has no join");
+    a->attach(b->built());
+  });
 }
 
 b200q_status b200q_op_shuffle_chunk_count(b200q_op* op, int64_t* out_count) {

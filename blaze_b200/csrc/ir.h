@@ -95,7 +95,7 @@ struct AggDef {
   }
 };
 
-enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG, N_SHUFFLE_WRITER };
+enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG, N_SHUFFLE_WRITER, N_JOIN_BUILD, N_JOIN };
 enum ShuffleKind : uint8_t { SHUFFLE_SINGLE = 0, SHUFFLE_HASH = 1, SHUFFLE_ROUND_ROBIN = 2, SHUFFLE_RANGE = 3 };   // PhysicalRepartition oneof (auron.proto:629-655)
 
 struct PlanNode {
@@ -121,6 +121,16 @@ struct PlanNode {
   uint64_t num_partitions = 1;
   std::vector<ExprP> hash_exprs;
   std::string data_file, index_file;
+  // N_JOIN_BUILD (BroadcastJoinBuildHashMapExecNode, auron.proto:450-453): keys resolved against the input schema
+  std::vector<ExprP> join_build_keys;
+  // N_JOIN (HashJoinExecNode / BroadcastJoinExecNode, auron.proto:441-463): `input` is the PROBED child, `join_build`
+  // the child whose rows are in the hash map (its subtree only supplies the schema: the map comes from a build op)
+  std::shared_ptr<PlanNode> join_build;
+  bool join_build_is_left = false;
+  int join_type = 0;                                                  // protobuf JoinType (auron.proto:475-483)
+  std::vector<std::pair<ExprP, ExprP>> join_on;                       // (left key, right key)
+  SchemaDef join_left_schema, join_right_schema;
+  std::string cached_build_hash_map_id;
 };
 using PlanP = std::shared_ptr<PlanNode>;
 

@@ -1,0 +1,233 @@
+// Hash join on the GPU: build + probe + gather kernels of JoinBuildStage / JoinProbeStage.
+//
+// Reference (paths relative to /root/reference/native-engine/datafusion-ext-plans/src/):
+//   Table::create_from_key_columns, lookup_many      joins/join_hash_map.rs:105-275
+//   FullJoiner::join / finish                        joins/bhj/full_join.rs:209-362
+//   SemiJoiner::join / finish                        joins/bhj/semi_join.rs:146-312
+// The reference sorts (hash, row) pairs on the host to group duplicates into `mapped_indices` ranges, then probes 8-lane
+// groups with software prefetch; every probe batch builds index vectors on one core and `take`s the columns.  Here the
+// table has one slot per distinct key (the keys themselves are stored, so there is no separate compare pass), the rows of
+// a key hang off the slot as a chain through `next[]` with their count in the slot, and a probe is: one lookup per row
+// that yields (chain head, match count) -> exclusive scan of the counts -> one pass that walks the chains and writes
+// (probe row, build row) pairs at their final positions -> one coalesced-write gather per output column.  The build side
+// (date_dim-sized) stays L2-resident; the probe side streams.  Row order is not a contract (assert_batches_sorted_eq!).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "kernels_join.cuh"
+
+namespace b200q {
+
+namespace {
+
+constexpr int JB = 256;
+
+int jgrid(int64_t n, int per_block = JB * 4) {
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + per_block - 1) / per_block, (int64_t)sms * 8));
+}
+
+__device__ __forceinline__ bool load_key(const JoinKeys& k, long long i, unsigned long long (&w)[2]) {
+  w[0] = w[1] = 0;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    if (c >= k.nkeys) break;
+    const DevCol col = k.col[c];
+    if (col.validity) { const unsigned long long bi = (unsigned long long)i + col.bit_offset; if (!((col.validity[bi >> 3] >> (bi & 7)) & 1)) return false; }
+    long long v;
+    switch (k.phys[c]) {
+      case PH_I8: v = ((const int8_t*)col.values)[i]; break;
+      case PH_I16: v = ((const int16_t*)col.values)[i]; break;
+      case PH_I32: v = ((const int32_t*)col.values)[i]; break;
+      default: v = ((const long long*)col.values)[i]; break;
+    }
+    w[c] = (unsigned long long)v;
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint32_t key_hash(const unsigned long long (&w)[2]) {
+  unsigned long long h = w[0] * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 32; h += w[1] * 0xC2B2AE3D27D4EB4Full; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  return (uint32_t)h;
+}
+
+// slot publication: keys are written, fenced, then the state becomes 2; readers fence after they have seen 2
+__device__ __forceinline__ uint32_t ld_state(const uint32_t* p) { const uint32_t v = *(const volatile uint32_t*)p; __threadfence(); return v; }
+__device__ __forceinline__ void st_state(uint32_t* p, uint32_t v) { __threadfence(); atomicExch(p, v); }
+
+__global__ void __launch_bounds__(JB) join_build_kernel(const JoinKeys k, long long n, const JoinTable t) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    unsigned long long w[2];
+    t.next[i] = JOIN_NIL;
+    if (!load_key(k, i, w)) continue;                                 // rows with a NULL key are not in the map (join_hash_map.rs:119-128)
+    uint32_t slot = key_hash(w) & t.mask;
+    while (true) {
+      uint32_t st = ld_state(t.state + slot);
+      if (st == 0) {
+        st = atomicCAS(t.state + slot, 0u, 1u);
+        if (st == 0) {
+          t.keys[(size_t)slot * t.nkw] = w[0];
+          if (t.nkw > 1) t.keys[(size_t)slot * t.nkw + 1] = w[1];
+          st_state(t.state + slot, 2u);
+          st = 2;
+        }
+      }
+      while (st == 1) st = ld_state(t.state + slot);                    // another lane is publishing this slot's key
+      const bool same = t.keys[(size_t)slot * t.nkw] == w[0] && (t.nkw == 1 || t.keys[(size_t)slot * t.nkw + 1] == w[1]);
+      if (same) {
+        t.next[i] = atomicExch(t.head + slot, (uint32_t)i);
+        atomicAdd(t.count + slot, 1u);
+        break;
+      }
+      slot = (slot + 1) & t.mask;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t find_slot(const JoinTable& t, const unsigned long long (&w)[2]) {
+  uint32_t slot = key_hash(w) & t.mask;
+  while (true) {
+    if (t.state[slot] == 0) return JOIN_NIL;                          // the table is read-only by now
+    if (t.keys[(size_t)slot * t.nkw] == w[0] && (t.nkw == 1 || t.keys[(size_t)slot * t.nkw + 1] == w[1])) return slot;
+    slot = (slot + 1) & t.mask;
+  }
+}
+
+__global__ void __launch_bounds__(JB) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    unsigned long long w[2];
+    uint32_t h = JOIN_NIL; int32_t c = 0;
+    if (load_key(k, i, w)) {                                           // a NULL in any key column never matches (full_join.rs:262-267)
+      const uint32_t slot = find_slot(t, w);
+      if (slot != JOIN_NIL) { h = t.head[slot]; c = (int32_t)t.count[slot]; }
+    }
+    head[i] = h;
+    if (count) count[i] = (probe_outer && c == 0) ? 1 : c;
+  }
+}
+
+__global__ void __launch_bounds__(JB) join_probe_emit_kernel(long long n, const JoinTable t, const uint32_t* __restrict__ head, const int32_t* __restrict__ offs,
+                                                             uint32_t* __restrict__ pidx, uint32_t* __restrict__ bidx, uint8_t* mark) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    long long o = offs[i];
+    const long long end = offs[i + 1];
+    uint32_t b = head[i];
+    if (b == JOIN_NIL) { if (o < end) { pidx[o] = (uint32_t)i; bidx[o] = JOIN_NIL; } continue; }      // unmatched outer row
+    for (; b != JOIN_NIL && o < end; b = t.next[b], o++) {
+      pidx[o] = (uint32_t)i; bidx[o] = b;
+      if (mark) mark[b] = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(JB) join_mark_build_kernel(long long n, const JoinTable t, const uint32_t* __restrict__ head, uint8_t* mark) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    uint32_t b = head[i];
+    if (b == JOIN_NIL || mark[b]) continue;                            // all rows of this key were marked together (semi_join.rs:214-226)
+    for (; b != JOIN_NIL; b = t.next[b]) mark[b] = 1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(JB) join_gather_kernel(const T* __restrict__ src, const uint8_t* __restrict__ vbits, uint32_t bit_offset, const uint8_t* __restrict__ vbytes,
+                                                         const uint32_t* __restrict__ idx, long long n, T* __restrict__ out, uint8_t* __restrict__ out_valid) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    const uint32_t j = idx[i];
+    T v{}; uint8_t ok = 0;
+    if (j != JOIN_NIL) {
+      ok = 1;
+      if (vbytes) ok = vbytes[j];
+      else if (vbits) { const unsigned long long bi = (unsigned long long)j + bit_offset; ok = (vbits[bi >> 3] >> (bi & 7)) & 1; }
+      if (ok) v = src[j];
+    }
+    out[i] = v;
+    if (out_valid) out_valid[i] = ok;
+  }
+}
+
+struct u128 { unsigned long long a, b; };
+
+__global__ void __launch_bounds__(JB) unpack_bits_kernel(const uint8_t* __restrict__ bits, uint32_t bit_offset, long long n, uint8_t* __restrict__ bytes) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    const unsigned long long bi = (unsigned long long)i + bit_offset;
+    bytes[i] = bits ? ((bits[bi >> 3] >> (bi & 7)) & 1) : 1;
+  }
+}
+
+__global__ void __launch_bounds__(JB) join_flags_kernel(const uint32_t* __restrict__ head, long long n, int invert, int32_t* __restrict__ flags) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) flags[i] = ((head[i] != JOIN_NIL) ? 1 : 0) ^ invert;
+}
+__global__ void __launch_bounds__(JB) join_match_bytes_kernel(const uint32_t* __restrict__ head, long long n, uint8_t* __restrict__ bytes) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) bytes[i] = head[i] != JOIN_NIL;
+}
+__global__ void __launch_bounds__(JB) bytes_to_flags_kernel(const uint8_t* __restrict__ bytes, long long n, int invert, int32_t* __restrict__ flags) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) flags[i] = (bytes[i] ? 1 : 0) ^ invert;
+}
+__global__ void __launch_bounds__(JB) compact_indices_kernel(const int32_t* __restrict__ flags, const int32_t* __restrict__ offs, long long n, uint32_t* __restrict__ idx) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) if (flags[i]) idx[offs[i]] = (uint32_t)i;
+}
+
+}  // namespace
+
+int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_build_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t);
+  return 1;
+}
+int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_count_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_head, d_count);
+  return 1;
+}
+int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head, const int32_t* d_offs, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_emit_kernel<<<jgrid(n), JB, 0, s>>>(n, t, d_head, d_offs, d_pidx, d_bidx, mark);
+  return 1;
+}
+int launch_join_mark_build(int64_t n, const JoinTable& t, const uint32_t* d_head, uint8_t* mark, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_mark_build_kernel<<<jgrid(n), JB, 0, s>>>(n, t, d_head, mark);
+  return 1;
+}
+int launch_join_gather(const void* src, const uint8_t* vbits, uint32_t bit_offset, const uint8_t* vbytes, int width, const uint32_t* idx, int64_t n, void* out, uint8_t* out_valid, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int g = jgrid(n);
+  switch (width) {
+    case 1: join_gather_kernel<uint8_t><<<g, JB, 0, s>>>((const uint8_t*)src, vbits, bit_offset, vbytes, idx, n, (uint8_t*)out, out_valid); break;
+    case 2: join_gather_kernel<uint16_t><<<g, JB, 0, s>>>((const uint16_t*)src, vbits, bit_offset, vbytes, idx, n, (uint16_t*)out, out_valid); break;
+    case 4: join_gather_kernel<uint32_t><<<g, JB, 0, s>>>((const uint32_t*)src, vbits, bit_offset, vbytes, idx, n, (uint32_t*)out, out_valid); break;
+    case 8: join_gather_kernel<unsigned long long><<<g, JB, 0, s>>>((const unsigned long long*)src, vbits, bit_offset, vbytes, idx, n, (unsigned long long*)out, out_valid); break;
+    default: join_gather_kernel<u128><<<g, JB, 0, s>>>((const u128*)src, vbits, bit_offset, vbytes, idx, n, (u128*)out, out_valid); break;
+  }
+  return 1;
+}
+int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s) {
+  if (n <= 0) return 0;
+  unpack_bits_kernel<<<jgrid(n), JB, 0, s>>>(bits, bit_offset, n, bytes);
+  return 1;
+}
+int launch_join_flags(const uint32_t* d_head, int64_t n, int invert, int32_t* d_flags, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_flags_kernel<<<jgrid(n), JB, 0, s>>>(d_head, n, invert, d_flags);
+  return 1;
+}
+int launch_join_match_bytes(const uint32_t* d_head, int64_t n, uint8_t* d_bytes, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_match_bytes_kernel<<<jgrid(n), JB, 0, s>>>(d_head, n, d_bytes);
+  return 1;
+}
+int launch_bytes_to_flags(const uint8_t* bytes, int64_t n, int invert, int32_t* d_flags, cudaStream_t s) {
+  if (n <= 0) return 0;
+  bytes_to_flags_kernel<<<jgrid(n), JB, 0, s>>>(bytes, n, invert, d_flags);
+  return 1;
+}
+int launch_join_compact_indices(const int32_t* d_flags, const int32_t* d_offs, int64_t n, uint32_t* d_idx, cudaStream_t s) {
+  if (n <= 0) return 0;
+  compact_indices_kernel<<<jgrid(n), JB, 0, s>>>(d_flags, d_offs, n, d_idx);
+  return 1;
+}
+
+}  // namespace b200q

@@ -109,6 +109,15 @@ __device__ __forceinline__ void or_bit(uint8_t* out, unsigned long long byte_off
 
 constexpr int ENC_NT = 512, ENC_RPT = SHUF_TILE / ENC_NT;
 
+// where sorted position `i` of the tile lands: byte offset of its record + its row inside the record; rows of that record
+__device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsigned long long F, unsigned B, unsigned p, unsigned idx, const unsigned long long* __restrict__ counts,
+                                                       const unsigned long long* __restrict__ part_off, unsigned& m, unsigned& j) {
+  const unsigned t = (unsigned)counts[p], rec = idx / B, nrec = (t + B - 1) / B;
+  j = idx - rec * B;
+  m = rec == nrec - 1 ? t - rec * B : B;
+  return part_off[p] + (unsigned long long)rec * F;
+}
+
 __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpec sp, const uint16_t* __restrict__ pids, long long n, const unsigned long long* __restrict__ counts,
                                                                    const unsigned long long* __restrict__ part_off, unsigned long long* cursors, uint8_t* out) {
 #ifdef B200Q_EMULATED_DEVICE                                                 // tools/emu: blocks run one at a time, shared memory is a static array
@@ -124,8 +133,9 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
   unsigned* s_start = s_cnt + P;                                            // P: exclusive prefix of s_cnt
   uint16_t* s_p = (uint16_t*)(s_start + P);                                 // SHUF_TILE: partition of every sorted position
   __shared__ unsigned s_warp[ENC_NT / 32];
-  const unsigned B = (unsigned)sp.batch_size;
+  const unsigned B = (unsigned)sp.batch_size, B8 = (B + 7) >> 3;
   const unsigned long long F = shuf_record_bytes(sp, B);
+  const uint32_t vlB = shuf_varint_len(B);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = (n + SHUF_TILE - 1) / SHUF_TILE;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -133,105 +143,121 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
     const int rows = (int)min((long long)SHUF_TILE, n - t0);
     for (int p = tid; p < P; p += ENC_NT) s_cnt[p] = 0;
     __syncthreads();
-    unsigned pid[ENC_RPT], lpos[ENC_RPT];
+    unsigned lpos[ENC_RPT];                                                 // rank inside (tile, partition), then position in the tile's partition order
+    {
+      unsigned pid[ENC_RPT];
 #pragma unroll
-    for (int k = 0; k < ENC_RPT; k++) {
-      const int i = k * ENC_NT + tid;
-      pid[k] = 0; lpos[k] = 0;
-      if (i < rows) { pid[k] = pids ? pids[t0 + i] : 0; lpos[k] = atomicAdd(&s_cnt[pid[k]], 1u); }       // rank inside (tile, partition)
-    }
-    __syncthreads();
-    {   // exclusive scan of s_cnt, one contiguous span of partitions per thread; reserve the tile's rows of every partition
-      const int per = (P + ENC_NT - 1) / ENC_NT, lo = min(P, tid * per), hi = min(P, lo + per);
-      unsigned sum = 0;
-      for (int p = lo; p < hi; p++) sum += s_cnt[p];
-      unsigned inc = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-      if (lane == 31) s_warp[warp] = inc;
+      for (int k = 0; k < ENC_RPT; k++) {
+        const int i = k * ENC_NT + tid;
+        pid[k] = 0; lpos[k] = 0;
+        if (i < rows) { pid[k] = pids ? pids[t0 + i] : 0; lpos[k] = atomicAdd(&s_cnt[pid[k]], 1u); }
+      }
       __syncthreads();
-      unsigned wbase = 0;
-      for (int w = 0; w < warp; w++) wbase += s_warp[w];
-      unsigned run = wbase + inc - sum;
-      for (int p = lo; p < hi; p++) {
-        const unsigned c = s_cnt[p];
-        s_start[p] = run; run += c;
-        if (c) s_gbase[p] = atomicAdd(cursors + p, (unsigned long long)c);
+      {   // exclusive scan of s_cnt, one contiguous span of partitions per thread; reserve the tile's rows of every partition
+        const int per = (P + ENC_NT - 1) / ENC_NT, lo = min(P, tid * per), hi = min(P, lo + per);
+        unsigned sum = 0;
+        for (int p = lo; p < hi; p++) sum += s_cnt[p];
+        unsigned inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_warp[w];
+        unsigned run = wbase + inc - sum;
+        for (int p = lo; p < hi; p++) {
+          const unsigned c = s_cnt[p];
+          s_start[p] = run; run += c;
+          if (c) s_gbase[p] = atomicAdd(cursors + p, (unsigned long long)c);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < ENC_RPT; k++) {
+        const int i = k * ENC_NT + tid;
+        if (i < rows) { lpos[k] += s_start[pid[k]]; s_p[lpos[k]] = (uint16_t)pid[k]; }
       }
     }
     __syncthreads();
+    // destination of the sorted positions this thread writes out: record base + row inside the record; bit k of `full`: the
+    // record holds batch_size rows (every record but a partition's last one) -> its plane stride and column offsets are constants
+    unsigned long long wb[ENC_RPT]; unsigned full = 0;
 #pragma unroll
     for (int k = 0; k < ENC_RPT; k++) {
       const int i = k * ENC_NT + tid;
-      if (i < rows) { lpos[k] += s_start[pid[k]]; s_p[lpos[k]] = (uint16_t)pid[k]; }
-    }
-    __syncthreads();
-    // destination of the sorted positions this thread writes out: record base + row inside the record, rows of that record
-    unsigned long long wb[ENC_RPT]; unsigned wm[ENC_RPT];
-#pragma unroll
-    for (int k = 0; k < ENC_RPT; k++) {
-      const int i = k * ENC_NT + tid;
-      wb[k] = 0; wm[k] = 0;
+      wb[k] = 0;
       if (i < rows) {
         const unsigned p = s_p[i];
-        const unsigned idx = (unsigned)s_gbase[p] + ((unsigned)i - s_start[p]);
-        const unsigned t = (unsigned)counts[p], rec = idx / B, j = idx - rec * B, nrec = (t + B - 1) / B;
-        wm[k] = rec == nrec - 1 ? t - rec * B : B;
-        wb[k] = part_off[p] + (unsigned long long)rec * F + j;
+        unsigned m, j;
+        wb[k] = dest_of(sp, F, B, p, (unsigned)s_gbase[p] + ((unsigned)i - s_start[p]), counts, part_off, m, j) + j;
+        if (m == B) full |= 1u << k;
       }
     }
     for (int c = 0; c < sp.ncols; c++) {
-      const ShufCol col = sp.col[c];
-      const int nh = col.width == 16 ? 2 : (col.width ? 1 : 0);
+      const unsigned width = sp.col[c].width, nullable = sp.col[c].nullable;
+      const void* __restrict__ values = sp.col[c].values;
+      const int nh = width == 16 ? 2 : (width ? 1 : 0);
+      const int nb = width < 8 ? (int)width : 8;
+      // data region of column c inside a full record
+      const unsigned long long off_full = (unsigned long long)vlB + (unsigned)c + (unsigned long long)sp.col[c].k8 * B8 + (unsigned long long)sp.col[c].kw * B + 1 + (nullable ? B8 : 0);
       for (int h = 0; h < nh; h++) {
+        if (width == 8) {
 #pragma unroll
-        for (int k = 0; k < ENC_RPT; k++) {
-          const int i = k * ENC_NT + tid;
-          if (i < rows) {
-            const long long r = t0 + i;
-            unsigned long long v;
-            switch (col.width) {
-              case 1: v = ((const uint8_t*)col.values)[r]; break;
-              case 2: v = ((const uint16_t*)col.values)[r]; break;
-              case 4: v = ((const uint32_t*)col.values)[r]; break;
-              case 8: v = ((const unsigned long long*)col.values)[r]; break;
-              default: v = ((const unsigned long long*)col.values)[2 * r + h]; break;
-            }
-            s_val[lpos[k]] = v;
-          }
+          for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const unsigned long long*)values)[t0 + i]; }
+        } else if (width == 4) {
+#pragma unroll
+          for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const uint32_t*)values)[t0 + i]; }
+        } else if (width == 16) {
+#pragma unroll
+          for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const unsigned long long*)values)[2 * (t0 + i) + h]; }
+        } else if (width == 2) {
+#pragma unroll
+          for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const uint16_t*)values)[t0 + i]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const uint8_t*)values)[t0 + i]; }
         }
         __syncthreads();
-        const int nb = col.width < 8 ? col.width : 8;
 #pragma unroll
         for (int k = 0; k < ENC_RPT; k++) {
           const int i = k * ENC_NT + tid;
           if (i < rows) {
             const unsigned long long v = s_val[i];
-            const unsigned long long m = wm[k], m8 = (m + 7) >> 3;
-            uint8_t* a = out + wb[k] + col_offset(sp, c, m, m8, shuf_varint_len(m)) + 1 + (col.nullable ? m8 : 0) + (unsigned long long)(h * 8) * m;
-            for (int b = 0; b < nb; b++) a[(unsigned long long)b * m] = (uint8_t)(v >> (8 * b));
+            if (full & (1u << k)) {
+              uint8_t* a = out + wb[k] + off_full + (unsigned long long)(h * 8) * B;
+              for (int b = 0; b < nb; b++) a[(size_t)b * B] = (uint8_t)(v >> (8 * b));
+            } else {                                                        // the short last record of a partition
+              const unsigned p = s_p[i];
+              unsigned m, j;
+              dest_of(sp, F, B, p, (unsigned)s_gbase[p] + ((unsigned)i - s_start[p]), counts, part_off, m, j);
+              const unsigned long long m8 = (m + 7) >> 3;
+              uint8_t* a = out + wb[k] + col_offset(sp, c, m, m8, shuf_varint_len(m)) + 1 + (nullable ? m8 : 0) + (unsigned long long)(h * 8) * m;
+              for (int b = 0; b < nb; b++) a[(size_t)b * m] = (uint8_t)(v >> (8 * b));
+            }
           }
         }
         __syncthreads();
       }
-      if (col.nullable || col.width == 0) {
+      if (nullable || width == 0) {
         // bit regions (validity bitmaps, Boolean values): set bits are OR-ed into the zeroed buffer from the rows' own destinations
+        const uint8_t* __restrict__ validity = sp.col[c].validity;
+        const unsigned bit_offset = sp.col[c].bit_offset;
 #pragma unroll
         for (int k = 0; k < ENC_RPT; k++) {
           const int i = k * ENC_NT + tid;
           if (i < rows) {
             const long long r = t0 + i;
-            const unsigned p = pid[k];
-            const unsigned idx = (unsigned)s_gbase[p] + (lpos[k] - s_start[p]);
-            const unsigned t = (unsigned)counts[p], rec = idx / B, j = idx - rec * B, nrec = (t + B - 1) / B;
-            const unsigned long long m = rec == nrec - 1 ? t - rec * B : B, m8 = (m + 7) >> 3;
-            const unsigned long long cb = part_off[p] + (unsigned long long)rec * F + col_offset(sp, c, m, m8, shuf_varint_len(m)) + 1;
-            const unsigned long long bi = (unsigned long long)r + col.bit_offset;
-            if (col.nullable) {
-              const bool valid = col.validity ? ((col.validity[bi >> 3] >> (bi & 7)) & 1) : true;
+            const unsigned p = s_p[lpos[k]];
+            unsigned m, j;
+            const unsigned long long rb = dest_of(sp, F, B, p, (unsigned)s_gbase[p] + (lpos[k] - s_start[p]), counts, part_off, m, j);
+            const unsigned long long m8 = (m + 7) >> 3;
+            const unsigned long long cb = rb + col_offset(sp, c, m, m8, shuf_varint_len(m)) + 1;
+            const unsigned long long bi = (unsigned long long)r + bit_offset;
+            if (nullable) {
+              const bool valid = validity ? ((validity[bi >> 3] >> (bi & 7)) & 1) : true;
               if (valid) or_bit(out, cb + (j >> 3), j & 7);
             }
-            if (col.width == 0 && ((((const uint8_t*)col.values)[bi >> 3] >> (bi & 7)) & 1)) or_bit(out, cb + (col.nullable ? m8 : 0) + (j >> 3), j & 7);
+            if (width == 0 && ((((const uint8_t*)values)[bi >> 3] >> (bi & 7)) & 1)) or_bit(out, cb + (nullable ? m8 : 0) + (j >> 3), j & 7);
           }
         }
       }

@@ -528,6 +528,60 @@ PlanP parse_shuffle_writer(Reader r) {       // ShuffleWriterExecNode{input=1, o
   return n;
 }
 
+// the `~TABLE` column the reference appends to the build side's batches (joins/join_hash_map.rs:409-431, 459-465)
+SchemaDef join_hash_map_schema(const SchemaDef& data) {
+  SchemaDef s = data;
+  for (auto& f : s.fields) f.nullable = true;
+  DType b; b.id = T_BINARY; s.fields.push_back(FieldDef{"~TABLE", b, true});
+  return s;
+}
+
+PlanP parse_join_build(Reader r) {           // BroadcastJoinBuildHashMapExecNode{input=1, keys=2}
+  auto n = std::make_shared<PlanNode>(); n->kind = N_JOIN_BUILD;
+  std::vector<Reader> keys;
+  while (!r.done()) { int wt; uint32_t f = r.tag(wt); if (f == 1) n->input = parse_plan(r.bytes()); else if (f == 2) keys.push_back(r.bytes()); else r.skip(wt); }
+  if (!n->input) bad("Missing required field in protobuf");
+  for (auto& k : keys) n->join_build_keys.push_back(parse_expr(k, n->input->schema));
+  n->schema = join_hash_map_schema(n->input->schema);
+  return n;
+}
+
+// HashJoinExecNode{schema=1,left=2,right=3,on=4,join_type=5,build_side=6} (from_proto.rs:187-223) and
+// BroadcastJoinExecNode{...,broadcast_side=6,cached_build_hash_map_id=7} (from_proto.rs:334-372): both become BroadcastJoinExec
+PlanP parse_join(Reader r, bool broadcast) {
+  auto n = std::make_shared<PlanNode>(); n->kind = N_JOIN;
+  PlanP left, right; std::vector<Reader> on; bool have_schema = false; uint64_t side = 0;
+  while (!r.done()) {
+    int wt; uint32_t f = r.tag(wt);
+    switch (f) {
+      case 1: n->schema = parse_schema(r.bytes()); have_schema = true; break;
+      case 2: left = parse_plan(r.bytes()); break;
+      case 3: right = parse_plan(r.bytes()); break;
+      case 4: on.push_back(r.bytes()); break;
+      case 5: n->join_type = (int)r.varint(); break;
+      case 6: side = r.varint(); break;
+      case 7: if (broadcast) n->cached_build_hash_map_id = r.str(); else r.skip(wt); break;
+      default: r.skip(wt);
+    }
+  }
+  if (!have_schema || !left || !right) bad("Missing required field in protobuf");
+  if (n->join_type < 0 || n->join_type > 6) bad("invalid JoinType");
+  if (side > 1) bad(broadcast ? "invalid BroadcastSide" : "invalid BuildSide");
+  // a broadcast side arrives wrapped in BroadcastJoinBuildHashMapExec: its data schema is what the join sees
+  auto data_schema = [](const PlanP& p) { return p->kind == N_JOIN_BUILD ? p->input->schema : p->schema; };
+  n->join_left_schema = data_schema(left); n->join_right_schema = data_schema(right);
+  for (auto& o : on) {                         // JoinOn{left=1, right=2}
+    Reader jr = o; ExprP l, rr;
+    while (!jr.done()) { int wt; uint32_t f = jr.tag(wt); if (f == 1) l = parse_expr(jr.bytes(), n->join_left_schema); else if (f == 2) rr = parse_expr(jr.bytes(), n->join_right_schema); else jr.skip(wt); }
+    if (!l || !rr) bad("JoinOn without both sides");
+    n->join_on.push_back({l, rr});
+  }
+  n->join_build_is_left = side == 0;           // JoinSide::LEFT_SIDE = 0 (auron.proto:670-673)
+  n->join_build = n->join_build_is_left ? left : right;
+  n->input = n->join_build_is_left ? right : left;
+  return n;
+}
+
 PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.proto:27-55)
   while (!r.done()) {
     int wt; uint32_t f = r.tag(wt);
@@ -535,10 +589,13 @@ PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.p
       case 2: return parse_shuffle_writer(r.bytes());
       case 6: return parse_projection(r.bytes());
       case 8: return parse_filter(r.bytes());
+      case 11: return parse_join(r.bytes(), false);
+      case 12: return parse_join_build(r.bytes());
+      case 13: return parse_join(r.bytes(), true);
       case 15: return parse_leaf(r.bytes(), false);
       case 16: return parse_agg(r.bytes());
       case 18: return parse_leaf(r.bytes(), true);
-      case 1: case 3: case 4: case 5: case 7: case 9: case 10: case 11: case 12: case 13: case 14: case 17: case 19: case 20:
+      case 1: case 3: case 4: case 5: case 7: case 9: case 10: case 14: case 17: case 19: case 20:
       case 21: case 22: case 23: case 24: case 25:
         unsupported("plan node #" + std::to_string(f) + " is outside the Filter/Project/Agg hot path (SURVEY.md §8)");
       default: r.skip(wt);
@@ -607,6 +664,20 @@ static void explain_rec(const PlanP& p, int depth, std::ostringstream& o) {
         o << "):" << a.data_type.str() << "/" << md[a.mode] << " AS " << a.field_name;
       }
       o << "] partial_skipping=" << (p->supports_partial_skipping ? "true" : "false") << " schema=" << schema_str(p->schema) << "\n"; break;
+    }
+    case N_JOIN_BUILD: {
+      o << ind << "BroadcastJoinBuildHashMapExec keys=[";
+      for (size_t i = 0; i < p->join_build_keys.size(); i++) o << (i ? ", " : "") << explain_expr(p->join_build_keys[i]);
+      o << "] schema=" << schema_str(p->schema) << "\n"; break;
+    }
+    case N_JOIN: {
+      static const char* jt[] = {"Inner", "Left", "Right", "Full", "LeftSemi", "LeftAnti", "Existence"};
+      o << ind << "BroadcastJoinExec " << jt[p->join_type] << " on=[";
+      for (size_t i = 0; i < p->join_on.size(); i++) o << (i ? ", " : "") << "(" << explain_expr(p->join_on[i].first) << ", " << explain_expr(p->join_on[i].second) << ")";
+      o << "] map_side=" << (p->join_build_is_left ? "Left" : "Right") << " schema=" << schema_str(p->schema) << "\n";
+      o << ind << "  [map side]\n"; explain_rec(p->join_build, depth + 2, o);
+      o << ind << "  [probed side]\n"; explain_rec(p->input, depth + 2, o);
+      return;
     }
     case N_SHUFFLE_WRITER: {
       static const char* kd[] = {"Single", "Hash", "RoundRobin", "Range"};

@@ -109,6 +109,13 @@ struct ShuffleResult {
   virtual void chunk(int64_t i, b200q_shuffle_chunk* out) const = 0;
 };
 
+// Hash join (join_stage.cu): the build side is its own op; probe ops attach to its result
+struct JoinBuilt;
+std::unique_ptr<Stage> make_join_build_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);
+std::unique_ptr<Stage> make_join_probe_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);
+struct JoinBuildResult { virtual ~JoinBuildResult() {} virtual std::shared_ptr<JoinBuilt> built() const = 0; };
+struct JoinProbeAttach { virtual ~JoinProbeAttach() {} virtual void attach(std::shared_ptr<JoinBuilt> b) = 0; };
+
 // helpers of the C ABI layer (capi.cu) shared with exchange.cu
 DType type_of_format(const char* arrow_format);
 void export_device(DevBatch& db, int device, ArrowDeviceArray* out);

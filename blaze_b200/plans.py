@@ -187,6 +187,86 @@ class AggExec(ExecutionPlan):
         return P.agg_node(self.input.node(), self.exec_mode, self.groupings, self.aggs, self.supports_partial_skipping)
 
 
+# protobuf JoinType (auron.proto:475-483): SEMI / ANTI are the Left forms (auron-serde/src/lib.rs:104-116)
+JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL, JOIN_SEMI, JOIN_ANTI, JOIN_EXISTENCE = range(7)
+LEFT_SIDE, RIGHT_SIDE = 0, 1
+
+
+def build_join_schema(left: Schema, right: Schema, join_type: int) -> Schema:
+    """the schema the Spark side sends with the node (joins/test.rs:163-176 for the tests): left ++ right with the
+    non-preserved side nullable; Semi / Anti = left; Existence = left ++ `exists#0: Boolean not null`"""
+    if join_type == JOIN_EXISTENCE:
+        return Schema(list(left) + [Field("exists#0", T.bool_, False)])
+    if join_type in (JOIN_SEMI, JOIN_ANTI):
+        return Schema(list(left))
+    ln, rn = join_type in (JOIN_RIGHT, JOIN_FULL), join_type in (JOIN_LEFT, JOIN_FULL)
+    return Schema([Field(f.name, f.dtype, f.nullable or ln) for f in left] + [Field(f.name, f.dtype, f.nullable or rn) for f in right])
+
+
+class BroadcastJoinBuildHashMapExec(ExecutionPlan):
+    """BroadcastJoinBuildHashMapExec::new(input, keys) (broadcast_join_build_hash_map_exec.rs:60-75): the map side of a join."""
+
+    def __init__(self, input: ExecutionPlan, keys: Sequence[E.Expr]):
+        self.input, self.keys = input, list(keys)
+        self._validate()
+
+    def schema(self):
+        return Schema([Field(f.name, f.dtype, True) for f in self.input.schema()] + [Field("~TABLE", T.binary, True)])    # join_hash_map.rs:409-431
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        return P.join_build_node(self.input.node(), self.keys)
+
+
+class BroadcastJoinExec(ExecutionPlan):
+    """BroadcastJoinExec::try_new(schema, left, right, on, join_type, broadcast_side, is_built, cached_build_hash_map_id)
+    (broadcast_join_exec.rs:96-121).  is_built=True serialises as BroadcastJoinExecNode (the map side arrives as a
+    BroadcastJoinBuildHashMapExec), False as HashJoinExecNode (shuffled hash join, from_proto.rs:187-223).
+    execute(): the map side runs as its own op (BroadcastJoinBuildHashMapExec over that child), the other side is probed."""
+
+    def __init__(self, schema: Schema, left: ExecutionPlan, right: ExecutionPlan, on, join_type: int, broadcast_side: int, is_built: bool = False,
+                 cached_build_hash_map_id: Optional[str] = None):
+        self._schema, self.left, self.right, self.on = schema, left, right, list(on)
+        self.join_type, self.broadcast_side, self.is_built, self.cached_id = join_type, broadcast_side, is_built, cached_build_hash_map_id or ""
+        self._validate()
+
+    try_new = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def schema(self):
+        return self._schema
+
+    def children(self):
+        return [self.left, self.right]
+
+    def _sides(self):
+        build, probe = (self.left, self.right) if self.broadcast_side == LEFT_SIDE else (self.right, self.left)
+        keys = [l if self.broadcast_side == LEFT_SIDE else r for l, r in self.on]
+        data = build.input if isinstance(build, BroadcastJoinBuildHashMapExec) else build
+        return data, keys, probe
+
+    def node(self):
+        return P.join_node(self._schema, self.left.node(), self.right.node(), self.on, self.join_type, self.broadcast_side, self.is_built, self.cached_id)
+
+    def execute(self, conf: Optional[native.Conf] = None, device: int = 0):
+        data, keys, probe = self._sides()
+        build_plan = BroadcastJoinBuildHashMapExec(data, keys)
+        with native.NativeOp(build_plan.plan_bytes(), conf, device) as bop:
+            for rb in data.leaf().batches:
+                bop.push(rb)
+            bop.finish()
+            self.build_metrics = bop.metrics()
+            with native.NativeOp(self.plan_bytes(), conf, device) as op:
+                op.attach_build(bop)
+                for rb in probe.leaf().batches:
+                    op.push(rb)
+                    yield from op.pull_all()
+                op.finish()
+                yield from op.pull_all()
+                self.last_metrics = op.metrics()
+
+
 class ShuffleWriterExec(ExecutionPlan):
     """ShuffleWriterExec::try_new(input, partitioning, output_data_file, output_index_file)
     (datafusion-ext-plans/src/shuffle_writer_exec.rs:180-197).  partitioning: ("single",) | ("hash", [exprs], n) |

@@ -126,6 +126,14 @@ def _build_pool():
         ("agg_expr", 4, "PhysicalExprNode", R), ("mode", 5, "enum:AggMode", R), ("grouping_expr_name", 6, _F.TYPE_STRING, R),
         ("agg_expr_name", 7, _F.TYPE_STRING, R), ("initial_input_buffer_offset", 8, _F.TYPE_UINT64),
         ("supports_partial_skipping", 9, _F.TYPE_BOOL)])
+    _enum(fd, "JoinType", [("INNER", 0), ("LEFT", 1), ("RIGHT", 2), ("FULL", 3), ("SEMI", 4), ("ANTI", 5), ("EXISTENCE", 6)])
+    _enum(fd, "JoinSide", [("LEFT_SIDE", 0), ("RIGHT_SIDE", 1)])
+    _msg(fd, "JoinOn", [("left", 1, "PhysicalExprNode"), ("right", 2, "PhysicalExprNode")])
+    _msg(fd, "HashJoinExecNode", [("schema", 1, "Schema"), ("left", 2, "PhysicalPlanNode"), ("right", 3, "PhysicalPlanNode"), ("on", 4, "JoinOn", R),
+                                  ("join_type", 5, "enum:JoinType"), ("build_side", 6, "enum:JoinSide")])
+    _msg(fd, "BroadcastJoinBuildHashMapExecNode", [("input", 1, "PhysicalPlanNode"), ("keys", 2, "PhysicalExprNode", R)])
+    _msg(fd, "BroadcastJoinExecNode", [("schema", 1, "Schema"), ("left", 2, "PhysicalPlanNode"), ("right", 3, "PhysicalPlanNode"), ("on", 4, "JoinOn", R),
+                                       ("join_type", 5, "enum:JoinType"), ("broadcast_side", 6, "enum:JoinSide"), ("cached_build_hash_map_id", 7, _F.TYPE_STRING)])
     _msg(fd, "PhysicalSingleRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
     _msg(fd, "PhysicalHashRepartition", [("hash_expr", 1, "PhysicalExprNode", R), ("partition_count", 2, _F.TYPE_UINT64)])
     _msg(fd, "PhysicalRoundRobinRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
@@ -136,7 +144,9 @@ def _build_pool():
     _msg(fd, "ShuffleWriterExecNode", [("input", 1, "PhysicalPlanNode"), ("output_partitioning", 2, "PhysicalRepartition"),
                                        ("output_data_file", 3, _F.TYPE_STRING), ("output_index_file", 4, _F.TYPE_STRING)])
     _msg(fd, "PhysicalPlanNode", [
-        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O), ("filter", 8, "FilterExecNode", O),
+        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O),
+        ("hash_join", 11, "HashJoinExecNode", O), ("broadcast_join_build_hash_map", 12, "BroadcastJoinBuildHashMapExecNode", O),
+        ("broadcast_join", 13, "BroadcastJoinExecNode", O), ("filter", 8, "FilterExecNode", O),
         ("empty_partitions", 15, "EmptyPartitionsExecNode", O), ("agg", 16, "AggExecNode", O),
         ("ffi_reader", 18, "FFIReaderExecNode", O),
     ], oneofs=["PhysicalPlanType"])
@@ -334,6 +344,34 @@ def agg_node(input_node, exec_mode, groupings, aggs, supports_partial_skipping=F
         a.mode.append(ag.mode)
     a.initial_input_buffer_offset = initial_input_buffer_offset
     a.supports_partial_skipping = supports_partial_skipping
+    return n
+
+
+def join_build_node(input_node, keys):
+    n = PhysicalPlanNode()
+    n.broadcast_join_build_hash_map.input.CopyFrom(input_node)
+    for k in keys:
+        n.broadcast_join_build_hash_map.keys.add().CopyFrom(expr_msg(k))
+    return n
+
+
+def join_node(schema: Schema, left_node, right_node, on, join_type: int, map_side: int, broadcast: bool, cached_id: str = ""):
+    """HashJoinExecNode (broadcast=False, `build_side`) / BroadcastJoinExecNode (broadcast=True, `broadcast_side`); on = [(left expr, right expr)]"""
+    n = PhysicalPlanNode()
+    j = n.broadcast_join if broadcast else n.hash_join
+    j.schema.CopyFrom(schema_msg(schema))
+    j.left.CopyFrom(left_node)
+    j.right.CopyFrom(right_node)
+    for l, r in on:
+        o = j.on.add()
+        o.left.CopyFrom(expr_msg(l))
+        o.right.CopyFrom(expr_msg(r))
+    j.join_type = join_type
+    if broadcast:
+        j.broadcast_side = map_side
+        j.cached_build_hash_map_id = cached_id
+    else:
+        j.build_side = map_side
     return n
 
 

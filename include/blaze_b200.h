@@ -36,6 +36,7 @@
  *                           BufferedData::write               datafusion-ext-plans/src/shuffle/buffered_data.rs:123-158
  *                           write_batch (byte planes)         datafusion-ext-commons/src/io/batch_serde.rs:66-77,264-306
  *                           IpcCompressionWriter              datafusion-ext-plans/src/common/ipc_compression.rs:34-112
+ *   b200q_op_attach_build   collect_join_hash_map + execute_join_with_map   datafusion-ext-plans/src/broadcast_join_exec.rs:317-385,562-639
  *   b200q_op_shuffle_chunk  the per-partition encoded bytes before compression — what BufferedData::write_rss
  *                           hands to an RSS partition writer (buffered_data.rs:160-196)
  *
@@ -222,6 +223,18 @@ b200q_status b200q_op_sync(b200q_op* op);
 
 b200q_status b200q_op_metrics(b200q_op* op, b200q_metrics* out);
 void b200q_op_destroy(b200q_op* op);
+
+/* ---- Hash join (HashJoinExecNode / BroadcastJoinExecNode + BroadcastJoinBuildHashMapExecNode) --------------------------
+ * Reference: BroadcastJoinExec (datafusion-ext-plans/src/broadcast_join_exec.rs:226-298,496-560), the joiners
+ * (joins/bhj/full_join.rs:90-379, joins/bhj/semi_join.rs:100-327) and JoinHashMap (joins/join_hash_map.rs:91-275).
+ * The map side is its own op, as it is its own plan node in the reference: create an op from a
+ * BroadcastJoinBuildHashMapExecNode{input, keys} plan, push the side's batches, finish it — the table and the side's
+ * columns stay in HBM.  Create the join op from the HashJoinExecNode / BroadcastJoinExecNode plan (its map-side child only
+ * supplies the schema), attach the finished build op, then push the PROBED side's batches and pull the joined rows.
+ * Several probe ops (the tasks of a stage) may attach to one build op — the counterpart of the process-wide map cache keyed by
+ * cached_build_hash_map_id (broadcast_join_exec.rs:640-677); the build op must outlive them only until they are destroyed
+ * (the table is reference counted).  Inner / Left / Right / Full / LeftSemi / LeftAnti / Existence, either side as the map. */
+b200q_status b200q_op_attach_build(b200q_op* probe_op, b200q_op* build_op);
 
 /* ---- ShuffleWriterExec result (plans rooted at ShuffleWriterExecNode) ----------------------------------------
  * Every pushed batch becomes one CHUNK: the rows of the batch grouped by output partition
