@@ -159,6 +159,13 @@ static void build_pipeline(b200q_op* op) {
       op->stages.push_back(make_agg_stage(op->cx, stage_in, filters, *n, gex, aargs));
       stage_in = op->stages.back()->out_schema;
       cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+    } else if (n->kind == N_SORT) {
+      if (pending_tail) {
+        op->stages.push_back(make_filter_project_stage(op->cx, stage_in, filters, cur_cols, n->input->schema));
+        stage_in = op->stages.back()->out_schema; cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
+      }
+      op->stages.push_back(make_sort_stage(op->cx, stage_in, *n));
+      stage_in = op->stages.back()->out_schema; cur_cols = identity_cols(stage_in);
     } else if (n->kind == N_JOIN_BUILD || n->kind == N_JOIN) {
       if (pending_tail) {                               // Filter / Project chain below the join side: its own fused stage
         op->stages.push_back(make_filter_project_stage(op->cx, stage_in, filters, cur_cols, n->input->schema));

@@ -95,7 +95,7 @@ struct AggDef {
   }
 };
 
-enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG, N_SHUFFLE_WRITER, N_JOIN_BUILD, N_JOIN };
+enum NodeKind : uint8_t { N_LEAF, N_FILTER, N_PROJECT, N_AGG, N_SHUFFLE_WRITER, N_JOIN_BUILD, N_JOIN, N_SORT };
 enum ShuffleKind : uint8_t { SHUFFLE_SINGLE = 0, SHUFFLE_HASH = 1, SHUFFLE_ROUND_ROBIN = 2, SHUFFLE_RANGE = 3 };   // PhysicalRepartition oneof (auron.proto:629-655)
 
 struct PlanNode {
@@ -131,6 +131,11 @@ struct PlanNode {
   std::vector<std::pair<ExprP, ExprP>> join_on;                       // (left key, right key)
   SchemaDef join_left_schema, join_right_schema;
   std::string cached_build_hash_map_id;
+  // N_SORT (SortExecNode, auron.proto:618-627; PhysicalSortExprNode :178-182)
+  struct SortExprDef { ExprP expr; bool asc = true; bool nulls_first = true; };
+  std::vector<SortExprDef> sort_exprs;
+  bool sort_has_fetch = false;
+  uint64_t sort_fetch = 0;
 };
 using PlanP = std::shared_ptr<PlanNode>;
 

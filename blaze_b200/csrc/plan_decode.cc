@@ -528,6 +528,32 @@ PlanP parse_shuffle_writer(Reader r) {       // ShuffleWriterExecNode{input=1, o
   return n;
 }
 
+PlanP parse_sort(Reader r) {                 // SortExecNode{input=1, expr=2 (PhysicalExprNode.sort = 11), fetch_limit=3{limit=1}}; try_parse_physical_sort_expr
+  auto n = std::make_shared<PlanNode>(); n->kind = N_SORT;
+  std::vector<Reader> exprs;
+  while (!r.done()) {
+    int wt; uint32_t f = r.tag(wt);
+    if (f == 1) n->input = parse_plan(r.bytes()); else if (f == 2) exprs.push_back(r.bytes());
+    else if (f == 3) { Reader fl = r.bytes(); n->sort_has_fetch = true; while (!fl.done()) { int w2; uint32_t g = fl.tag(w2); if (g == 1) n->sort_fetch = fl.varint(); else fl.skip(w2); } }
+    else r.skip(wt);
+  }
+  if (!n->input) bad("Missing required field in protobuf");
+  n->schema = n->input->schema;                                             // sort_exec.rs:164-166
+  for (auto& e : exprs) {
+    Reader er = e; bool found = false;
+    while (!er.done()) {
+      int wt; uint32_t f = er.tag(wt);
+      if (f != 11) { er.skip(wt); continue; }
+      Reader sr = er.bytes(); PlanNode::SortExprDef d; d.asc = false; d.nulls_first = false;      // proto3 defaults
+      while (!sr.done()) { int w2; uint32_t g = sr.tag(w2); if (g == 1) d.expr = parse_expr(sr.bytes(), n->schema); else if (g == 2) d.asc = sr.varint() != 0; else if (g == 3) d.nulls_first = sr.varint() != 0; else sr.skip(w2); }
+      if (!d.expr) bad("physical_plan::from_proto() Unexpected expr: sort expression without an expression");
+      n->sort_exprs.push_back(d); found = true;
+    }
+    if (!found) bad("physical_plan::from_proto() Unexpected expr: expected a sort expression");
+  }
+  return n;
+}
+
 // the `~TABLE` column the reference appends to the build side's batches (joins/join_hash_map.rs:409-431, 459-465)
 SchemaDef join_hash_map_schema(const SchemaDef& data) {
   SchemaDef s = data;
@@ -588,6 +614,7 @@ PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.p
     switch (f) {
       case 2: return parse_shuffle_writer(r.bytes());
       case 6: return parse_projection(r.bytes());
+      case 7: return parse_sort(r.bytes());
       case 8: return parse_filter(r.bytes());
       case 11: return parse_join(r.bytes(), false);
       case 12: return parse_join_build(r.bytes());
@@ -595,7 +622,7 @@ PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.p
       case 15: return parse_leaf(r.bytes(), false);
       case 16: return parse_agg(r.bytes());
       case 18: return parse_leaf(r.bytes(), true);
-      case 1: case 3: case 4: case 5: case 7: case 9: case 10: case 14: case 17: case 19: case 20:
+      case 1: case 3: case 4: case 5: case 9: case 10: case 14: case 17: case 19: case 20:
       case 21: case 22: case 23: case 24: case 25:
         unsupported("plan node #" + std::to_string(f) + " is outside the Filter/Project/Agg hot path (SURVEY.md §8)");
       default: r.skip(wt);
@@ -664,6 +691,12 @@ static void explain_rec(const PlanP& p, int depth, std::ostringstream& o) {
         o << "):" << a.data_type.str() << "/" << md[a.mode] << " AS " << a.field_name;
       }
       o << "] partial_skipping=" << (p->supports_partial_skipping ? "true" : "false") << " schema=" << schema_str(p->schema) << "\n"; break;
+    }
+    case N_SORT: {
+      o << ind << "SortExec [";
+      for (size_t i = 0; i < p->sort_exprs.size(); i++) o << (i ? ", " : "") << explain_expr(p->sort_exprs[i].expr) << (p->sort_exprs[i].asc ? " ASC" : " DESC") << (p->sort_exprs[i].nulls_first ? " NULLS FIRST" : " NULLS LAST");
+      o << "]"; if (p->sort_has_fetch) o << " fetch=" << p->sort_fetch;
+      o << " schema=" << schema_str(p->schema) << "\n"; break;
     }
     case N_JOIN_BUILD: {
       o << ind << "BroadcastJoinBuildHashMapExec keys=[";

@@ -109,6 +109,9 @@ struct ShuffleResult {
   virtual void chunk(int64_t i, b200q_shuffle_chunk* out) const = 0;
 };
 
+// SortExec (sort_stage.cu): collects its input, emits the sorted (and `fetch`-limited) rows at finish
+std::unique_ptr<Stage> make_sort_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);
+
 // Hash join (join_stage.cu): the build side is its own op; probe ops attach to its result
 struct JoinBuilt;
 std::unique_ptr<Stage> make_join_build_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);

@@ -187,6 +187,26 @@ class AggExec(ExecutionPlan):
         return P.agg_node(self.input.node(), self.exec_mode, self.groupings, self.aggs, self.supports_partial_skipping)
 
 
+class SortExec(ExecutionPlan):
+    """SortExec::new(input, exprs, fetch) (sort_exec.rs:97-112); exprs = [(expr, descending, nulls_first)] like arrow's
+    PhysicalSortExpr{expr, SortOptions{descending, nulls_first}} (SortOptions::default() = ascending, NULLs first)."""
+
+    def __init__(self, input: ExecutionPlan, exprs, fetch: Optional[int] = None):
+        self.input, self.exprs, self.fetch = input, [(e, bool(d), bool(nf)) for e, d, nf in exprs], fetch
+        self._validate()
+
+    new = classmethod(lambda cls, input, exprs, fetch=None: cls(input, exprs, fetch))
+
+    def schema(self):
+        return self.input.schema()
+
+    def children(self):
+        return [self.input]
+
+    def node(self):
+        return P.sort_node(self.input.node(), [(e, not d, nf) for e, d, nf in self.exprs], self.fetch)      # wire: asc = !descending (from_proto.rs:240-246)
+
+
 # protobuf JoinType (auron.proto:475-483): SEMI / ANTI are the Left forms (auron-serde/src/lib.rs:104-116)
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_FULL, JOIN_SEMI, JOIN_ANTI, JOIN_EXISTENCE = range(7)
 LEFT_SIDE, RIGHT_SIDE = 0, 1

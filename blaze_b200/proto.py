@@ -105,11 +105,13 @@ def _build_pool():
                                              ("args", 3, "PhysicalExprNode", R), ("return_type", 4, "ArrowType")])
     _msg(fd, "PhysicalSCAndExprNode", [("left", 1, "PhysicalExprNode"), ("right", 2, "PhysicalExprNode")])
     _msg(fd, "PhysicalSCOrExprNode", [("left", 1, "PhysicalExprNode"), ("right", 2, "PhysicalExprNode")])
+    _msg(fd, "PhysicalSortExprNode", [("expr", 1, "PhysicalExprNode"), ("asc", 2, _F.TYPE_BOOL), ("nulls_first", 3, _F.TYPE_BOOL)])
     _msg(fd, "PhysicalExprNode", [
         ("column", 1, "PhysicalColumn", O), ("literal", 2, "ScalarValue", O), ("bound_reference", 3, "BoundReference", O),
         ("binary_expr", 4, "PhysicalBinaryExprNode", O), ("agg_expr", 5, "PhysicalAggExprNode", O),
         ("is_null_expr", 6, "PhysicalIsNull", O), ("is_not_null_expr", 7, "PhysicalIsNotNull", O),
         ("not_expr", 8, "PhysicalNot", O), ("case_", 9, "PhysicalCaseNode", O), ("cast", 10, "PhysicalCastNode", O),
+        ("sort", 11, "PhysicalSortExprNode", O),
         ("negative", 12, "PhysicalNegativeNode", O), ("in_list", 13, "PhysicalInListNode", O),
         ("scalar_function", 14, "PhysicalScalarFunctionNode", O), ("try_cast", 15, "PhysicalTryCastNode", O),
         ("sc_and_expr", 3000, "PhysicalSCAndExprNode", O), ("sc_or_expr", 3001, "PhysicalSCOrExprNode", O),
@@ -134,6 +136,8 @@ def _build_pool():
     _msg(fd, "BroadcastJoinBuildHashMapExecNode", [("input", 1, "PhysicalPlanNode"), ("keys", 2, "PhysicalExprNode", R)])
     _msg(fd, "BroadcastJoinExecNode", [("schema", 1, "Schema"), ("left", 2, "PhysicalPlanNode"), ("right", 3, "PhysicalPlanNode"), ("on", 4, "JoinOn", R),
                                        ("join_type", 5, "enum:JoinType"), ("broadcast_side", 6, "enum:JoinSide"), ("cached_build_hash_map_id", 7, _F.TYPE_STRING)])
+    _msg(fd, "FetchLimit", [("limit", 1, _F.TYPE_UINT64)])
+    _msg(fd, "SortExecNode", [("input", 1, "PhysicalPlanNode"), ("expr", 2, "PhysicalExprNode", R), ("fetch_limit", 3, "FetchLimit")])
     _msg(fd, "PhysicalSingleRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
     _msg(fd, "PhysicalHashRepartition", [("hash_expr", 1, "PhysicalExprNode", R), ("partition_count", 2, _F.TYPE_UINT64)])
     _msg(fd, "PhysicalRoundRobinRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
@@ -144,7 +148,7 @@ def _build_pool():
     _msg(fd, "ShuffleWriterExecNode", [("input", 1, "PhysicalPlanNode"), ("output_partitioning", 2, "PhysicalRepartition"),
                                        ("output_data_file", 3, _F.TYPE_STRING), ("output_index_file", 4, _F.TYPE_STRING)])
     _msg(fd, "PhysicalPlanNode", [
-        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O),
+        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O), ("sort", 7, "SortExecNode", O),
         ("hash_join", 11, "HashJoinExecNode", O), ("broadcast_join_build_hash_map", 12, "BroadcastJoinBuildHashMapExecNode", O),
         ("broadcast_join", 13, "BroadcastJoinExecNode", O), ("filter", 8, "FilterExecNode", O),
         ("empty_partitions", 15, "EmptyPartitionsExecNode", O), ("agg", 16, "AggExecNode", O),
@@ -344,6 +348,19 @@ def agg_node(input_node, exec_mode, groupings, aggs, supports_partial_skipping=F
         a.mode.append(ag.mode)
     a.initial_input_buffer_offset = initial_input_buffer_offset
     a.supports_partial_skipping = supports_partial_skipping
+    return n
+
+
+def sort_node(input_node, sort_exprs, fetch=None):
+    """sort_exprs: [(expr, asc, nulls_first)] (PhysicalSortExprNode, auron.proto:178-182); fetch: optional FetchLimit"""
+    n = PhysicalPlanNode()
+    n.sort.input.CopyFrom(input_node)
+    for e, asc, nulls_first in sort_exprs:
+        x = n.sort.expr.add()
+        x.sort.expr.CopyFrom(expr_msg(e))
+        x.sort.asc, x.sort.nulls_first = asc, nulls_first
+    if fetch is not None:
+        n.sort.fetch_limit.limit = fetch
     return n
 
 

@@ -36,6 +36,7 @@
  *                           BufferedData::write               datafusion-ext-plans/src/shuffle/buffered_data.rs:123-158
  *                           write_batch (byte planes)         datafusion-ext-commons/src/io/batch_serde.rs:66-77,264-306
  *                           IpcCompressionWriter              datafusion-ext-plans/src/common/ipc_compression.rs:34-112
+ *   SortExecNode plans      SortExec::new + ExternalSorter::insert_batch / output   datafusion-ext-plans/src/sort_exec.rs:97-112,626-752
  *   b200q_op_attach_build   collect_join_hash_map + execute_join_with_map   datafusion-ext-plans/src/broadcast_join_exec.rs:317-385,562-639
  *   b200q_op_shuffle_chunk  the per-partition encoded bytes before compression — what BufferedData::write_rss
  *                           hands to an RSS partition writer (buffered_data.rs:160-196)
