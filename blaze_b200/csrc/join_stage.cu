@@ -66,7 +66,8 @@ struct JoinBuilt {
   std::vector<DevMemP> values;                    // per column, contiguous
   std::vector<DevMemP> valid_bytes;               // per column: one byte per row, null when the column has no NULL
   JoinTable table{};
-  DevMemP t_keys, t_state, t_head, t_count, t_next;
+  DevMemP t_keys, t_state, t_head, t_count, t_next, t_stats;
+  uint32_t max_dup = 0;                           // rows of the most duplicated key
   int device = 0;
 };
 
@@ -144,9 +145,10 @@ class JoinBuildStage : public Stage, public JoinBuildResult {
     b->t_head = DevMem::alloc((size_t)cap * 4, cx.stream);
     b->t_count = DevMem::alloc((size_t)cap * 4, cx.stream, true);
     b->t_next = DevMem::alloc((size_t)total * 4 + 16, cx.stream);
+    b->t_stats = DevMem::alloc(16, cx.stream, true);
     B200Q_CUDA(cudaMemsetAsync(b->t_head->ptr, 0xFF, (size_t)cap * 4, cx.stream));
     t.keys = (unsigned long long*)b->t_keys->ptr; t.state = (uint32_t*)b->t_state->ptr; t.head = (uint32_t*)b->t_head->ptr;
-    t.count = (uint32_t*)b->t_count->ptr; t.next = (uint32_t*)b->t_next->ptr;
+    t.count = (uint32_t*)b->t_count->ptr; t.next = (uint32_t*)b->t_next->ptr; t.stats = (uint32_t*)b->t_stats->ptr;
     if (total > 0) {
       JoinKeys k{}; k.nkeys = (int)keys_.size();
       for (int i = 0; i < k.nkeys; i++) {
@@ -166,6 +168,7 @@ class JoinBuildStage : public Stage, public JoinBuildResult {
       B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
       cx.m.launches += launch_join_build(k, total, t, cx.stream);
       B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+      B200Q_CUDA(cudaMemcpyAsync(&b->max_dup, b->t_stats->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
       B200Q_CUDA(cudaStreamSynchronize(cx.stream));
       float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; cx.m.hot_ms += ms; cx.m.hot_rows += total; cx.m.hot_launches++; cx.m.fast_launches++;
     }
@@ -301,21 +304,27 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
     const int64_t n = in.num_rows;
     if (n == 0) return;
     JoinKeys k{}; fill_keys(k, probe_keys_, in);
-    DevMemP head = DevMem::alloc((size_t)n * 4 + 16, cx.stream);
+    DevMemP cursor = DevMem::alloc(16, cx.stream, true);
+    auto read_cursor = [&]() { unsigned long long v = 0; B200Q_CUDA(cudaMemcpyAsync(&v, cursor->ptr, 8, cudaMemcpyDeviceToHost, cx.stream)); B200Q_CUDA(cudaStreamSynchronize(cx.stream)); return (int64_t)v; };
     B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
     if (!semi_like_) {
-      DevMemP cnt = DevMem::alloc((size_t)n * 4 + 16, cx.stream), offs;
-      cx.m.launches += launch_join_probe_count(k, n, built_->table, probe_outer_ ? 1 : 0, (uint32_t*)head->ptr, (int32_t*)cnt->ptr, cx.stream);
-      const int64_t total = scan(cx, (const int32_t*)cnt->ptr, n, offs);
-      if (total > 0) {
-        DevMemP pidx = DevMem::alloc((size_t)total * 4 + 16, cx.stream), bidx = DevMem::alloc((size_t)total * 4 + 16, cx.stream);
-        cx.m.launches += launch_join_probe_emit(n, built_->table, (const uint32_t*)head->ptr, (const int32_t*)offs->ptr, (uint32_t*)pidx->ptr, (uint32_t*)bidx->ptr,
-                                                build_outer_ ? (uint8_t*)map_joined_->ptr : nullptr, cx.stream);
-        emit(outs, gather_probe(cx, in, (const uint32_t*)pidx->ptr, total, false), gather_build(cx, (const uint32_t*)bidx->ptr, total, probe_outer_), total);
+      // unique build keys (the PK side of a PK-FK join): at most one output row per probe row -> one fused pass; otherwise count first
+      int64_t cap = n;
+      if (built_->max_dup > 1) {
+        cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, nullptr, nullptr, nullptr, cx.stream);
+        cap = read_cursor();
+        B200Q_CUDA(cudaMemsetAsync(cursor->ptr, 0, 8, cx.stream));
+      }
+      if (cap > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "join: more than 2^31-1 output rows from one probe batch; push smaller batches");
+      if (cap > 0) {
+        DevMemP pidx = DevMem::alloc((size_t)cap * 4 + 16, cx.stream), bidx = DevMem::alloc((size_t)cap * 4 + 16, cx.stream);
+        cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, (uint32_t*)pidx->ptr, (uint32_t*)bidx->ptr,
+                                                 build_outer_ ? (uint8_t*)map_joined_->ptr : nullptr, cx.stream);
+        const int64_t total = read_cursor();
+        if (total > 0) emit(outs, gather_probe(cx, in, (const uint32_t*)pidx->ptr, total, false), gather_build(cx, (const uint32_t*)bidx->ptr, total, probe_outer_), total);
       }
     } else {
-      cx.m.launches += launch_join_probe_count(k, n, built_->table, 0, (uint32_t*)head->ptr, nullptr, cx.stream);
-      if (!probe_is_join_side_) cx.m.launches += launch_join_mark_build(n, built_->table, (const uint32_t*)head->ptr, (uint8_t*)map_joined_->ptr, cx.stream);
+      if (!probe_is_join_side_) cx.m.launches += launch_join_probe_mark(k, n, built_->table, (uint8_t*)map_joined_->ptr, cx.stream);
       else if (jt_ == PJ_EXISTENCE) {                  // every probe row + exists#0 (semi_join.rs:252-258)
         DevBatch ob; ob.num_rows = n;
         for (auto& c : in.cols) {
@@ -334,22 +343,18 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
           }
           ob.cols.push_back(o);
         }
-        DevMemP fb = DevMem::alloc((size_t)n + 16, cx.stream);
+        DevMemP head = DevMem::alloc((size_t)n * 4 + 16, cx.stream), fb = DevMem::alloc((size_t)n + 16, cx.stream);
+        cx.m.launches += launch_join_probe_count(k, n, built_->table, 0, (uint32_t*)head->ptr, nullptr, cx.stream);
         cx.m.launches += launch_join_match_bytes((const uint32_t*)head->ptr, n, (uint8_t*)fb->ptr, cx.stream);
         DevColumn ex; ex.type.id = T_BOOL; ex.values = DevMem::alloc(bitmap_bytes(n), cx.stream, true);
         cx.m.launches += launch_pack_valid((const uint8_t*)fb->ptr, (uint32_t*)ex.values->ptr, n, cx.stream);
         ob.cols.push_back(ex);
         outs.push_back(std::move(ob));
       } else {                                         // LeftSemi / LeftAnti with the probe side as the join side (semi_join.rs:243-251)
-        DevMemP fl = DevMem::alloc((size_t)n * 4 + 16, cx.stream), offs;
-        cx.m.launches += launch_join_flags((const uint32_t*)head->ptr, n, jt_ == PJ_ANTI ? 1 : 0, (int32_t*)fl->ptr, cx.stream);
-        const int64_t total = scan(cx, (const int32_t*)fl->ptr, n, offs);
-        if (total > 0) {
-          DevMemP idx = DevMem::alloc((size_t)total * 4 + 16, cx.stream);
-          cx.m.launches += launch_join_compact_indices((const int32_t*)fl->ptr, (const int32_t*)offs->ptr, n, (uint32_t*)idx->ptr, cx.stream);
-          DevBatch ob; ob.num_rows = total; ob.cols = gather_probe(cx, in, (const uint32_t*)idx->ptr, total, false);
-          outs.push_back(std::move(ob));
-        }
+        DevMemP idx = DevMem::alloc((size_t)n * 4 + 16, cx.stream);
+        cx.m.launches += launch_join_probe_select(k, n, built_->table, jt_ == PJ_ANTI ? 1 : 0, (unsigned long long*)cursor->ptr, (uint32_t*)idx->ptr, cx.stream);
+        const int64_t total = read_cursor();
+        if (total > 0) { DevBatch ob; ob.num_rows = total; ob.cols = gather_probe(cx, in, (const uint32_t*)idx->ptr, total, false); outs.push_back(std::move(ob)); }
       }
     }
     B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));

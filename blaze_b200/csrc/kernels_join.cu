@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(JB) join_build_kernel(const JoinKeys k, long l
       const bool same = t.keys[(size_t)slot * t.nkw] == w[0] && (t.nkw == 1 || t.keys[(size_t)slot * t.nkw + 1] == w[1]);
       if (same) {
         t.next[i] = atomicExch(t.head + slot, (uint32_t)i);
-        atomicAdd(t.count + slot, 1u);
+        const uint32_t c = atomicAdd(t.count + slot, 1u) + 1;
+        if (c > 1) atomicMax(t.stats, c);                              // stats[0] = rows of the most duplicated key (0 / 1: keys are unique)
         break;
       }
       slot = (slot + 1) & t.mask;
@@ -127,6 +128,66 @@ __global__ void __launch_bounds__(JB) join_mark_build_kernel(long long n, const 
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
     uint32_t b = head[i];
     if (b == JOIN_NIL || mark[b]) continue;                            // all rows of this key were marked together (semi_join.rs:214-226)
+    for (; b != JOIN_NIL; b = t.next[b]) mark[b] = 1;
+  }
+}
+
+// Fused probe of the pair-producing joins (Inner / Left / Right / Full): lookup, then the warp reserves the output rows of its
+// 32 probe rows with ONE atomic on `cursor` and every lane writes its (probe row, build row) pairs — no per-row
+// intermediates and no scan; the order of the output rows is whatever the reservation order is (not a contract).
+// pidx == null: only count (cursor += matches), for build sides with duplicated keys whose output size is not bounded by n.
+__global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
+                                                              uint32_t* __restrict__ pidx, uint32_t* __restrict__ bidx, uint8_t* mark) {
+  const unsigned lane = threadIdx.x & 31;
+  const long long nround = (n + 31) & ~31LL;
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < nround; i += (long long)gridDim.x * JB) {
+    unsigned long long w[2];
+    uint32_t h = JOIN_NIL; unsigned c = 0;
+    if (i < n) {
+      if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) { h = t.head[slot]; c = t.count[slot]; } }
+      if (probe_outer && c == 0) c = 1;
+    }
+    unsigned inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+    const unsigned total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    if (total == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (!pidx || c == 0) continue;
+    unsigned long long o = base + inc - c;
+    if (h == JOIN_NIL) { pidx[o] = (uint32_t)i; bidx[o] = JOIN_NIL; continue; }                       // unmatched outer row
+    for (uint32_t b = h; b != JOIN_NIL; b = t.next[b], o++) { pidx[o] = (uint32_t)i; bidx[o] = b; if (mark) mark[b] = 1; }
+  }
+}
+
+// LeftSemi / LeftAnti with the probed side as the join side: idx[...] = the probe rows that have (invert: have no) partner
+__global__ void __launch_bounds__(JB) join_probe_select_kernel(const JoinKeys k, long long n, const JoinTable t, int invert, unsigned long long* cursor, uint32_t* __restrict__ idx) {
+  const unsigned lane = threadIdx.x & 31;
+  const long long nround = (n + 31) & ~31LL;
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < nround; i += (long long)gridDim.x * JB) {
+    unsigned long long w[2];
+    bool keep = false;
+    if (i < n) { const bool found = load_key(k, i, w) && find_slot(t, w) != JOIN_NIL; keep = found != (invert != 0); }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (m == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (keep) idx[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+  }
+}
+
+// semi-style probes where the BUILD side is the join side: lookup + mark the key's rows
+__global__ void __launch_bounds__(JB) join_probe_mark_kernel(const JoinKeys k, long long n, const JoinTable t, uint8_t* mark) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    unsigned long long w[2];
+    if (!load_key(k, i, w)) continue;
+    const uint32_t slot = find_slot(t, w);
+    if (slot == JOIN_NIL) continue;
+    uint32_t b = t.head[slot];
+    if (mark[b]) continue;                                             // all rows of this key were marked together (semi_join.rs:214-226)
     for (; b != JOIN_NIL; b = t.next[b]) mark[b] = 1;
   }
 }
@@ -190,6 +251,21 @@ int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head
 int launch_join_mark_build(int64_t n, const JoinTable& t, const uint32_t* d_head, uint8_t* mark, cudaStream_t s) {
   if (n <= 0) return 0;
   join_mark_build_kernel<<<jgrid(n), JB, 0, s>>>(n, t, d_head, mark);
+  return 1;
+}
+int launch_join_probe_pairs(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_pairs_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_cursor, d_pidx, d_bidx, mark);
+  return 1;
+}
+int launch_join_probe_select(const JoinKeys& k, int64_t n, const JoinTable& t, int invert, unsigned long long* d_cursor, uint32_t* d_idx, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_select_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, invert, d_cursor, d_idx);
+  return 1;
+}
+int launch_join_probe_mark(const JoinKeys& k, int64_t n, const JoinTable& t, uint8_t* mark, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_mark_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, mark);
   return 1;
 }
 int launch_join_gather(const void* src, const uint8_t* vbits, uint32_t bit_offset, const uint8_t* vbytes, int width, const uint32_t* idx, int64_t n, void* out, uint8_t* out_valid, cudaStream_t s) {

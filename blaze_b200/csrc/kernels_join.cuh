@@ -27,6 +27,7 @@ struct JoinTable {
   uint32_t* head;               // first build row of the key's chain
   uint32_t* count;              // rows in the chain
   uint32_t* next;               // per build row: next row with the same key, JOIN_NIL at the end
+  uint32_t* stats;              // [0] rows of the most duplicated key (0 or 1: the keys are unique)
   uint32_t mask;                // capacity - 1
   int32_t nkw;                  // key words per slot (1 or 2)
 };
@@ -36,6 +37,13 @@ int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStre
 int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s);
 // (probe row, build row) pairs at offs[r]...; marks map_joined[build row] = 1 when mark != null; unmatched outer rows pair with JOIN_NIL
 int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head, const int32_t* d_offs, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s);
+// fused probes (no per-row intermediates; output positions reserved with one atomic per warp on *d_cursor, zeroed by the caller):
+//   pairs : (probe row, build row) pairs of Inner / Left / Right / Full; d_pidx == null only counts
+//   select: the probe rows with (invert: without) a partner — LeftSemi / LeftAnti probed from the left
+//   mark  : marks the build rows whose key some probe row has — semi forms where the build side is the join side
+int launch_join_probe_pairs(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s);
+int launch_join_probe_select(const JoinKeys& k, int64_t n, const JoinTable& t, int invert, unsigned long long* d_cursor, uint32_t* d_idx, cudaStream_t s);
+int launch_join_probe_mark(const JoinKeys& k, int64_t n, const JoinTable& t, uint8_t* mark, cudaStream_t s);
 // semi-style probes where the BUILD side is the join side: mark every build row whose key some probe row has
 int launch_join_mark_build(int64_t n, const JoinTable& t, const uint32_t* d_head, uint8_t* mark, cudaStream_t s);
 // out[i] = idx[i] == JOIN_NIL ? NULL : src[idx[i]]   (width bytes per value; src_valid / out_valid: one byte per row, may be null)
