@@ -42,7 +42,9 @@ WORKLOADS = {
     "M1": "M1: HashAggregateExec SUM(v),COUNT(v) GROUP BY k; k~U[0,2^20) int64, v~U[-1e6,1e6) int64 (BASELINE.json configs[1])",
     "M0": "M0: FilterExec[a<500] (s=0.5) -> ProjectExec[a, a+b]; a~U[0,1000), b~U[-2^31,2^31) int64 (BASELINE.json configs[0] shape)",
 }
-ALG_BYTES_PER_ROW = {"M2": 32.0, "M1": 16.0, "M0": 24.0}
+WORKLOADS["M3"] = "M3: ShuffleWriterExec 200-way hash partition (murmur3 seed 42 pmod 200 on k1) + batch_serde encode of 4 int64 columns, output kept in HBM (BASELINE.json configs[3], map side)"
+WORKLOADS["M4"] = "M4: HashJoinExec store_sales x date_dim (73,049-row map side, unique key), inner, probe side 4 int64 columns, 7 output columns (BASELINE.json configs[3], join)"
+ALG_BYTES_PER_ROW = {"M2": 32.0, "M1": 16.0, "M0": 24.0, "M3": 64.0, "M4": 88.0}
 
 
 def env_int(name, default):
@@ -318,6 +320,97 @@ class Runner:
         self.cols = None
 
 
+def torch_murmur3_pid(torch, k, parts):
+    """pmod(murmur3_x86_32(le_bytes(int64 k), seed 42), parts) with int64 tensor arithmetic (hash/mur.rs:19-87) — independent of the library's kernel"""
+    M = 0xFFFFFFFF
+    def mul(a, b): return (a * b) & M
+    def rotl(x, r): return ((x << r) | (x >> (32 - r))) & M
+    def mix_k1(k1): return mul(rotl(mul(k1, 0xcc9e2d51), 15), 0x1b873593)
+    def mix_h1(h1, k1): return (mul(rotl(h1 ^ k1, 13), 5) + 0xe6546b64) & M
+    lo, hi = k & M, (k >> 32) & M
+    h = mix_h1(mix_h1(torch.full_like(k, 42), mix_k1(lo)), mix_k1(hi))
+    h = h ^ 8
+    h = h ^ (h >> 16); h = mul(h, 0x85ebca6b); h = h ^ (h >> 13); h = mul(h, 0xc2b2ae35); h = h ^ (h >> 16)
+    signed = torch.where(h >= 2**31, h - 2**32, h)
+    return torch.remainder(signed, parts)
+
+
+def extra_shuffle_and_join(torch, dist, native, world, local, dev, rows, steps, warmup, peak, peak_src, seed):
+    """M3 (shuffle write) and M4 (hash join): device-resident steps, kernel time from the library's own CUDA events, verified"""
+    from blaze_b200 import exprs as E, plans as PL, types as T
+    out = []
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    ri = lambda lo, hi: torch.randint(lo, hi, (rows,), dtype=torch.int64, device=dev, generator=gen)
+    ND = 73049
+    cols = [ri(0, ND), ri(0, K1_CARD), ri(0, K2_CARD), ri(-10**6, 10**6)]                    # ss_sold_date_sk, k1, k2, v
+    names = ["sk", "k1", "k2", "v"]
+    ins = T.Schema([T.Field(n, T.int64, False) for n in names])
+    batch = lambda: native.DeviceBatch([(c.data_ptr(), 0, rows) for c in cols], rows, local, keepalive=tuple(cols))
+    stats = {"ns": 0, "rows": 0, "launches": 0, "all": 0}
+    # ---- M3
+    P = 200
+    plan3 = PL.ShuffleWriterExec(PL.MemoryExec(ins), ("hash", [E.Column("k1")], P), "", "").plan_bytes()
+    conf3 = native.default_conf(shuffle_output_on_device=1)
+    keep = {}
+    def step3():
+        with native.NativeOp(plan3, conf3, local) as op:
+            op.push_device(batch()); op.finish()
+            m = op.metrics()
+            stats["ns"] += m["hot_kernel_ns"]; stats["rows"] += m["hot_kernel_rows"]; stats["launches"] += m["hot_kernel_launches"]; stats["all"] += m["gpu_kernel_launches"]
+            keep["chunks"] = [(c["rows"], c["part_rows"], c["part_off"]) for c in op.shuffle_chunks()]
+    for _ in range(warmup): step3()
+    for k_ in stats: stats[k_] = 0
+    ms = timed(torch, dist, world, dev, step3, steps, 0)
+    pid = torch_murmur3_pid(torch, cols[1], P)
+    exp = torch.bincount(pid, minlength=P).cpu()
+    got = torch.zeros(P, dtype=torch.int64)
+    for _, pr, _ in keep["chunks"]: got += torch.tensor(pr, dtype=torch.int64)
+    rec = lambda m: (1 if m < 128 else 2 if m < 16384 else 3 if m < 2**21 else 4) + 4 + 32 * m
+    exp_bytes = sum(((t - 1) // 10000) * rec(10000) + rec(t - ((t - 1) // 10000) * 10000) for _, pr, _ in keep["chunks"] for t in pr if t)
+    ok3 = bool(torch.equal(got, exp)) and sum(po[-1] for _, _, po in keep["chunks"]) == exp_bytes
+    ach = ALG_BYTES_PER_ROW["M3"] * stats["rows"] / max(1, stats["ns"])
+    out.append({"workload": WORKLOADS["M3"], "value": rows * world / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rows_per_gpu": rows, "verified": ok3,
+                "verification": "rows per partition == bincount of an independent torch murmur3; encoded bytes == the batch_serde size formula (contents: tests/test_gpu_shuffle_writer.py)",
+                "gpu_launches": stats["all"], "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                                           "kernel": "shuffle_pids_kernel + shuffle_encode_kernel", "launches": stats["launches"], "avg_launch_ms": stats["ns"] / max(1, stats["launches"]) / 1e6,
+                                                           "alg_bytes_per_row": ALG_BYTES_PER_ROW["M3"]}})
+    # ---- M4
+    d_sk = torch.arange(ND, dtype=torch.int64, device=dev)
+    bcols = [d_sk, 1900 + d_sk // 366, (d_sk // 30) % 12 + 1]
+    sd = T.Schema([T.Field(n, T.int64, False) for n in ("d_date_sk", "d_year", "d_moy")])
+    build = PL.BroadcastJoinBuildHashMapExec(PL.MemoryExec(sd), [E.Column("d_date_sk")])
+    join = PL.BroadcastJoinExec(PL.build_join_schema(ins, sd, PL.JOIN_INNER), PL.MemoryExec(ins), build, [(E.Column("sk"), E.Column("d_date_sk"))], PL.JOIN_INNER, PL.RIGHT_SIDE, True, "m").plan_bytes()
+    for k_ in stats: stats[k_] = 0
+    def step4():
+        with native.NativeOp(build.plan_bytes(), None, local) as bop:                         # the map side is rebuilt every step (73,049 rows)
+            bop.push_device(native.DeviceBatch([(c.data_ptr(), 0, ND) for c in bcols], ND, local, keepalive=tuple(bcols))); bop.finish()
+            with native.NativeOp(join, None, local) as op:
+                op.attach_build(bop)
+                op.push_device(batch()); op.finish()
+                n_out, ysum = 0, 0
+                while True:
+                    o = op.pull_device()
+                    if o is None: break
+                    n_out += o.array.length
+                    if keep.get("check"): ysum += int(device_cols(o, torch)[5].sum().item())
+                    native.release_device_array(o)
+                m = op.metrics()
+                stats["ns"] += m["hot_kernel_ns"]; stats["rows"] += m["hot_kernel_rows"]; stats["launches"] += m["hot_kernel_launches"]; stats["all"] += m["gpu_kernel_launches"]
+                keep["join"] = (n_out, ysum)
+    for _ in range(warmup): step4()
+    for k_ in stats: stats[k_] = 0
+    ms = timed(torch, dist, world, dev, step4, steps, 0)
+    st = dict(stats); keep["check"] = True; step4()
+    ok4 = keep["join"] == (rows, int((1900 + cols[0] // 366).sum().item()))
+    ach = ALG_BYTES_PER_ROW["M4"] * st["rows"] / max(1, st["ns"])
+    out.append({"workload": WORKLOADS["M4"], "value": rows * world / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rows_per_gpu": rows, "verified": ok4,
+                "verification": "output rows == probe rows (every key matches a unique map key) and SUM(d_year) over the output == SUM(1900 + sk // 366) over the probe side",
+                "gpu_launches": st["all"], "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                                        "kernel": "join_probe_pairs_kernel + join_gather_kernel x 7 (per 2^24-row probe chunk)", "launches": st["launches"],
+                                                        "avg_launch_ms": st["ns"] / max(1, st["launches"]) / 1e6, "alg_bytes_per_row": ALG_BYTES_PER_ROW["M4"]}})
+    return out, ok3, ok4
+
+
 def timed(torch, dist, world, dev, fn, steps, warmup):
     """W untimed steps, then exactly K steps between barrier + synchronize, device-timed, max over ranks -> ms per step"""
     def barrier():
@@ -468,6 +561,14 @@ def run_ours(args):
                       "rows_per_gpu": extra_rows, "verified": ok, "gpu_launches": r.stats["launches"], "roofline": roofline_of(w, r.stats, extra_rows, peak, peak_src)})
         r.close(); del r
         torch.cuda.empty_cache()
+
+    x_rows = env_int("B200Q_BENCH_X_ROWS", min(extra_rows, 1 << 28))
+    xs, ok3, ok4 = extra_shuffle_and_join(torch, dist, native, world, local, dev, x_rows, max(1, min(args.steps, 5)), 3, peak, peak_src, 48 + 1000 * rank)
+    extra += xs
+    verified["M3"], verified["M4"] = {"ok": ok3}, {"ok": ok4}
+    if not ok3: failures.append("M3")
+    if not ok4: failures.append("M4")
+    torch.cuda.empty_cache()
 
     if exchange is not None:
         exchange.close()
