@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels_shuffle.cuh"
 
@@ -109,6 +110,29 @@ __device__ __forceinline__ void or_bit(uint8_t* out, unsigned long long byte_off
 
 constexpr int ENC_NT = 512, ENC_RPT = SHUF_TILE / ENC_NT;
 
+// ---- TMA (cp.async.bulk) staging of the input columns -------------------------------------------------------------------
+// One elected thread copies a whole tile of a column (4096 values, contiguous in HBM) into shared memory with ONE bulk copy
+// that completes on an mbarrier; two buffers, so the copy of the next column (or of the next tile's first column) is in
+// flight while the current one is permuted and written out, and the first copy of a tile overlaps its ranking phase.
+#ifndef B200Q_EMULATED_DEVICE
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void*, const void*, unsigned, unsigned long long*) {}
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+#endif
+
 // where sorted position `i` of the tile lands: byte offset of its record + its row inside the record; rows of that record
 __device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsigned long long F, unsigned B, unsigned p, unsigned idx, const unsigned long long* __restrict__ counts,
                                                        const unsigned long long* __restrict__ part_off, unsigned& m, unsigned& j) {
@@ -118,16 +142,18 @@ __device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsign
   return part_off[p] + (unsigned long long)rec * F;
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpec sp, const uint16_t* __restrict__ pids, long long n, const unsigned long long* __restrict__ counts,
                                                                    const unsigned long long* __restrict__ part_off, unsigned long long* cursors, uint8_t* out) {
 #ifdef B200Q_EMULATED_DEVICE                                                 // tools/emu: blocks run one at a time, shared memory is a static array
-  static unsigned long long smem_words[(SHUF_TILE * 10 + SHUF_MAX_PARTS * 16) / 8];
+  static unsigned long long smem_words[(SHUF_TILE * 26 + SHUF_MAX_PARTS * 16) / 8];
   unsigned char* smem = (unsigned char*)smem_words;
 #else
   extern __shared__ __align__(16) unsigned char smem[];
 #endif
   const int P = sp.num_partitions;
-  unsigned long long* s_val = (unsigned long long*)smem;                    // SHUF_TILE values in partition order
+  unsigned long long* s_in = (unsigned long long*)smem;                     // TMA: two input buffers of SHUF_TILE values (input order)
+  unsigned long long* s_val = s_in + (TMA ? 2 * SHUF_TILE : 0);             // SHUF_TILE values in partition order
   unsigned long long* s_gbase = s_val + SHUF_TILE;                          // P: index inside the partition of the tile's first row of it
   unsigned* s_cnt = (unsigned*)(s_gbase + P);                               // P: rows of the tile per partition
   unsigned* s_start = s_cnt + P;                                            // P: exclusive prefix of s_cnt
@@ -138,6 +164,30 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
   const uint32_t vlB = shuf_varint_len(B);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = (n + SHUF_TILE - 1) / SHUF_TILE;
+  // TMA load sequence of this CTA: load j = column s_ec[j % ne] of the CTA's (j / ne)-th tile, into buffer j & 1
+  __shared__ unsigned long long s_bar[2];                               // 8-byte aligned by type
+  __shared__ unsigned char s_ec[SHUF_MAX_COLS];
+  __shared__ int s_ne;
+  unsigned consumed = 0;
+  auto issue = [&](unsigned j) {
+    if (!TMA || s_ne == 0) return;
+    const long long tl = blockIdx.x + (long long)(j / (unsigned)s_ne) * gridDim.x;
+    if (tl >= ntiles || (tl + 1) * SHUF_TILE > n) return;                   // only full tiles are staged by bulk copies
+    const int c = s_ec[j % (unsigned)s_ne];
+    const unsigned w = sp.col[c].width, bytes = SHUF_TILE * w;
+    mbar_expect_tx(&s_bar[j & 1], bytes);
+    bulk_g2s(s_in + (size_t)(j & 1) * SHUF_TILE, (const uint8_t*)sp.col[c].values + (size_t)tl * SHUF_TILE * w, bytes, &s_bar[j & 1]);
+  };
+  if (TMA) {
+    if (tid == 0) {
+      int ne = 0;
+      for (int c = 0; c < sp.ncols; c++) if (sp.col[c].tma) s_ec[ne++] = (unsigned char)c;
+      s_ne = ne;
+      mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) { issue(0); issue(1); }
+  }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long t0 = tile * SHUF_TILE;
     const int rows = (int)min((long long)SHUF_TILE, n - t0);
@@ -201,7 +251,24 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
       // data region of column c inside a full record
       const unsigned long long off_full = (unsigned long long)vlB + (unsigned)c + (unsigned long long)sp.col[c].k8 * B8 + (unsigned long long)sp.col[c].kw * B + 1 + (nullable ? B8 : 0);
       for (int h = 0; h < nh; h++) {
-        if (width == 8) {
+        const bool staged = TMA && sp.col[c].tma && rows == SHUF_TILE;
+        if (staged) {                                                       // the column's tile is (being) copied into s_in[consumed & 1]
+          mbar_wait(&s_bar[consumed & 1], (consumed >> 1) & 1);
+          const unsigned long long* in = s_in + (size_t)(consumed & 1) * SHUF_TILE;
+          if (width == 8) {
+#pragma unroll
+            for (int k = 0; k < ENC_RPT; k++) s_val[lpos[k]] = in[k * ENC_NT + tid];
+          } else if (width == 4) {
+#pragma unroll
+            for (int k = 0; k < ENC_RPT; k++) s_val[lpos[k]] = ((const uint32_t*)in)[k * ENC_NT + tid];
+          } else if (width == 2) {
+#pragma unroll
+            for (int k = 0; k < ENC_RPT; k++) s_val[lpos[k]] = ((const uint16_t*)in)[k * ENC_NT + tid];
+          } else {
+#pragma unroll
+            for (int k = 0; k < ENC_RPT; k++) s_val[lpos[k]] = ((const uint8_t*)in)[k * ENC_NT + tid];
+          }
+        } else if (width == 8) {
 #pragma unroll
           for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const unsigned long long*)values)[t0 + i]; }
         } else if (width == 4) {
@@ -218,6 +285,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
           for (int k = 0; k < ENC_RPT; k++) { const int i = k * ENC_NT + tid; if (i < rows) s_val[lpos[k]] = ((const uint8_t*)values)[t0 + i]; }
         }
         __syncthreads();
+        if (staged) { if (tid == 0) issue(consumed + 2); consumed++; }     // the buffer just read is free: start the copy two loads ahead
 #pragma unroll
         for (int k = 0; k < ENC_RPT; k++) {
           const int i = k * ENC_NT + tid;
@@ -286,13 +354,25 @@ int launch_shuffle_layout(const ShufSpec& sp, const unsigned long long* d_counts
 int launch_shuffle_encode(const ShufSpec& sp, const uint16_t* d_pids, int64_t n, const unsigned long long* d_counts, const unsigned long long* d_part_off,
                           unsigned long long* d_cursors, uint8_t* d_out, cudaStream_t s) {
   if (n <= 0) return 0;
-  const size_t smem = (size_t)SHUF_TILE * 8 + (size_t)sp.num_partitions * 16 + (size_t)SHUF_TILE * 2;
+  ShufSpec spx = sp;
+  bool tma = false;
 #ifndef B200Q_EMULATED_DEVICE
-  cudaFuncSetAttribute(shuffle_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHUF_TILE * 10 + SHUF_MAX_PARTS * 16);      // per device: cheap, idempotent
+  static const bool no_tma = getenv("B200Q_SHUFFLE_NO_TMA") != nullptr;                     // A/B measurements
+  for (int c = 0; c < spx.ncols; c++) {                                                     // bulk copies need 16-byte aligned sources
+    ShufCol& col = spx.col[c];
+    col.tma = !no_tma && (col.width == 1 || col.width == 2 || col.width == 4 || col.width == 8) && ((uintptr_t)col.values & 15) == 0 && n >= SHUF_TILE;
+    tma = tma || col.tma;
+  }
 #endif
+  const size_t smem = (size_t)SHUF_TILE * (tma ? 24 : 8) + (size_t)spx.num_partitions * 16 + (size_t)SHUF_TILE * 2;
   const int64_t ntiles = (n + SHUF_TILE - 1) / SHUF_TILE;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * 2));
-  shuffle_encode_kernel<<<grid, ENC_NT, smem, s>>>(sp, d_pids, n, d_counts, d_part_off, d_cursors, d_out);
+#ifndef B200Q_EMULATED_DEVICE
+  cudaFuncSetAttribute(shuffle_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHUF_TILE * 10 + SHUF_MAX_PARTS * 16);      // per device: cheap, idempotent
+  cudaFuncSetAttribute(shuffle_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHUF_TILE * 26 + SHUF_MAX_PARTS * 16);
+  if (tma) { shuffle_encode_kernel<true><<<grid, ENC_NT, smem, s>>>(spx, d_pids, n, d_counts, d_part_off, d_cursors, d_out); return 1; }
+#endif
+  shuffle_encode_kernel<false><<<grid, ENC_NT, smem, s>>>(spx, d_pids, n, d_counts, d_part_off, d_cursors, d_out);
   return 1;
 }
 

@@ -20,7 +20,8 @@ struct ShufCol {
   uint32_t bit_offset;                      // Arrow offset for validity / Boolean values
   uint8_t width;                            // 0: Boolean (bits), else 1, 2, 4, 8, 16 bytes
   uint8_t nullable;                         // the field is nullable: the record carries a validity bitmap for it
-  uint8_t _pad[2];
+  uint8_t tma;                              // set by the launcher: the column's tiles are staged by cp.async.bulk (16-byte aligned, width 1/2/4/8)
+  uint8_t _pad[1];
   uint32_t k8, kw;                          // columns before this one take k8 * ceil(m/8) + kw * m bytes (+ one flag byte each)
 };
 
