@@ -240,31 +240,40 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
     if (!map_joined_ && (build_outer_ || (semi_like_ && !probe_is_join_side_))) map_joined_ = DevMem::alloc((size_t)built_->rows + 16, cx.stream, true);
   }
 
-  // one output column = gather of a probe-side or build-side column through an index vector
-  DevColumn gather(OpContext& cx, const DType& type, const void* src, const uint8_t* vbits, uint32_t bit_off, const uint8_t* vbytes, const uint32_t* idx, int64_t n, bool may_be_null) {
-    DevColumn o; o.type = type;
-    const int w = type.byte_width();
-    o.values = DevMem::alloc((size_t)n * w + 16, cx.stream);
-    DevMemP ob = may_be_null ? DevMem::alloc((size_t)n + 16, cx.stream) : nullptr;
-    cx.m.launches += launch_join_gather(src, vbits, bit_off, vbytes, w, idx, n, o.values->ptr, ob ? (uint8_t*)ob->ptr : nullptr, cx.stream);
-    if (ob) { o.validity = DevMem::alloc(bitmap_bytes(n), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)ob->ptr, (uint32_t*)o.validity->ptr, n, cx.stream); }
-    return o;
+  // all columns of one side through one index vector: one kernel per 16 columns
+  struct Src { DType type; const void* values; const uint8_t* vbits; uint32_t bit_offset; const uint8_t* vbytes; bool may_be_null; };
+  std::vector<DevColumn> gather_all(OpContext& cx, const std::vector<Src>& srcs, const uint32_t* idx, int64_t n) {
+    std::vector<DevColumn> out; std::vector<DevMemP> valid_bytes;
+    for (size_t c0 = 0; c0 < srcs.size(); c0 += 16) {
+      GatherSpec g{}; g.ncols = (int)std::min<size_t>(16, srcs.size() - c0);
+      for (int c = 0; c < g.ncols; c++) {
+        const Src& s = srcs[c0 + (size_t)c];
+        DevColumn o; o.type = s.type;
+        const int w = s.type.byte_width();
+        o.values = DevMem::alloc((size_t)n * w + 16, cx.stream);
+        DevMemP ob = s.may_be_null ? DevMem::alloc((size_t)n + 16, cx.stream) : nullptr;
+        g.col[c] = GatherCol{s.values, s.vbits, s.vbytes, o.values->ptr, ob ? (uint8_t*)ob->ptr : nullptr, s.bit_offset, w};
+        out.push_back(o); valid_bytes.push_back(ob);
+      }
+      cx.m.launches += launch_join_gather_multi(g, idx, n, cx.stream);
+    }
+    for (size_t c = 0; c < out.size(); c++)
+      if (valid_bytes[c]) { out[c].validity = DevMem::alloc(bitmap_bytes(n), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)valid_bytes[c]->ptr, (uint32_t*)out[c].validity->ptr, n, cx.stream); }
+    return out;
   }
   std::vector<DevColumn> gather_probe(OpContext& cx, const DevBatch& in, const uint32_t* idx, int64_t n, bool nil_possible) {
-    std::vector<DevColumn> out;
-    for (size_t c = 0; c < in.cols.size(); c++) {
-      const DevColumn& s = in.cols[c];
+    std::vector<Src> srcs;
+    for (auto& s : in.cols) {
       const int w = s.type.byte_width();
-      out.push_back(gather(cx, s.type, (const uint8_t*)s.values->ptr + (size_t)s.offset * w, s.validity ? (const uint8_t*)s.validity->ptr : nullptr, (uint32_t)s.offset, nullptr, idx, n, nil_possible || s.validity));
+      srcs.push_back(Src{s.type, (const uint8_t*)s.values->ptr + (size_t)s.offset * w, s.validity ? (const uint8_t*)s.validity->ptr : nullptr, (uint32_t)s.offset, nullptr, nil_possible || (bool)s.validity});
     }
-    return out;
+    return gather_all(cx, srcs, idx, n);
   }
   std::vector<DevColumn> gather_build(OpContext& cx, const uint32_t* idx, int64_t n, bool nil_possible) {
-    std::vector<DevColumn> out;
+    std::vector<Src> srcs;
     for (size_t c = 0; c < built_->schema.fields.size(); c++)
-      out.push_back(gather(cx, built_->schema.fields[c].type, built_->values[c]->ptr, nullptr, 0, built_->valid_bytes[c] ? (const uint8_t*)built_->valid_bytes[c]->ptr : nullptr, idx, n,
-                           nil_possible || built_->valid_bytes[c]));
-    return out;
+      srcs.push_back(Src{built_->schema.fields[c].type, built_->values[c]->ptr, nullptr, 0, built_->valid_bytes[c] ? (const uint8_t*)built_->valid_bytes[c]->ptr : nullptr, nil_possible || (bool)built_->valid_bytes[c]});
+    return gather_all(cx, srcs, idx, n);
   }
   std::vector<DevColumn> null_columns(OpContext& cx, const SchemaDef& s, int64_t n) {
     std::vector<DevColumn> out;

@@ -132,33 +132,52 @@ __global__ void __launch_bounds__(JB) join_mark_build_kernel(long long n, const 
   }
 }
 
-// Fused probe of the pair-producing joins (Inner / Left / Right / Full): lookup, then the warp reserves the output rows of its
-// 32 probe rows with ONE atomic on `cursor` and every lane writes its (probe row, build row) pairs — no per-row
-// intermediates and no scan; the order of the output rows is whatever the reservation order is (not a contract).
+// Fused probe of the pair-producing joins (Inner / Left / Right / Full): lookup, then the CTA reserves the output rows of its
+// 2048 consecutive probe rows with ONE atomic on `cursor` (block scan of the match counts) and every thread writes its
+// (probe row, build row) pairs — no per-row intermediates, no global scan.  The output rows of a tile are contiguous and
+// come from a contiguous input range, so the gathers that follow read near-streaming; the order is not a contract.
 // pidx == null: only count (cursor += matches), for build sides with duplicated keys whose output size is not bounded by n.
+constexpr int JP_ROWS = 8;
 __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
                                                               uint32_t* __restrict__ pidx, uint32_t* __restrict__ bidx, uint8_t* mark) {
-  const unsigned lane = threadIdx.x & 31;
-  const long long nround = (n + 31) & ~31LL;
-  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < nround; i += (long long)gridDim.x * JB) {
-    unsigned long long w[2];
-    uint32_t h = JOIN_NIL; unsigned c = 0;
-    if (i < n) {
-      if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) { h = t.head[slot]; c = t.count[slot]; } }
-      if (probe_outer && c == 0) c = 1;
+  __shared__ unsigned s_warp[JB / 32];
+  __shared__ unsigned long long s_base;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ntiles = (n + JB * JP_ROWS - 1) / (JB * JP_ROWS);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = tile * (JB * JP_ROWS);
+    uint32_t h[JP_ROWS]; unsigned c[JP_ROWS]; unsigned mine = 0;
+#pragma unroll
+    for (int r = 0; r < JP_ROWS; r++) {
+      const long long i = t0 + r * JB + threadIdx.x;
+      unsigned long long w[2];
+      h[r] = JOIN_NIL; c[r] = 0;
+      if (i < n) {
+        if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) { h[r] = t.head[slot]; c[r] = t.count[slot]; } }
+        if (probe_outer && c[r] == 0) c[r] = 1;
+      }
+      mine += c[r];
     }
-    unsigned inc = c;
+    unsigned inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-    const unsigned total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-    if (total == 0) continue;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (!pidx || c == 0) continue;
-    unsigned long long o = base + inc - c;
-    if (h == JOIN_NIL) { pidx[o] = (uint32_t)i; bidx[o] = JOIN_NIL; continue; }                       // unmatched outer row
-    for (uint32_t b = h; b != JOIN_NIL; b = t.next[b], o++) { pidx[o] = (uint32_t)i; bidx[o] = b; if (mark) mark[b] = 1; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+    for (int w = 0; w < JB / 32; w++) { const unsigned v = s_warp[w]; if (w < (int)warp) before += v; total += v; }
+    if (threadIdx.x == 0 && total) s_base = atomicAdd(cursor, (unsigned long long)total);
+    __syncthreads();
+    if (pidx && mine) {
+      unsigned long long o = s_base + before + inc - mine;
+#pragma unroll
+      for (int r = 0; r < JP_ROWS; r++) {
+        if (c[r] == 0) continue;
+        const uint32_t i = (uint32_t)(t0 + r * JB + threadIdx.x);
+        if (h[r] == JOIN_NIL) { pidx[o] = i; bidx[o] = JOIN_NIL; o++; continue; }                     // unmatched outer row
+        for (uint32_t b = h[r]; b != JOIN_NIL; b = t.next[b], o++) { pidx[o] = i; bidx[o] = b; if (mark) mark[b] = 1; }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -211,6 +230,31 @@ __global__ void __launch_bounds__(JB) join_gather_kernel(const T* __restrict__ s
 
 struct u128 { unsigned long long a, b; };
 
+// all output columns of one side in ONE pass over the index vector: column c of row i = src_c[idx[i]] (NULL when idx is NIL or
+// the source value is NULL); validity leaves as one byte per row
+__global__ void __launch_bounds__(JB) join_gather_multi_kernel(const GatherSpec g, const uint32_t* __restrict__ idx, long long n) {
+  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
+    const uint32_t j = idx[i];
+    for (int c = 0; c < g.ncols; c++) {
+      const GatherCol col = g.col[c];
+      uint8_t ok = 0;
+      if (j != JOIN_NIL) {
+        ok = 1;
+        if (col.vbytes) ok = col.vbytes[j];
+        else if (col.vbits) { const unsigned long long bi = (unsigned long long)j + col.bit_offset; ok = (col.vbits[bi >> 3] >> (bi & 7)) & 1; }
+      }
+      switch (col.width) {
+        case 1: ((uint8_t*)col.out)[i] = ok ? ((const uint8_t*)col.src)[j] : 0; break;
+        case 2: ((uint16_t*)col.out)[i] = ok ? ((const uint16_t*)col.src)[j] : 0; break;
+        case 4: ((uint32_t*)col.out)[i] = ok ? ((const uint32_t*)col.src)[j] : 0; break;
+        case 8: ((unsigned long long*)col.out)[i] = ok ? ((const unsigned long long*)col.src)[j] : 0; break;
+        default: { u128 v{0, 0}; if (ok) v = ((const u128*)col.src)[j]; ((u128*)col.out)[i] = v; break; }
+      }
+      if (col.out_valid) col.out_valid[i] = ok;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(JB) unpack_bits_kernel(const uint8_t* __restrict__ bits, uint32_t bit_offset, long long n, uint8_t* __restrict__ bytes) {
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
     const unsigned long long bi = (unsigned long long)i + bit_offset;
@@ -255,7 +299,7 @@ int launch_join_mark_build(int64_t n, const JoinTable& t, const uint32_t* d_head
 }
 int launch_join_probe_pairs(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s) {
   if (n <= 0) return 0;
-  join_probe_pairs_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_cursor, d_pidx, d_bidx, mark);
+  join_probe_pairs_kernel<<<jgrid(n, JB * JP_ROWS), JB, 0, s>>>(k, n, t, probe_outer, d_cursor, d_pidx, d_bidx, mark);
   return 1;
 }
 int launch_join_probe_select(const JoinKeys& k, int64_t n, const JoinTable& t, int invert, unsigned long long* d_cursor, uint32_t* d_idx, cudaStream_t s) {
@@ -278,6 +322,11 @@ int launch_join_gather(const void* src, const uint8_t* vbits, uint32_t bit_offse
     case 8: join_gather_kernel<unsigned long long><<<g, JB, 0, s>>>((const unsigned long long*)src, vbits, bit_offset, vbytes, idx, n, (unsigned long long*)out, out_valid); break;
     default: join_gather_kernel<u128><<<g, JB, 0, s>>>((const u128*)src, vbits, bit_offset, vbytes, idx, n, (u128*)out, out_valid); break;
   }
+  return 1;
+}
+int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n, cudaStream_t s) {
+  if (n <= 0 || g.ncols == 0) return 0;
+  join_gather_multi_kernel<<<jgrid(n), JB, 0, s>>>(g, idx, n);
   return 1;
 }
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s) {

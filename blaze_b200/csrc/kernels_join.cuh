@@ -49,6 +49,10 @@ int launch_join_mark_build(int64_t n, const JoinTable& t, const uint32_t* d_head
 // out[i] = idx[i] == JOIN_NIL ? NULL : src[idx[i]]   (width bytes per value; src_valid / out_valid: one byte per row, may be null)
 int launch_join_gather(const void* src, const uint8_t* src_valid_bits, uint32_t src_bit_offset, const uint8_t* src_valid_bytes, int width, const uint32_t* idx, int64_t n,
                        void* out, uint8_t* out_valid_bytes, cudaStream_t s);
+// the same for up to 16 columns that share one index vector, in one pass
+struct GatherCol { const void* src; const uint8_t* vbits; const uint8_t* vbytes; void* out; uint8_t* out_valid; uint32_t bit_offset; int32_t width; };
+struct GatherSpec { int32_t ncols; int32_t _pad; GatherCol col[16]; };
+int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n, cudaStream_t s);
 // bytes[i] = bit (i + bit_offset) of bits (all 1 when bits is null)
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s);
 // flags[i] = (head[i] != NIL) ^ invert, as int32 for the scan; idx[offs[i]] = i for rows whose flag is set
