@@ -197,6 +197,17 @@ class Runner:
         """input resident in HBM -> result resident in HBM (kept for the verification of the last step)"""
         native = self.native
         self._drop_last()
+        if os.environ.get("B200Q_BENCH_PHASES") and self.world == 1:                       # where a step's time goes (host clock, each phase synchronised)
+            t = [time.perf_counter()]
+            def lap(): self.torch.cuda.synchronize(); t.append(time.perf_counter())
+            op = native.NativeOp(self.plans["single"], self.conf, self.local); lap()
+            op.push_device(self._input_batch()); op.sync(); lap()
+            op.finish(); lap()
+            self.last = self._pull_all_device(op); lap()
+            m = op.metrics(); self._acc(m); op.close(); lap()
+            names = ["create", "push(update kernels)", "finish(emit + Final stage)", "pull", "destroy"]
+            sys.stderr.write("phases[%s] " % self.w + ", ".join(f"{n}={1e3 * (b - a):.3f}ms" for n, a, b in zip(names, t, t[1:])) + f", hot_kernels={m['hot_kernel_ns'] / 1e6:.3f}ms, launches={m['gpu_kernel_launches']}\n")
+            return
         if self.w == "M0" or self.world == 1:
             with native.NativeOp(self.plans["single"], self.conf, self.local) as op:
                 op.push_device(self._input_batch())

@@ -68,6 +68,7 @@ __device__ __forceinline__ uint64_t agg_find_or_insert(const AggLayout& lay, con
     const unsigned t = (unsigned)hdr;
     unsigned flags = (unsigned)(hdr >> 32);
     if (t == tag) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");                          // pairs with the inserter's st.release: key words / identities are visible before they are read or RED-ed
       bool eq = (flags >> 16) == knull;
       for (int i = 0; eq && i < lay.nkw; i++) eq = ld_relaxed_u64(ke + 1 + i) == kw[i];
       if (eq) { *flags_out = flags; return s; }
