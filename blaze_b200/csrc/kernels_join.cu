@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(JB) join_mark_build_kernel(long long n, const 
 // Fused probe of the pair-producing joins (Inner / Left / Right / Full): lookup, then the CTA reserves the output rows of its
 // 2048 consecutive probe rows with ONE atomic on `cursor` (block scan of the match counts) and every thread writes its
 // (probe row, build row) pairs — no per-row intermediates, no global scan.  The output rows of a tile are contiguous and
-// come from a contiguous input range, so the gathers that follow read near-streaming; the order is not a contract.
+// keep the input order inside the tile (a thread owns 8 consecutive rows), so the gathers that follow read streaming; the
+// order of the tiles is not a contract.
 // pidx == null: only count (cursor += matches), for build sides with duplicated keys whose output size is not bounded by n.
 constexpr int JP_ROWS = 8;
 __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, 
     uint32_t h[JP_ROWS]; unsigned c[JP_ROWS]; unsigned mine = 0;
 #pragma unroll
     for (int r = 0; r < JP_ROWS; r++) {
-      const long long i = t0 + r * JB + threadIdx.x;
+      const long long i = t0 + (long long)threadIdx.x * JP_ROWS + r;         // a thread owns 8 CONSECUTIVE rows: the tile's output keeps the input order
       unsigned long long w[2];
       h[r] = JOIN_NIL; c[r] = 0;
       if (i < n) {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, 
 #pragma unroll
       for (int r = 0; r < JP_ROWS; r++) {
         if (c[r] == 0) continue;
-        const uint32_t i = (uint32_t)(t0 + r * JB + threadIdx.x);
+        const uint32_t i = (uint32_t)(t0 + (long long)threadIdx.x * JP_ROWS + r);
         if (h[r] == JOIN_NIL) { pidx[o] = i; bidx[o] = JOIN_NIL; o++; continue; }                     // unmatched outer row
         for (uint32_t b = h[r]; b != JOIN_NIL; b = t.next[b], o++) { pidx[o] = i; bidx[o] = b; if (mark) mark[b] = 1; }
       }

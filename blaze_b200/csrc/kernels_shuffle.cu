@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "kernels_shuffle.cuh"
+#include "tma.cuh"
 
 namespace b200q {
 
@@ -108,34 +109,16 @@ __device__ __forceinline__ void or_bit(uint8_t* out, unsigned long long byte_off
   atomicOr((unsigned*)(uintptr_t)(a & ~3ull), 1u << (((unsigned)(a & 3ull) << 3) + bit));
 }
 
-constexpr int ENC_NT = 512, ENC_RPT = SHUF_TILE / ENC_NT;
+constexpr int ENC_NT = 512, ENC_RPT = SHUF_TILE / ENC_NT, SHUF_SMEM_PARTS = 512;
 
 // ---- TMA (cp.async.bulk) staging of the input columns -------------------------------------------------------------------
 // One elected thread copies a whole tile of a column (4096 values, contiguous in HBM) into shared memory with ONE bulk copy
 // that completes on an mbarrier; two buffers, so the copy of the next column (or of the next tile's first column) is in
 // flight while the current one is permuted and written out, and the first copy of a tile overlaps its ranking phase.
-#ifndef B200Q_EMULATED_DEVICE
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-#else
-__device__ __forceinline__ void mbar_init(unsigned long long*, unsigned) {}
-__device__ __forceinline__ void mbar_fence_init() {}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(void*, const void*, unsigned, unsigned long long*) {}
-__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
-#endif
 
 // where sorted position `i` of the tile lands: byte offset of its record + its row inside the record; rows of that record
-__device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsigned long long F, unsigned B, unsigned p, unsigned idx, const unsigned long long* __restrict__ counts,
-                                                       const unsigned long long* __restrict__ part_off, unsigned& m, unsigned& j) {
+__device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsigned long long F, unsigned B, unsigned p, unsigned idx, const unsigned long long* counts,
+                                                       const unsigned long long* part_off, unsigned& m, unsigned& j) {
   const unsigned t = (unsigned)counts[p], rec = idx / B, nrec = (t + B - 1) / B;
   j = idx - rec * B;
   m = rec == nrec - 1 ? t - rec * B : B;
@@ -143,8 +126,8 @@ __device__ __forceinline__ unsigned long long dest_of(const ShufSpec& sp, unsign
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpec sp, const uint16_t* __restrict__ pids, long long n, const unsigned long long* __restrict__ counts,
-                                                                   const unsigned long long* __restrict__ part_off, unsigned long long* cursors, uint8_t* out) {
+__global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpec sp, const uint16_t* __restrict__ pids, long long n, const unsigned long long* __restrict__ counts_g,
+                                                                   const unsigned long long* __restrict__ part_off_g, unsigned long long* cursors, uint8_t* out) {
 #ifdef B200Q_EMULATED_DEVICE                                                 // tools/emu: blocks run one at a time, shared memory is a static array
   static unsigned long long smem_words[(SHUF_TILE * 26 + SHUF_MAX_PARTS * 16) / 8];
   unsigned char* smem = (unsigned char*)smem_words;
@@ -164,6 +147,14 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
   const uint32_t vlB = shuf_varint_len(B);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = (n + SHUF_TILE - 1) / SHUF_TILE;
+  // rows / byte offset of every partition are looked up once per row and tile: keep them in shared memory when they fit
+  __shared__ unsigned long long s_tab[2 * SHUF_SMEM_PARTS];
+  if (P <= SHUF_SMEM_PARTS) {
+    for (int p = tid; p < P; p += ENC_NT) { s_tab[p] = counts_g[p]; s_tab[SHUF_SMEM_PARTS + p] = part_off_g[p]; }
+    __syncthreads();
+  }
+  const unsigned long long* counts = P <= SHUF_SMEM_PARTS ? s_tab : counts_g;
+  const unsigned long long* part_off = P <= SHUF_SMEM_PARTS ? s_tab + SHUF_SMEM_PARTS : part_off_g;
   // TMA load sequence of this CTA: load j = column s_ec[j % ne] of the CTA's (j / ne)-th tile, into buffer j & 1
   __shared__ unsigned long long s_bar[2];                               // 8-byte aligned by type
   __shared__ unsigned char s_ec[SHUF_MAX_COLS];
@@ -293,7 +284,15 @@ __global__ void __launch_bounds__(ENC_NT, 2) shuffle_encode_kernel(const ShufSpe
             const unsigned long long v = s_val[i];
             if (full & (1u << k)) {
               uint8_t* a = out + wb[k] + off_full + (unsigned long long)(h * 8) * B;
-              for (int b = 0; b < nb; b++) a[(size_t)b * B] = (uint8_t)(v >> (8 * b));
+              if (nb == 8) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) { *a = (uint8_t)(v >> (8 * b)); a += B; }
+              } else if (nb == 4) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) { *a = (uint8_t)(v >> (8 * b)); a += B; }
+              } else {
+                for (int b = 0; b < nb; b++) { *a = (uint8_t)(v >> (8 * b)); a += B; }
+              }
             } else {                                                        // the short last record of a partition
               const unsigned p = s_p[i];
               unsigned m, j;
@@ -357,7 +356,9 @@ int launch_shuffle_encode(const ShufSpec& sp, const uint16_t* d_pids, int64_t n,
   ShufSpec spx = sp;
   bool tma = false;
 #ifndef B200Q_EMULATED_DEVICE
-  static const bool no_tma = getenv("B200Q_SHUFFLE_NO_TMA") != nullptr;                     // A/B measurements
+  // measured on B200 (profiles/r02_shapes_shuffle_*): the bulk-copy staging costs 64 KB more shared memory per CTA (a smaller L1 for the
+  // write-combining of the byte stores) and the kernel is bound by its store phase, not by the column loads: off unless asked for
+  static const bool no_tma = getenv("B200Q_SHUFFLE_TMA") == nullptr;
   for (int c = 0; c < spx.ncols; c++) {                                                     // bulk copies need 16-byte aligned sources
     ShufCol& col = spx.col[c];
     col.tma = !no_tma && (col.width == 1 || col.width == 2 || col.width == 4 || col.width == 8) && ((uintptr_t)col.values & 15) == 0 && n >= SHUF_TILE;
