@@ -301,7 +301,7 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
 
   void push(OpContext& cx, DevBatch& in, std::vector<DevBatch>& outs) override {
     need_built(cx);
-    const int64_t step = 1LL << 24;                    // bounds the per-launch index vectors and the int32 scan
+    const int64_t step = 1LL << 26;                    // bounds the per-launch index vectors / output columns
     for (int64_t r0 = 0; r0 < in.num_rows; r0 += step) {
       DevBatch part; part.num_rows = std::min(step, in.num_rows - r0);
       for (auto& c : in.cols) { DevColumn p = c; p.offset = c.offset + r0; part.cols.push_back(p); }
@@ -317,20 +317,48 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
     auto read_cursor = [&]() { unsigned long long v = 0; B200Q_CUDA(cudaMemcpyAsync(&v, cursor->ptr, 8, cudaMemcpyDeviceToHost, cx.stream)); B200Q_CUDA(cudaStreamSynchronize(cx.stream)); return (int64_t)v; };
     B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
     if (!semi_like_) {
-      // unique build keys (the PK side of a PK-FK join): at most one output row per probe row -> one fused pass; otherwise count first
-      int64_t cap = n;
-      if (built_->max_dup > 1) {
-        cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, nullptr, nullptr, nullptr, cx.stream);
-        cap = read_cursor();
-        B200Q_CUDA(cudaMemsetAsync(cursor->ptr, 0, 8, cx.stream));
-      }
-      if (cap > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "join: more than 2^31-1 output rows from one probe batch; push smaller batches");
-      if (cap > 0) {
-        DevMemP pidx = DevMem::alloc((size_t)cap * 4 + 16, cx.stream), bidx = DevMem::alloc((size_t)cap * 4 + 16, cx.stream);
-        cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, (uint32_t*)pidx->ptr, (uint32_t*)bidx->ptr,
-                                                 build_outer_ ? (uint8_t*)map_joined_->ptr : nullptr, cx.stream);
-        const int64_t total = read_cursor();
-        if (total > 0) emit(outs, gather_probe(cx, in, (const uint32_t*)pidx->ptr, total, false), gather_build(cx, (const uint32_t*)bidx->ptr, total, probe_outer_), total);
+      // count the output rows (keys only: 8 B/row), then
+      //   unique map keys (the PK side of a PK-FK join): ONE fused probe + gather pass writes the output columns in probe-row order;
+      //   duplicated map keys: (probe row, map row) pairs, then one gather pass per side
+      cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, nullptr, nullptr, nullptr, cx.stream);
+      const int64_t total = read_cursor();
+      if (total > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "join: more than 2^31-1 output rows from one probe batch; push smaller batches");
+      B200Q_CUDA(cudaMemsetAsync(cursor->ptr, 0, 8, cx.stream));
+      uint8_t* mark = build_outer_ ? (uint8_t*)map_joined_->ptr : nullptr;
+      if (total > 0 && built_->max_dup <= 1 && in.cols.size() <= 16 && built_->schema.fields.size() <= 16) {
+        GatherSpec pc{}, bc{};
+        std::vector<DevColumn> pcols, bcols; std::vector<DevMemP> pvb, bvb;
+        auto out_col = [&](const DType& t, bool may_be_null, GatherCol& g, std::vector<DevColumn>& cols, std::vector<DevMemP>& vbs) {
+          DevColumn o; o.type = t;
+          o.values = DevMem::alloc((size_t)total * t.byte_width() + 16, cx.stream);
+          DevMemP vb = may_be_null ? DevMem::alloc((size_t)total + 16, cx.stream) : nullptr;
+          g.out = o.values->ptr; g.out_valid = vb ? (uint8_t*)vb->ptr : nullptr; g.width = t.byte_width();
+          cols.push_back(o); vbs.push_back(vb);
+        };
+        pc.ncols = (int)in.cols.size();
+        for (int c = 0; c < pc.ncols; c++) {
+          const DevColumn& sc = in.cols[(size_t)c];
+          GatherCol& g = pc.col[c];
+          g.src = (const uint8_t*)sc.values->ptr + (size_t)sc.offset * sc.type.byte_width(); g.vbits = sc.validity ? (const uint8_t*)sc.validity->ptr : nullptr; g.bit_offset = (uint32_t)sc.offset; g.vbytes = nullptr;
+          out_col(sc.type, (bool)sc.validity, g, pcols, pvb);
+        }
+        bc.ncols = (int)built_->schema.fields.size();
+        for (int c = 0; c < bc.ncols; c++) {
+          GatherCol& g = bc.col[c];
+          g.src = built_->values[(size_t)c]->ptr; g.vbits = nullptr; g.bit_offset = 0; g.vbytes = built_->valid_bytes[(size_t)c] ? (const uint8_t*)built_->valid_bytes[(size_t)c]->ptr : nullptr;
+          out_col(built_->schema.fields[(size_t)c].type, probe_outer_ || built_->valid_bytes[(size_t)c], g, bcols, bvb);
+        }
+        cx.m.launches += launch_join_probe_fused(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, pc, bc, mark, cx.stream);
+        auto pack = [&](std::vector<DevColumn>& cols, std::vector<DevMemP>& vbs) {
+          for (size_t c = 0; c < cols.size(); c++)
+            if (vbs[c]) { cols[c].validity = DevMem::alloc(bitmap_bytes(total), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)vbs[c]->ptr, (uint32_t*)cols[c].validity->ptr, total, cx.stream); }
+        };
+        pack(pcols, pvb); pack(bcols, bvb);
+        emit(outs, pcols, bcols, total);
+      } else if (total > 0) {
+        DevMemP pidx = DevMem::alloc((size_t)total * 4 + 16, cx.stream), bidx = DevMem::alloc((size_t)total * 4 + 16, cx.stream);
+        cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, (uint32_t*)pidx->ptr, (uint32_t*)bidx->ptr, mark, cx.stream);
+        emit(outs, gather_probe(cx, in, (const uint32_t*)pidx->ptr, total, false), gather_build(cx, (const uint32_t*)bidx->ptr, total, probe_outer_), total);
       }
     } else {
       if (!probe_is_join_side_) cx.m.launches += launch_join_probe_mark(k, n, built_->table, (uint8_t*)map_joined_->ptr, cx.stream);

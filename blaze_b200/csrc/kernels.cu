@@ -483,8 +483,11 @@ int launch_filter_project_lean(const ColTable& cols, int ncols, const LeanFpSpec
     d.out[o].lit = sp.out[o].lit; d.out[o].dst = out_values[o];
   }
 #ifndef B200Q_EMULATED_DEVICE
-  {   // large batches: the TMA-staged single pass (16-byte aligned columns; B200Q_FILTER_TWO_PASS=1 keeps the round-1 two-pass form for A/B runs)
-    static const bool two_pass = getenv("B200Q_FILTER_TWO_PASS") != nullptr;
+  {   // large batches: the TMA-staged single pass exists (B200Q_FILTER_TMA=1) but is NOT the default: measured on B200 at 2^28 rows it runs at
+      // 1.12e11 rows/s (0.41 of the HBM peak) against 1.78e11 (0.65) for the two-pass form — with a fully resident grid walking the tiles in
+      // lockstep, every tile's look-back has to sum the aggregates of a whole wave (~440 tiles, 14 dependent L2 round trips) while a tile is only
+      // ~2 us of HBM time; the two-pass form already moves its 32 B/row at 87 % of the copy bandwidth (profiles/r02_shapes_m0_*.txt)
+    static const bool two_pass = getenv("B200Q_FILTER_TMA") == nullptr;
     bool aligned = true;
     for (int c = 0; c < ncols; c++) aligned = aligned && (((uintptr_t)d.col[c]) & 15) == 0;
     if (!two_pass && aligned && sp.nfilt && n >= FL_TWO_PASS_MIN_ROWS) {

@@ -256,6 +256,81 @@ __global__ void __launch_bounds__(JB) join_gather_multi_kernel(const GatherSpec 
   }
 }
 
+// Fused probe + gather of the pair-producing joins when the map side's keys are UNIQUE (the PK side of a PK-FK join: every probe
+// row has at most one partner).  One pass over the probe batch: lookup, ballots give every survivor its rank inside the tile in
+// ROW order, one atomic per 2048-row tile reserves the tile's output rows, and the probe-side columns are copied (coalesced in,
+// coalesced out) and the map-side columns gathered (L2-resident dimension table) straight into the output columns — no index
+// vectors at all.  `total` rows were counted by a first pass (join_probe_pairs_kernel without outputs), so the outputs are exact.
+__global__ void __launch_bounds__(JB) join_probe_fused_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
+                                                              const GatherSpec pc, const GatherSpec bc, uint8_t* mark) {
+  __shared__ unsigned s_cnt[JP_ROWS * (JB / 32) + 1];
+  __shared__ unsigned long long s_base;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1;
+  const long long ntiles = (n + JB * JP_ROWS - 1) / (JB * JP_ROWS);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = tile * (JB * JP_ROWS);
+    uint32_t h[JP_ROWS]; unsigned bal[JP_ROWS];
+#pragma unroll
+    for (int r = 0; r < JP_ROWS; r++) {
+      const long long i = t0 + r * JB + threadIdx.x;
+      unsigned long long w[2];
+      h[r] = JOIN_NIL; bool out = false;
+      if (i < n) {
+        if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) h[r] = t.head[slot]; }
+        out = h[r] != JOIN_NIL || probe_outer;
+      }
+      bal[r] = __ballot_sync(0xFFFFFFFFu, out);
+      if (lane == 0) s_cnt[r * (JB / 32) + warp] = __popc(bal[r]);
+      if (!out) h[r] = 0xFFFFFFFEu;                                        // no output row for this probe row
+    }
+    __syncthreads();
+    if (warp == 0) {                                                       // exclusive prefix of the 64 (round, warp) counts in row order
+      unsigned a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1], inc = a + b;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+      const unsigned total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+      s_cnt[2 * lane] = inc - a - b; s_cnt[2 * lane + 1] = inc - b;
+      if (lane == 0 && total) s_base = atomicAdd(cursor, (unsigned long long)total);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < JP_ROWS; r++) {
+      if (h[r] == 0xFFFFFFFEu) continue;
+      const long long i = t0 + r * JB + threadIdx.x;
+      const unsigned long long o = s_base + s_cnt[r * (JB / 32) + warp] + __popc(bal[r] & lt);
+      for (int c = 0; c < pc.ncols; c++) {
+        const GatherCol col = pc.col[c];
+        uint8_t ok = 1;
+        if (col.vbits) { const unsigned long long bi = (unsigned long long)i + col.bit_offset; ok = (col.vbits[bi >> 3] >> (bi & 7)) & 1; }
+        switch (col.width) {
+          case 1: ((uint8_t*)col.out)[o] = ((const uint8_t*)col.src)[i]; break;
+          case 2: ((uint16_t*)col.out)[o] = ((const uint16_t*)col.src)[i]; break;
+          case 4: ((uint32_t*)col.out)[o] = ((const uint32_t*)col.src)[i]; break;
+          case 8: ((unsigned long long*)col.out)[o] = ((const unsigned long long*)col.src)[i]; break;
+          default: ((u128*)col.out)[o] = ((const u128*)col.src)[i]; break;
+        }
+        if (col.out_valid) col.out_valid[o] = ok;
+      }
+      const uint32_t b = h[r];
+      if (b != JOIN_NIL && mark) mark[b] = 1;
+      for (int c = 0; c < bc.ncols; c++) {
+        const GatherCol col = bc.col[c];
+        uint8_t ok = b != JOIN_NIL;
+        if (ok && col.vbytes) ok = col.vbytes[b];
+        switch (col.width) {
+          case 1: ((uint8_t*)col.out)[o] = ok ? ((const uint8_t*)col.src)[b] : 0; break;
+          case 2: ((uint16_t*)col.out)[o] = ok ? ((const uint16_t*)col.src)[b] : 0; break;
+          case 4: ((uint32_t*)col.out)[o] = ok ? ((const uint32_t*)col.src)[b] : 0; break;
+          case 8: ((unsigned long long*)col.out)[o] = ok ? ((const unsigned long long*)col.src)[b] : 0; break;
+          default: { u128 v{0, 0}; if (ok) v = ((const u128*)col.src)[b]; ((u128*)col.out)[o] = v; break; }
+        }
+        if (col.out_valid) col.out_valid[o] = ok;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(JB) unpack_bits_kernel(const uint8_t* __restrict__ bits, uint32_t bit_offset, long long n, uint8_t* __restrict__ bytes) {
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
     const unsigned long long bi = (unsigned long long)i + bit_offset;
@@ -328,6 +403,12 @@ int launch_join_gather(const void* src, const uint8_t* vbits, uint32_t bit_offse
 int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n, cudaStream_t s) {
   if (n <= 0 || g.ncols == 0) return 0;
   join_gather_multi_kernel<<<jgrid(n), JB, 0, s>>>(g, idx, n);
+  return 1;
+}
+int launch_join_probe_fused(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
+                            uint8_t* mark, cudaStream_t s) {
+  if (n <= 0) return 0;
+  join_probe_fused_kernel<<<jgrid(n, JB * JP_ROWS), JB, 0, s>>>(k, n, t, probe_outer, d_cursor, probe_cols, build_cols, mark);
   return 1;
 }
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s) {

@@ -53,6 +53,10 @@ int launch_join_gather(const void* src, const uint8_t* src_valid_bits, uint32_t 
 struct GatherCol { const void* src; const uint8_t* vbits; const uint8_t* vbytes; void* out; uint8_t* out_valid; uint32_t bit_offset; int32_t width; };
 struct GatherSpec { int32_t ncols; int32_t _pad; GatherCol col[16]; };
 int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n, cudaStream_t s);
+// unique map keys: probe + gather fused, outputs written in probe-row order at positions reserved per tile on *d_cursor; probe_cols: src = the probe
+// batch's columns (vbits + bit_offset for validity), build_cols: src = the map side's columns (vbytes); at most 16 columns per side
+int launch_join_probe_fused(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
+                            uint8_t* mark, cudaStream_t s);
 // bytes[i] = bit (i + bit_offset) of bits (all 1 when bits is null)
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s);
 // flags[i] = (head[i] != NIL) ^ invert, as int32 for the scan; idx[offs[i]] = i for rows whose flag is set
