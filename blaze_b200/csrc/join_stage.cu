@@ -66,7 +66,7 @@ struct JoinBuilt {
   std::vector<DevMemP> values;                    // per column, contiguous
   std::vector<DevMemP> valid_bytes;               // per column: one byte per row, null when the column has no NULL
   JoinTable table{};
-  DevMemP t_keys, t_state, t_head, t_count, t_next, t_stats;
+  DevMemP t_keys, t_state, t_head, t_count, t_next, t_stats, t_packed;
   uint32_t max_dup = 0;                           // rows of the most duplicated key
   int device = 0;
 };
@@ -146,9 +146,10 @@ class JoinBuildStage : public Stage, public JoinBuildResult {
     b->t_count = DevMem::alloc((size_t)cap * 4, cx.stream, true);
     b->t_next = DevMem::alloc((size_t)total * 4 + 16, cx.stream);
     b->t_stats = DevMem::alloc(16, cx.stream, true);
+    b->t_packed = DevMem::alloc((size_t)cap * (keys_.size() == 1 ? 2 : 4) * 8 + 16, cx.stream);
     B200Q_CUDA(cudaMemsetAsync(b->t_head->ptr, 0xFF, (size_t)cap * 4, cx.stream));
     t.keys = (unsigned long long*)b->t_keys->ptr; t.state = (uint32_t*)b->t_state->ptr; t.head = (uint32_t*)b->t_head->ptr;
-    t.count = (uint32_t*)b->t_count->ptr; t.next = (uint32_t*)b->t_next->ptr; t.stats = (uint32_t*)b->t_stats->ptr;
+    t.count = (uint32_t*)b->t_count->ptr; t.next = (uint32_t*)b->t_next->ptr; t.stats = (uint32_t*)b->t_stats->ptr; t.packed = (unsigned long long*)b->t_packed->ptr;
     if (total > 0) {
       JoinKeys k{}; k.nkeys = (int)keys_.size();
       for (int i = 0; i < k.nkeys; i++) {
@@ -172,6 +173,7 @@ class JoinBuildStage : public Stage, public JoinBuildResult {
       B200Q_CUDA(cudaStreamSynchronize(cx.stream));
       float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; cx.m.hot_ms += ms; cx.m.hot_rows += total; cx.m.hot_launches++; cx.m.fast_launches++;
     }
+    if (total == 0) { JoinKeys k0{}; cx.m.launches += launch_join_build(k0, 0, t, cx.stream); }      // an empty map side still needs its (all-empty) probe view
     B200Q_CUDA(cudaStreamSynchronize(cx.stream));           // probe ops run on their own streams
     cx.m.num_groups = total; cx.m.table_capacity = (int64_t)cap;
     built_ = b;
@@ -317,15 +319,18 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
     auto read_cursor = [&]() { unsigned long long v = 0; B200Q_CUDA(cudaMemcpyAsync(&v, cursor->ptr, 8, cudaMemcpyDeviceToHost, cx.stream)); B200Q_CUDA(cudaStreamSynchronize(cx.stream)); return (int64_t)v; };
     B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
     if (!semi_like_) {
-      // count the output rows (keys only: 8 B/row), then
-      //   unique map keys (the PK side of a PK-FK join): ONE fused probe + gather pass writes the output columns in probe-row order;
+      // pass 1 looks every probe row up (keys only: 8 B/row in, for unique map keys 4 B/row of chain heads out) and counts the output rows, then
+      //   unique map keys (the PK side of a PK-FK join): ONE fused gather pass writes the output columns of both sides in probe-row order;
       //   duplicated map keys: (probe row, map row) pairs, then one gather pass per side
-      cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, nullptr, nullptr, nullptr, cx.stream);
+      const bool fused = built_->max_dup <= 1 && in.cols.size() <= 16 && built_->schema.fields.size() <= 16;
+      DevMemP head = fused ? DevMem::alloc((size_t)n * 4 + 16, cx.stream) : nullptr;
+      if (fused) cx.m.launches += launch_join_probe_count(k, n, built_->table, probe_outer_ ? 1 : 0, (uint32_t*)head->ptr, nullptr, cx.stream, (unsigned long long*)cursor->ptr);
+      else cx.m.launches += launch_join_probe_pairs(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, nullptr, nullptr, nullptr, cx.stream);
       const int64_t total = read_cursor();
       if (total > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "join: more than 2^31-1 output rows from one probe batch; push smaller batches");
       B200Q_CUDA(cudaMemsetAsync(cursor->ptr, 0, 8, cx.stream));
       uint8_t* mark = build_outer_ ? (uint8_t*)map_joined_->ptr : nullptr;
-      if (total > 0 && built_->max_dup <= 1 && in.cols.size() <= 16 && built_->schema.fields.size() <= 16) {
+      if (total > 0 && fused) {
         GatherSpec pc{}, bc{};
         std::vector<DevColumn> pcols, bcols; std::vector<DevMemP> pvb, bvb;
         auto out_col = [&](const DType& t, bool may_be_null, GatherCol& g, std::vector<DevColumn>& cols, std::vector<DevMemP>& vbs) {
@@ -348,7 +353,7 @@ class JoinProbeStage : public Stage, public JoinProbeAttach {
           g.src = built_->values[(size_t)c]->ptr; g.vbits = nullptr; g.bit_offset = 0; g.vbytes = built_->valid_bytes[(size_t)c] ? (const uint8_t*)built_->valid_bytes[(size_t)c]->ptr : nullptr;
           out_col(built_->schema.fields[(size_t)c].type, probe_outer_ || built_->valid_bytes[(size_t)c], g, bcols, bvb);
         }
-        cx.m.launches += launch_join_probe_fused(k, n, built_->table, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, pc, bc, mark, cx.stream);
+        cx.m.launches += launch_join_probe_fused((const uint32_t*)head->ptr, n, probe_outer_ ? 1 : 0, (unsigned long long*)cursor->ptr, pc, bc, mark, cx.stream);
         auto pack = [&](std::vector<DevColumn>& cols, std::vector<DevMemP>& vbs) {
           for (size_t c = 0; c < cols.size(); c++)
             if (vbs[c]) { cols[c].validity = DevMem::alloc(bitmap_bytes(total), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)vbs[c]->ptr, (uint32_t*)cols[c].validity->ptr, total, cx.stream); }

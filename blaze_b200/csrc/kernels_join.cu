@@ -49,9 +49,8 @@ __device__ __forceinline__ bool load_key(const JoinKeys& k, long long i, unsigne
 }
 
 __device__ __forceinline__ uint32_t key_hash(const unsigned long long (&w)[2]) {
-  unsigned long long h = w[0] * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 32; h += w[1] * 0xC2B2AE3D27D4EB4Full; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-  return (uint32_t)h;
+  unsigned long long h = (w[0] ^ (w[1] * 0xC2B2AE3D27D4EB4Full)) * 0x9E3779B97F4A7C15ull;      // multiplicative (Fibonacci) hash: the high bits mix every input bit
+  return (uint32_t)(h >> 32) ^ (uint32_t)(h >> 13);
 }
 
 // slot publication: keys are written, fenced, then the state becomes 2; readers fence after they have seen 2
@@ -88,25 +87,45 @@ __global__ void __launch_bounds__(JB) join_build_kernel(const JoinKeys k, long l
   }
 }
 
-__device__ __forceinline__ uint32_t find_slot(const JoinTable& t, const unsigned long long (&w)[2]) {
+// probe view: ONE 16-byte load per probed slot for single-key tables ({key, count << 32 | head}; head = NIL marks an empty slot)
+__device__ __forceinline__ bool probe(const JoinTable& t, const unsigned long long (&w)[2], uint32_t& head, uint32_t& count) {
   uint32_t slot = key_hash(w) & t.mask;
   while (true) {
-    if (t.state[slot] == 0) return JOIN_NIL;                          // the table is read-only by now
-    if (t.keys[(size_t)slot * t.nkw] == w[0] && (t.nkw == 1 || t.keys[(size_t)slot * t.nkw + 1] == w[1])) return slot;
+    unsigned long long hc;
+    bool same;
+    if (t.nkw == 1) { const ulonglong2 e = *(const ulonglong2*)(t.packed + (size_t)slot * 2); hc = e.y; same = e.x == w[0]; }
+    else { const ulonglong2 e = *(const ulonglong2*)(t.packed + (size_t)slot * 4); hc = t.packed[(size_t)slot * 4 + 2]; same = e.x == w[0] && e.y == w[1]; }
+    if ((uint32_t)hc == JOIN_NIL) return false;
+    if (same) { head = (uint32_t)hc; count = (uint32_t)(hc >> 32); return true; }
     slot = (slot + 1) & t.mask;
   }
 }
+__global__ void __launch_bounds__(JB) join_pack_kernel(const JoinTable t) {
+  const unsigned long long cap = (unsigned long long)t.mask + 1;
+  const int stride = t.nkw == 1 ? 2 : 4;
+  for (unsigned long long s = blockIdx.x * (unsigned long long)JB + threadIdx.x; s < cap; s += (unsigned long long)gridDim.x * JB) {
+    const bool used = t.state[s] == 2;
+    for (int i = 0; i < t.nkw; i++) t.packed[s * stride + i] = used ? t.keys[s * t.nkw + i] : 0;
+    t.packed[s * stride + t.nkw] = used ? ((unsigned long long)t.count[s] << 32) | t.head[s] : (unsigned long long)JOIN_NIL;
+  }
+}
 
-__global__ void __launch_bounds__(JB) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count) {
+__global__ void __launch_bounds__(JB) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count,
+                                                              unsigned long long* total) {
+  unsigned long long mine = 0;
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
     unsigned long long w[2];
-    uint32_t h = JOIN_NIL; int32_t c = 0;
-    if (load_key(k, i, w)) {                                           // a NULL in any key column never matches (full_join.rs:262-267)
-      const uint32_t slot = find_slot(t, w);
-      if (slot != JOIN_NIL) { h = t.head[slot]; c = (int32_t)t.count[slot]; }
-    }
+    uint32_t h = JOIN_NIL, c = 0;
+    if (load_key(k, i, w)) probe(t, w, h, c);                          // a NULL in any key column never matches (full_join.rs:262-267)
+    if (probe_outer && c == 0) c = 1;
     head[i] = h;
-    if (count) count[i] = (probe_outer && c == 0) ? 1 : c;
+    if (count) count[i] = (int32_t)c;
+    mine += c;
+  }
+  if (total) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
   }
 }
 
@@ -135,8 +154,7 @@ __global__ void __launch_bounds__(JB) join_mark_build_kernel(long long n, const 
 // Fused probe of the pair-producing joins (Inner / Left / Right / Full): lookup, then the CTA reserves the output rows of its
 // 2048 consecutive probe rows with ONE atomic on `cursor` (block scan of the match counts) and every thread writes its
 // (probe row, build row) pairs — no per-row intermediates, no global scan.  The output rows of a tile are contiguous and
-// keep the input order inside the tile (a thread owns 8 consecutive rows), so the gathers that follow read streaming; the
-// order of the tiles is not a contract.
+// come from a contiguous input range, so the gathers that follow stay inside a 16 KB window per column; the order is not a contract.
 // pidx == null: only count (cursor += matches), for build sides with duplicated keys whose output size is not bounded by n.
 constexpr int JP_ROWS = 8;
 __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
@@ -150,11 +168,11 @@ __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, 
     uint32_t h[JP_ROWS]; unsigned c[JP_ROWS]; unsigned mine = 0;
 #pragma unroll
     for (int r = 0; r < JP_ROWS; r++) {
-      const long long i = t0 + (long long)threadIdx.x * JP_ROWS + r;         // a thread owns 8 CONSECUTIVE rows: the tile's output keeps the input order
+      const long long i = t0 + r * JB + threadIdx.x;
       unsigned long long w[2];
       h[r] = JOIN_NIL; c[r] = 0;
       if (i < n) {
-        if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) { h[r] = t.head[slot]; c[r] = t.count[slot]; } }
+        if (load_key(k, i, w)) probe(t, w, h[r], c[r]);
         if (probe_outer && c[r] == 0) c[r] = 1;
       }
       mine += c[r];
@@ -173,7 +191,7 @@ __global__ void __launch_bounds__(JB) join_probe_pairs_kernel(const JoinKeys k, 
 #pragma unroll
       for (int r = 0; r < JP_ROWS; r++) {
         if (c[r] == 0) continue;
-        const uint32_t i = (uint32_t)(t0 + (long long)threadIdx.x * JP_ROWS + r);
+        const uint32_t i = (uint32_t)(t0 + r * JB + threadIdx.x);
         if (h[r] == JOIN_NIL) { pidx[o] = i; bidx[o] = JOIN_NIL; o++; continue; }                     // unmatched outer row
         for (uint32_t b = h[r]; b != JOIN_NIL; b = t.next[b], o++) { pidx[o] = i; bidx[o] = b; if (mark) mark[b] = 1; }
       }
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(JB) join_probe_select_kernel(const JoinKeys k,
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < nround; i += (long long)gridDim.x * JB) {
     unsigned long long w[2];
     bool keep = false;
-    if (i < n) { const bool found = load_key(k, i, w) && find_slot(t, w) != JOIN_NIL; keep = found != (invert != 0); }
+    if (i < n) { uint32_t h_, c_; const bool found = load_key(k, i, w) && probe(t, w, h_, c_); keep = found != (invert != 0); }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
     if (m == 0) continue;
     unsigned long long base = 0;
@@ -204,9 +222,8 @@ __global__ void __launch_bounds__(JB) join_probe_mark_kernel(const JoinKeys k, l
   for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
     unsigned long long w[2];
     if (!load_key(k, i, w)) continue;
-    const uint32_t slot = find_slot(t, w);
-    if (slot == JOIN_NIL) continue;
-    uint32_t b = t.head[slot];
+    uint32_t b, c_;
+    if (!probe(t, w, b, c_)) continue;
     if (mark[b]) continue;                                             // all rows of this key were marked together (semi_join.rs:214-226)
     for (; b != JOIN_NIL; b = t.next[b]) mark[b] = 1;
   }
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(JB) join_gather_multi_kernel(const GatherSpec 
 // ROW order, one atomic per 2048-row tile reserves the tile's output rows, and the probe-side columns are copied (coalesced in,
 // coalesced out) and the map-side columns gathered (L2-resident dimension table) straight into the output columns — no index
 // vectors at all.  `total` rows were counted by a first pass (join_probe_pairs_kernel without outputs), so the outputs are exact.
-__global__ void __launch_bounds__(JB) join_probe_fused_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, unsigned long long* cursor,
+__global__ void __launch_bounds__(JB) join_probe_fused_kernel(const uint32_t* __restrict__ head, long long n, int probe_outer, unsigned long long* cursor,
                                                               const GatherSpec pc, const GatherSpec bc, uint8_t* mark) {
   __shared__ unsigned s_cnt[JP_ROWS * (JB / 32) + 1];
   __shared__ unsigned long long s_base;
@@ -273,12 +290,8 @@ __global__ void __launch_bounds__(JB) join_probe_fused_kernel(const JoinKeys k, 
 #pragma unroll
     for (int r = 0; r < JP_ROWS; r++) {
       const long long i = t0 + r * JB + threadIdx.x;
-      unsigned long long w[2];
       h[r] = JOIN_NIL; bool out = false;
-      if (i < n) {
-        if (load_key(k, i, w)) { const uint32_t slot = find_slot(t, w); if (slot != JOIN_NIL) h[r] = t.head[slot]; }
-        out = h[r] != JOIN_NIL || probe_outer;
-      }
+      if (i < n) { h[r] = head[i]; out = h[r] != JOIN_NIL || probe_outer; }
       bal[r] = __ballot_sync(0xFFFFFFFFu, out);
       if (lane == 0) s_cnt[r * (JB / 32) + warp] = __popc(bal[r]);
       if (!out) h[r] = 0xFFFFFFFEu;                                        // no output row for this probe row
@@ -354,13 +367,13 @@ __global__ void __launch_bounds__(JB) compact_indices_kernel(const int32_t* __re
 }  // namespace
 
 int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStream_t s) {
-  if (n <= 0) return 0;
-  join_build_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t);
-  return 1;
+  if (n > 0) join_build_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t);
+  join_pack_kernel<<<jgrid((int64_t)t.mask + 1), JB, 0, s>>>(t);
+  return n > 0 ? 2 : 1;
 }
-int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s) {
+int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s, unsigned long long* d_total) {
   if (n <= 0) return 0;
-  join_probe_count_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_head, d_count);
+  join_probe_count_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_head, d_count, d_total);
   return 1;
 }
 int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head, const int32_t* d_offs, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s) {
@@ -405,10 +418,10 @@ int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n
   join_gather_multi_kernel<<<jgrid(n), JB, 0, s>>>(g, idx, n);
   return 1;
 }
-int launch_join_probe_fused(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
+int launch_join_probe_fused(const uint32_t* d_head, int64_t n, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
                             uint8_t* mark, cudaStream_t s) {
   if (n <= 0) return 0;
-  join_probe_fused_kernel<<<jgrid(n, JB * JP_ROWS), JB, 0, s>>>(k, n, t, probe_outer, d_cursor, probe_cols, build_cols, mark);
+  join_probe_fused_kernel<<<jgrid(n, JB * JP_ROWS), JB, 0, s>>>(d_head, n, probe_outer, d_cursor, probe_cols, build_cols, mark);
   return 1;
 }
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s) {

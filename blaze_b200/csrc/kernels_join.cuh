@@ -28,13 +28,14 @@ struct JoinTable {
   uint32_t* count;              // rows in the chain
   uint32_t* next;               // per build row: next row with the same key, JOIN_NIL at the end
   uint32_t* stats;              // [0] rows of the most duplicated key (0 or 1: the keys are unique)
+  unsigned long long* packed;   // probe view, written once after the build: per slot {key words..., count << 32 | head} (2 or 4 words; head = NIL: empty slot)
   uint32_t mask;                // capacity - 1
   int32_t nkw;                  // key words per slot (1 or 2)
 };
 
-int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStream_t s);
+int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStream_t s);      // fills keys / state / head / count / next, then packs the probe view
 // per probe row: head of the matching chain (JOIN_NIL: no match / NULL key) and out_count = matches (probe_outer: at least 1)
-int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s);
+int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s, unsigned long long* d_total = nullptr);   // d_total += sum of the counts
 // (probe row, build row) pairs at offs[r]...; marks map_joined[build row] = 1 when mark != null; unmatched outer rows pair with JOIN_NIL
 int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head, const int32_t* d_offs, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s);
 // fused probes (no per-row intermediates; output positions reserved with one atomic per warp on *d_cursor, zeroed by the caller):
@@ -53,9 +54,10 @@ int launch_join_gather(const void* src, const uint8_t* src_valid_bits, uint32_t 
 struct GatherCol { const void* src; const uint8_t* vbits; const uint8_t* vbytes; void* out; uint8_t* out_valid; uint32_t bit_offset; int32_t width; };
 struct GatherSpec { int32_t ncols; int32_t _pad; GatherCol col[16]; };
 int launch_join_gather_multi(const GatherSpec& g, const uint32_t* idx, int64_t n, cudaStream_t s);
-// unique map keys: probe + gather fused, outputs written in probe-row order at positions reserved per tile on *d_cursor; probe_cols: src = the probe
+// unique map keys: gather of both sides fused, driven by the per-row chain heads of launch_join_probe_count (d_head), outputs written in probe-row order at
+// positions reserved per tile on *d_cursor; probe_cols: src = the probe
 // batch's columns (vbits + bit_offset for validity), build_cols: src = the map side's columns (vbytes); at most 16 columns per side
-int launch_join_probe_fused(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
+int launch_join_probe_fused(const uint32_t* d_head, int64_t n, int probe_outer, unsigned long long* d_cursor, const GatherSpec& probe_cols, const GatherSpec& build_cols,
                             uint8_t* mark, cudaStream_t s);
 // bytes[i] = bit (i + bit_offset) of bits (all 1 when bits is null)
 int launch_unpack_bits(const uint8_t* bits, uint32_t bit_offset, int64_t n, uint8_t* bytes, cudaStream_t s);
