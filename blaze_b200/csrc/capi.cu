@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "lz4_frame.h"
+#include "parquet_meta.h"
 #include "runtime.h"
 
 namespace b200q {
@@ -634,6 +635,14 @@ b200q_status b200q_op_finish(b200q_op* op) {
   return guarded(op, [&] {
     if (op->finished) return;
     B200Q_CUDA(cudaSetDevice(op->cx.device));
+    {   // a ParquetScanExec leaf is the op's own source: read + decode the split now, one device batch per row group
+      const PlanNode* leaf = op->plan.get();
+      while (leaf->input) leaf = leaf->input.get();
+      if (leaf->kind == N_LEAF && leaf->leaf_kind == "ParquetScan") {
+        if (op->cx.m.input_batches) throw ExecError(B200Q_ERR_STATE, "an op whose leaf is a ParquetScanExecNode takes no pushed batches");
+        run_parquet_scan(op->cx, *leaf, [&](DevBatch& b) { run_stages(op, b, 0); });
+      }
+    }
     if (op->staging_ready) staging_flush(op);
     for (size_t i = 0; i < op->stages.size(); i++) {
       std::vector<DevBatch> outs;
@@ -717,6 +726,34 @@ void b200q_op_destroy(b200q_op* op) {
   if (op->cx.stream) cudaStreamSynchronize(op->cx.stream);
   delete op;                     // the stream itself goes away with the last allocation that references it
 }
+
+b200q_status b200q_parquet_explain(const uint8_t* footer, size_t n, char* buf, size_t cap, size_t* needed) {
+  return guarded(nullptr, [&] {
+    const PqFileMeta m = parquet_parse_footer(footer, n);
+    std::string o = "rows=" + std::to_string(m.num_rows) + " flat=" + (m.flat ? "true" : "false") + "\n";
+    for (auto& c : m.columns) o += "column " + c.name + " physical=" + std::to_string(c.type) + (c.optional ? " optional" : " required") + " arrow=" + (c.arrow.id == T_NULL ? std::string("unsupported") : c.arrow.str()) + "\n";
+    for (size_t g = 0; g < m.row_groups.size(); g++) {
+      o += "row_group " + std::to_string(g) + " rows=" + std::to_string(m.row_groups[g].num_rows) + "\n";
+      for (size_t c = 0; c < m.row_groups[g].columns.size(); c++) {
+        const PqColumnChunk& cc = m.row_groups[g].columns[c];
+        o += "  chunk " + std::to_string(c) + " codec=" + std::to_string(cc.codec) + " values=" + std::to_string(cc.num_values) + " start=" + std::to_string(cc.start()) + " bytes=" + std::to_string(cc.total_compressed_size) +
+             " nulls=" + std::to_string(cc.stats.null_count) + " min_max=" + (cc.stats.has_min && cc.stats.has_max ? "yes" : "no") + "\n";
+      }
+    }
+    if (needed) *needed = o.size() + 1;
+    if (buf && cap) { const size_t k = std::min(cap - 1, o.size()); memcpy(buf, o.data(), k); buf[k] = 0; }
+  });
+}
+b200q_status b200q_snappy_uncompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len) {
+  if ((!src && n) || !out_len) return fail(B200Q_ERR_INVALID_ARG, "null argument");
+  return guarded(nullptr, [&] {
+    std::vector<uint8_t> v; snappy_uncompress(src, n, v);
+    *out_len = v.size();
+    if (!dst || cap < v.size()) throw ExecError(B200Q_ERR_INVALID_ARG, "snappy output needs " + std::to_string(v.size()) + " bytes");
+    if (!v.empty()) memcpy(dst, v.data(), v.size());
+  });
+}
+b200q_status b200q_set_file_reader(b200q_file_reader_fn fn, void* ctx) { set_file_reader(fn, ctx); return B200Q_OK; }
 
 b200q_status b200q_op_attach_build(b200q_op* probe_op, b200q_op* build_op) {
   if (!probe_op || !build_op) return fail(B200Q_ERR_INVALID_ARG, "null argument");

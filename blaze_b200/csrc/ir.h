@@ -131,6 +131,13 @@ struct PlanNode {
   std::vector<std::pair<ExprP, ExprP>> join_on;                       // (left key, right key)
   SchemaDef join_left_schema, join_right_schema;
   std::string cached_build_hash_map_id;
+  // N_LEAF, leaf_kind "ParquetScan" (ParquetScanExecNode + FileScanExecConf, auron.proto:368-419)
+  struct ScanFile { std::string path; uint64_t size = 0; bool has_range = false; int64_t range_start = 0, range_end = 0; };
+  std::vector<ScanFile> scan_files;
+  SchemaDef scan_file_schema;                                         // base_conf.schema: the file's columns as Spark sees them
+  std::vector<int> scan_projection;                                   // indices into scan_file_schema (empty: every column)
+  std::vector<ExprP> scan_pruning;                                    // pruning_predicates, resolved against scan_file_schema
+  bool scan_has_limit = false; uint64_t scan_limit = 0;
   // N_SORT (SortExecNode, auron.proto:618-627; PhysicalSortExprNode :178-182)
   struct SortExprDef { ExprP expr; bool asc = true; bool nulls_first = true; };
   std::vector<SortExprDef> sort_exprs;

@@ -112,15 +112,28 @@ __global__ void __launch_bounds__(JB) join_pack_kernel(const JoinTable t) {
 
 __global__ void __launch_bounds__(JB) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count,
                                                               unsigned long long* total) {
+  // 8 rows per thread and step: the eight key loads, then the eight table probes, are independent of each other — with one row per
+  // thread the kernel is latency-bound (16 KB of key loads in flight per SM, measured 4.4e10 rows/s)
+  constexpr int R = 8;
   unsigned long long mine = 0;
-  for (long long i = blockIdx.x * (long long)JB + threadIdx.x; i < n; i += (long long)gridDim.x * JB) {
-    unsigned long long w[2];
-    uint32_t h = JOIN_NIL, c = 0;
-    if (load_key(k, i, w)) probe(t, w, h, c);                          // a NULL in any key column never matches (full_join.rs:262-267)
-    if (probe_outer && c == 0) c = 1;
-    head[i] = h;
-    if (count) count[i] = (int32_t)c;
-    mine += c;
+  const long long ntiles = (n + JB * R - 1) / (JB * R);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = tile * (JB * R);
+    unsigned long long w[R][2]; bool ok[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { const long long i = t0 + r * JB + threadIdx.x; ok[r] = i < n && load_key(k, i, w[r]); }      // a NULL in any key column never matches (full_join.rs:262-267)
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const long long i = t0 + r * JB + threadIdx.x;
+      uint32_t h = JOIN_NIL, c = 0;
+      if (ok[r]) probe(t, w[r], h, c);
+      if (i < n) {
+        if (probe_outer && c == 0) c = 1;
+        head[i] = h;
+        if (count) count[i] = (int32_t)c;
+        mine += c;
+      }
+    }
   }
   if (total) {
 #pragma unroll
@@ -373,7 +386,7 @@ int launch_join_build(const JoinKeys& k, int64_t n, const JoinTable& t, cudaStre
 }
 int launch_join_probe_count(const JoinKeys& k, int64_t n, const JoinTable& t, int probe_outer, uint32_t* d_head, int32_t* d_count, cudaStream_t s, unsigned long long* d_total) {
   if (n <= 0) return 0;
-  join_probe_count_kernel<<<jgrid(n), JB, 0, s>>>(k, n, t, probe_outer, d_head, d_count, d_total);
+  join_probe_count_kernel<<<jgrid(n, JB * 8), JB, 0, s>>>(k, n, t, probe_outer, d_head, d_count, d_total);
   return 1;
 }
 int launch_join_probe_emit(int64_t n, const JoinTable& t, const uint32_t* d_head, const int32_t* d_offs, uint32_t* d_pidx, uint32_t* d_bidx, uint8_t* mark, cudaStream_t s) {

@@ -102,18 +102,17 @@ SchemaElement parse_schema_element(TReader& r) {
 }
 
 PqStats parse_stats(TReader& r) {
-  PqStats s; int t, id = 0; std::string old_min, old_max; bool has_old_min = false, has_old_max = false;
+  PqStats s; int t, id = 0;
   while (r.field(t, id)) {
     switch (id) {
-      case 1: old_max = r.binary(); has_old_max = true; break;
-      case 2: old_min = r.binary(); has_old_min = true; break;
+      case 1: r.binary(); break;                                   // the deprecated max / min have an undefined sort order: not used for pruning
+      case 2: r.binary(); break;
       case 3: s.null_count = r.zigzag(); break;
       case 5: s.max = r.binary(); s.has_max = true; break;
       case 6: s.min = r.binary(); s.has_min = true; break;
       default: r.skip(t);
     }
   }
-  (void)old_min; (void)old_max; (void)has_old_min; (void)has_old_max;      // the deprecated fields have an undefined sort order: not used for pruning
   return s;
 }
 

@@ -1,0 +1,208 @@
+// ParquetScanExec as the SOURCE of an op: footer + page framing on the host (parquet_meta.cc),
+// column-chunk decode on the GPU (kernels_parquet.cu), row-group pruning from the min / max statistics.
+//
+// Reference: ParquetExec::execute (datafusion-ext-plans/src/parquet_exec.rs:150-203) builds DataFusion's ParquetOpener over
+// the `parquet` crate (row-group pruning by statistics, optional page filtering); bytes arrive through FsProvider
+// (:316-396).  Here: every row group inside the split's byte range is one device batch — its projected column chunks
+// are read (local files, or the host's reader callback: b200q_set_file_reader, the counterpart of FsProvider), their pages
+// decompressed and described as run tables on the host, and expanded on the device; the batch then flows through the
+// stages above the scan (FilterExec / AggExec / ...).  A row group is skipped when a pruning predicate `col cmp literal`
+// cannot hold for its [min, max] statistics — an optimisation only: Spark keeps the FilterExec above the scan, so the
+// rows that leave the pipeline are the same.
+#include <cstdio>
+#include <cstring>
+
+#include "kernels_join.cuh"
+#include "kernels_parquet.cuh"
+#include "parquet_meta.h"
+#include "runtime.h"
+
+namespace b200q {
+
+static b200q_file_reader_fn g_reader = nullptr;
+static void* g_reader_ctx = nullptr;
+void set_file_reader(b200q_file_reader_fn fn, void* ctx) { g_reader = fn; g_reader_ctx = ctx; }
+
+namespace {
+
+inline size_t bitmap_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4; }
+
+struct FileIo {
+  std::string path; FILE* f = nullptr; int64_t size = -1;
+  explicit FileIo(const std::string& p, uint64_t declared_size) : path(p) {
+    if (g_reader) { size = (int64_t)declared_size; return; }
+    std::string local = p;
+    if (local.rfind("file://", 0) == 0) local = local.substr(7); else if (local.rfind("file:", 0) == 0) local = local.substr(5);
+    f = fopen(local.c_str(), "rb");
+    if (!f) throw ExecError(B200Q_ERR_EXECUTION, "parquet: cannot open " + p + " (register a reader with b200q_set_file_reader for non-local file systems)");
+    fseek(f, 0, SEEK_END); size = ftell(f);
+  }
+  ~FileIo() { if (f) fclose(f); }
+  void read(int64_t off, size_t len, uint8_t* dst) {
+    if (off < 0 || (int64_t)(off + (int64_t)len) > size) throw ExecError(B200Q_ERR_EXECUTION, "parquet: read past the end of " + path);
+    if (g_reader) { if (g_reader(g_reader_ctx, path.c_str(), off, (int64_t)len, dst) != 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: the file reader callback failed for " + path); return; }
+    if (fseek(f, (long)off, SEEK_SET) != 0 || fread(dst, 1, len, f) != len) throw ExecError(B200Q_ERR_EXECUTION, "parquet: short read from " + path);
+  }
+};
+
+// statistics are PLAIN-encoded single values (little-endian) for INT32 / INT64
+bool stat_i64(const PqColumnSchema& cs, const std::string& v, long long& out) {
+  if (cs.type == PQ_INT32 && v.size() == 4) { int32_t x; memcpy(&x, v.data(), 4); out = x; return true; }
+  if (cs.type == PQ_INT64 && v.size() == 8) { long long x; memcpy(&x, v.data(), 8); out = x; return true; }
+  return false;
+}
+
+// may the predicate hold for some row of a row group whose column `col` lies in [mn, mx]?  Unknown shapes -> true (keep)
+bool may_match(const ExprP& e, const std::vector<int>& file_col_of, const PqFileMeta& meta, const PqRowGroup& rg) {
+  if (e->kind == E_BINARY && e->op == OP_AND) return may_match(e->children[0], file_col_of, meta, rg) && may_match(e->children[1], file_col_of, meta, rg);
+  if (e->kind == E_BINARY && e->op == OP_OR) return may_match(e->children[0], file_col_of, meta, rg) || may_match(e->children[1], file_col_of, meta, rg);
+  if (e->kind != E_BINARY || e->op < OP_EQ || e->op > OP_GE) return true;
+  ExprP l = e->children[0], r = e->children[1]; int op = e->op;
+  if (l->kind == E_LITERAL && r->kind == E_COLUMN) { std::swap(l, r); static const int flip[] = {OP_EQ, OP_NE, OP_GT, OP_GE, OP_LT, OP_LE}; op = flip[op - OP_EQ]; }
+  if (l->kind != E_COLUMN || r->kind != E_LITERAL || r->lit_null || !l->type.is_intlike() || !r->type.is_intlike()) return true;
+  const int fc = l->col_index >= 0 && (size_t)l->col_index < file_col_of.size() ? file_col_of[(size_t)l->col_index] : -1;
+  if (fc < 0) return true;
+  const PqStats& st = rg.columns[(size_t)fc].stats;
+  long long mn, mx;
+  if (!st.has_min || !st.has_max || !stat_i64(meta.columns[(size_t)fc], st.min, mn) || !stat_i64(meta.columns[(size_t)fc], st.max, mx)) return true;
+  const long long v = (long long)r->lit_lo;
+  switch (op) {
+    case OP_EQ: return v >= mn && v <= mx;
+    case OP_LT: return mn < v;
+    case OP_LE: return mn <= v;
+    case OP_GT: return mx > v;
+    case OP_GE: return mx >= v;
+    default: return true;                                               // NotEq
+  }
+}
+
+DevMemP upload(OpContext& cx, const void* p, size_t n, size_t pad = 16) {
+  DevMemP d = DevMem::alloc(n + pad, cx.stream, true);
+  if (n) B200Q_CUDA(cudaMemcpyAsync(d->ptr, p, n, cudaMemcpyHostToDevice, cx.stream));
+  cx.m.h2d_bytes += (int64_t)n;
+  return d;
+}
+
+// one column chunk -> one device column of `rows` rows
+DevColumn decode_chunk(OpContext& cx, FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, DevMemP d_err) {
+  if (cs.arrow.id == T_NULL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " has a physical / logical type outside the GPU path");
+  if (cs.arrow != want) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " is " + cs.arrow.str() + " in the file, the plan expects " + want.str() + " (schema adaption stays on the host)");
+  std::vector<uint8_t> raw((size_t)cc.total_compressed_size);
+  io.read(cc.start(), raw.size(), raw.data());
+  std::vector<PqPage> pages = parquet_read_pages(raw.data(), raw.size(), cc, cs);
+  // flatten: page bodies back to back, level runs by row, value runs by stored-value ordinal
+  std::vector<uint8_t> bytes; std::vector<PqDevRun> lruns, vruns; const PqPage* dict = nullptr;
+  int64_t row = 0, ord = 0; bool any_null = false;
+  for (auto& pg : pages) if (pg.type != PQ_DICTIONARY_PAGE && !pg.def_runs.empty()) any_null = true;
+  for (auto& pg : pages) {
+    if (pg.type == PQ_DICTIONARY_PAGE) { dict = &pg; continue; }
+    const uint64_t base = bytes.size();
+    bytes.insert(bytes.end(), pg.bytes.begin(), pg.bytes.end());
+    if (any_null) {
+      if (pg.def_runs.empty()) lruns.push_back(PqDevRun{(uint32_t)row, (uint32_t)pg.num_values, PQR_RLE, 1, {}, 1});
+      uint32_t at = (uint32_t)row;
+      for (auto& r : pg.def_runs) { lruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), 1, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
+    }
+    if (pg.non_null > 0) {
+      if (!pg.idx_runs.empty()) {
+        uint32_t at = (uint32_t)ord;
+        for (auto& r : pg.idx_runs) { vruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), (uint8_t)pg.dict_bit_width, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
+      } else vruns.push_back(PqDevRun{(uint32_t)ord, (uint32_t)pg.non_null, PQR_PLAIN, 0, {}, base + pg.values_offset});
+    }
+    row += pg.num_values; ord += pg.non_null;
+  }
+  if (row != rows) throw ExecError(B200Q_ERR_EXECUTION, "parquet: column " + cs.name + " holds " + std::to_string(row) + " values, its row group " + std::to_string(rows) + " rows");
+  PqDecodeSpec sp{};
+  DevMemP d_bytes = upload(cx, bytes.data(), bytes.size()), d_vruns = upload(cx, vruns.data(), vruns.size() * sizeof(PqDevRun)), d_dict, d_lruns;
+  sp.bytes = (const uint8_t*)d_bytes->ptr; sp.value_runs = (const PqDevRun*)d_vruns->ptr; sp.n_value_runs = (int)vruns.size();
+  if (dict) { d_dict = upload(cx, dict->bytes.data(), dict->bytes.size()); sp.dict = (const uint8_t*)d_dict->ptr; sp.dict_count = dict->num_values; }
+  int out_w = want.byte_width();
+  switch (cs.type) {
+    case PQ_BOOLEAN: sp.src_width = 0; sp.out_kind = PQO_BOOL_BYTES; out_w = 1; break;
+    case PQ_INT32: sp.src_width = 4; sp.out_kind = want.id == T_INT8 ? PQO_I8 : want.id == T_INT16 ? PQO_I16 : want.id == T_DECIMAL128 ? PQO_DEC_FROM_I32 : PQO_I32; break;
+    case PQ_INT64: sp.src_width = 8; sp.out_kind = want.id == T_DECIMAL128 ? PQO_DEC_FROM_I64 : PQO_I64; break;
+    case PQ_FLOAT: sp.src_width = 4; sp.out_kind = PQO_I32; break;
+    case PQ_DOUBLE: sp.src_width = 8; sp.out_kind = PQO_I64; break;
+    default: sp.src_width = cs.type_length; sp.out_kind = PQO_DEC_FROM_FLBA; break;
+  }
+  if (dict && sp.src_width > 0 && (int64_t)dict->bytes.size() < (int64_t)dict->num_values * sp.src_width) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary page shorter than its entry count");
+  DevColumn col; col.type = want;
+  DevMemP d_valid, d_ord;
+  if (any_null) {
+    d_lruns = upload(cx, lruns.data(), lruns.size() * sizeof(PqDevRun));
+    d_valid = DevMem::alloc((size_t)rows + 16, cx.stream);
+    cx.m.launches += launch_pq_levels((const uint8_t*)d_bytes->ptr, (const PqDevRun*)d_lruns->ptr, (int)lruns.size(), rows, (uint8_t*)d_valid->ptr, cx.stream);
+    DevMemP fl = DevMem::alloc((size_t)rows * 4 + 16, cx.stream), sums = DevMem::alloc((size_t)scan_num_blocks(rows) * 4 + 16, cx.stream);
+    d_ord = DevMem::alloc((size_t)(rows + 1) * 4, cx.stream);
+    cx.m.launches += launch_bytes_to_flags((const uint8_t*)d_valid->ptr, rows, 0, (int32_t*)fl->ptr, cx.stream);
+    cx.m.launches += launch_exclusive_scan_i32((const int32_t*)fl->ptr, (int32_t*)d_ord->ptr, rows, (int32_t*)sums->ptr, cx.stream);
+    col.validity = DevMem::alloc(bitmap_bytes(rows), cx.stream, true);
+    cx.m.launches += launch_pack_valid((const uint8_t*)d_valid->ptr, (uint32_t*)col.validity->ptr, rows, cx.stream);
+  }
+  DevMemP out = DevMem::alloc((size_t)rows * out_w + 16, cx.stream);
+  cx.m.launches += launch_pq_decode(sp, any_null ? (const uint8_t*)d_valid->ptr : nullptr, any_null ? (const int32_t*)d_ord->ptr : nullptr, rows, out->ptr, (int*)d_err->ptr, cx.stream);
+  if (cs.type == PQ_BOOLEAN) { col.values = DevMem::alloc(bitmap_bytes(rows), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)out->ptr, (uint32_t*)col.values->ptr, rows, cx.stream); }
+  else col.values = out;
+  return col;
+}
+
+}  // namespace
+
+void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<void(DevBatch&)>& emit) {
+  int64_t remaining = leaf.scan_has_limit ? (int64_t)leaf.scan_limit : -1;
+  DevMemP d_err = DevMem::alloc(16, cx.stream, true);
+  for (auto& sf : leaf.scan_files) {
+    if (remaining == 0) break;
+    FileIo io(sf.path, sf.size);
+    if (io.size < 12) throw ExecError(B200Q_ERR_EXECUTION, "parquet: " + sf.path + " is too small to be a parquet file");
+    uint8_t tail[8]; io.read(io.size - 8, 8, tail);
+    if (memcmp(tail + 4, "PAR1", 4) != 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: " + sf.path + " has no PAR1 footer (encrypted files are not supported)");
+    uint32_t flen; memcpy(&flen, tail, 4);
+    if ((int64_t)flen + 8 > io.size) throw ExecError(B200Q_ERR_EXECUTION, "parquet: footer length exceeds the file");
+    std::vector<uint8_t> footer(flen); io.read(io.size - 8 - flen, flen, footer.data());
+    const PqFileMeta meta = parquet_parse_footer(footer.data(), footer.size());
+    if (!meta.flat) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: nested / repeated columns are not on the GPU path");
+    // plan column (by name; exact, then case-insensitive) -> file leaf
+    std::vector<int> file_col_of(leaf.scan_file_schema.fields.size(), -1);
+    for (size_t i = 0; i < file_col_of.size(); i++) {
+      const std::string& want = leaf.scan_file_schema.fields[i].name;
+      for (size_t j = 0; j < meta.columns.size() && file_col_of[i] < 0; j++) if (meta.columns[j].name == want) file_col_of[i] = (int)j;
+      for (size_t j = 0; j < meta.columns.size() && file_col_of[i] < 0; j++)
+        if (meta.columns[j].name.size() == want.size()) { bool eq = true; for (size_t k = 0; k < want.size(); k++) eq = eq && tolower((unsigned char)want[k]) == tolower((unsigned char)meta.columns[j].name[k]); if (eq) file_col_of[i] = (int)j; }
+    }
+    for (auto& rg : meta.row_groups) {
+      if (remaining == 0) break;
+      if (rg.num_rows == 0 || rg.columns.empty()) continue;
+      const int64_t rg_start = rg.columns[0].start();                     // a row group belongs to the split that holds its first byte
+      if (sf.has_range && (rg_start < sf.range_start || rg_start >= sf.range_end)) continue;
+      bool keep = true;
+      for (auto& p : leaf.scan_pruning) keep = keep && may_match(p, file_col_of, meta, rg);
+      if (!keep) { cx.m.fast_launches++; continue; }                        // pruned row groups show up in fast_path_launches
+      if (rg.num_rows > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: row group above 2^31-1 rows");
+      DevBatch b; b.num_rows = rg.num_rows;
+      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+      for (int pi : leaf.scan_projection) {
+        const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
+        const int fc = file_col_of[(size_t)pi];
+        if (fc < 0) {                                                       // column missing in this file (schema evolution): all NULL
+          DevColumn c; c.type = f.type;
+          c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
+          c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
+          b.cols.push_back(c);
+        } else b.cols.push_back(decode_chunk(cx, io, rg.columns[(size_t)fc], meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
+      }
+      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+      int err = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
+      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
+      if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
+      if (remaining >= 0) remaining -= b.num_rows;
+      cx.m.input_rows += b.num_rows; cx.m.input_batches++;
+      emit(b);
+    }
+  }
+}
+
+}  // namespace b200q

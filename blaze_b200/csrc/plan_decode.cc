@@ -375,6 +375,53 @@ PlanP parse_leaf(Reader r, bool ffi) {
   return n;
 }
 
+// ParquetScanExecNode{base_conf=1, pruning_predicates=2, fsResourceId=3}; FileScanExecConf{num_partitions=1, partition_index=2, file_group=3,
+// schema=4, projection=6, limit=7, statistics=8, partition_schema=9} (auron.proto:404-419; from_proto.rs ParquetScan arm)
+PlanP parse_parquet_scan(Reader r) {
+  auto n = std::make_shared<PlanNode>(); n->kind = N_LEAF; n->leaf_kind = "ParquetScan";
+  std::vector<Reader> preds; bool have_conf = false;
+  while (!r.done()) {
+    int wt; uint32_t f = r.tag(wt);
+    if (f == 1) {
+      Reader c = r.bytes(); have_conf = true;
+      while (!c.done()) {
+        int w2; uint32_t g = c.tag(w2);
+        if (g == 3) {                                                            // FileGroup{files=1}
+          Reader fg = c.bytes();
+          while (!fg.done()) {
+            int w3; uint32_t h = fg.tag(w3);
+            if (h != 1) { fg.skip(w3); continue; }
+            Reader pf = fg.bytes(); PlanNode::ScanFile sf;                       // PartitionedFile{path=1,size=2,last_modified_ns=3,partition_values=4,range=5}
+            while (!pf.done()) {
+              int w4; uint32_t k = pf.tag(w4);
+              if (k == 1) sf.path = pf.str(); else if (k == 2) sf.size = pf.varint();
+              else if (k == 4) { pf.bytes(); unsupported("parquet scan with partition values (partition columns are appended by the host)"); }
+              else if (k == 5) { Reader fr = pf.bytes(); sf.has_range = true; while (!fr.done()) { int w5; uint32_t q = fr.tag(w5); if (q == 1) sf.range_start = (int64_t)fr.varint(); else if (q == 2) sf.range_end = (int64_t)fr.varint(); else fr.skip(w5); } }
+              else pf.skip(w4);
+            }
+            n->scan_files.push_back(sf);
+          }
+        } else if (g == 4) n->scan_file_schema = parse_schema(c.bytes());
+        else if (g == 6) { std::vector<uint64_t> v; c.varints(w2, v); for (uint64_t x : v) n->scan_projection.push_back((int)x); }
+        else if (g == 7) { Reader l = c.bytes(); n->scan_has_limit = true; while (!l.done()) { int w3; uint32_t h = l.tag(w3); if (h == 1) n->scan_limit = l.varint(); else l.skip(w3); } }
+        else if (g == 9) { SchemaDef ps = parse_schema(c.bytes()); if (!ps.fields.empty()) unsupported("parquet scan with a partition schema"); }
+        else c.skip(w2);
+      }
+    } else if (f == 2) preds.push_back(r.bytes());
+    else r.skip(wt);
+  }
+  if (!have_conf) bad("Missing required field in protobuf");
+  if (n->scan_projection.empty()) for (size_t i = 0; i < n->scan_file_schema.fields.size(); i++) n->scan_projection.push_back((int)i);
+  for (int i : n->scan_projection) {
+    if (i < 0 || (size_t)i >= n->scan_file_schema.fields.size()) bad("parquet scan projection index out of range");
+    n->schema.fields.push_back(n->scan_file_schema.fields[(size_t)i]);
+  }
+  for (auto& p : preds) {
+    try { n->scan_pruning.push_back(parse_expr(p, n->scan_file_schema)); } catch (const PlanError&) {}      // pruning is an optimisation: predicates outside the expression subset are dropped
+  }
+  return n;
+}
+
 PlanP parse_filter(Reader r) {               // FilterExecNode{input=1, expr=2}
   auto n = std::make_shared<PlanNode>(); n->kind = N_FILTER;
   std::vector<Reader> exprs;
@@ -613,6 +660,7 @@ PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.p
     int wt; uint32_t f = r.tag(wt);
     switch (f) {
       case 2: return parse_shuffle_writer(r.bytes());
+      case 5: return parse_parquet_scan(r.bytes());
       case 6: return parse_projection(r.bytes());
       case 7: return parse_sort(r.bytes());
       case 8: return parse_filter(r.bytes());
@@ -622,7 +670,7 @@ PlanP parse_plan(Reader r) {                  // PhysicalPlanNode oneof (auron.p
       case 15: return parse_leaf(r.bytes(), false);
       case 16: return parse_agg(r.bytes());
       case 18: return parse_leaf(r.bytes(), true);
-      case 1: case 3: case 4: case 5: case 9: case 10: case 14: case 17: case 19: case 20:
+      case 1: case 3: case 4: case 9: case 10: case 14: case 17: case 19: case 20:
       case 21: case 22: case 23: case 24: case 25:
         unsupported("plan node #" + std::to_string(f) + " is outside the Filter/Project/Agg hot path (SURVEY.md §8)");
       default: r.skip(wt);
@@ -671,7 +719,16 @@ static void explain_rec(const PlanP& p, int depth, std::ostringstream& o) {
     return r + "]";
   };
   switch (p->kind) {
-    case N_LEAF: o << ind << p->leaf_kind << " schema=" << schema_str(p->schema) << "\n"; break;
+    case N_LEAF:
+      o << ind << p->leaf_kind;
+      if (p->leaf_kind == "ParquetScan") {
+        o << " files=[";
+        for (size_t i = 0; i < p->scan_files.size(); i++) { o << (i ? ", " : "") << p->scan_files[i].path; if (p->scan_files[i].has_range) o << "[" << p->scan_files[i].range_start << "," << p->scan_files[i].range_end << ")"; }
+        o << "] pruning=[";
+        for (size_t i = 0; i < p->scan_pruning.size(); i++) o << (i ? ", " : "") << explain_expr(p->scan_pruning[i]);
+        o << "]"; if (p->scan_has_limit) o << " limit=" << p->scan_limit;
+      }
+      o << " schema=" << schema_str(p->schema) << "\n"; break;
     case N_FILTER:
       o << ind << "FilterExec [";
       for (size_t i = 0; i < p->predicates.size(); i++) o << (i ? ", " : "") << explain_expr(p->predicates[i]);

@@ -109,6 +109,10 @@ struct ShuffleResult {
   virtual void chunk(int64_t i, b200q_shuffle_chunk* out) const = 0;
 };
 
+// ParquetScanExec (parquet_source.cu): the source of an op whose leaf is a ParquetScanExecNode; `emit` receives one device batch per row group
+void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<void(DevBatch&)>& emit);
+void set_file_reader(b200q_file_reader_fn fn, void* ctx);
+
 // SortExec (sort_stage.cu): collects its input, emits the sorted (and `fetch`-limited) rows at finish
 std::unique_ptr<Stage> make_sort_stage(OpContext& cx, const SchemaDef& in_schema, const PlanNode& node);
 

@@ -76,7 +76,7 @@ SYMBOLS = ["b200q_version", "b200q_build_info", "b200q_last_error", "b200q_devic
            "b200q_plan_explain", "b200q_op_create", "b200q_op_input_schema", "b200q_op_output_schema", "b200q_op_push",
            "b200q_op_push_device", "b200q_op_finish", "b200q_op_pull", "b200q_op_pull_device", "b200q_op_sync",
            "b200q_op_metrics", "b200q_op_destroy", "b200q_murmur3_partition",
-           "b200q_op_attach_build", "b200q_op_shuffle_chunk_count", "b200q_op_shuffle_chunk", "b200q_lz4_frame_compress",
+           "b200q_set_file_reader", "b200q_parquet_explain", "b200q_snappy_uncompress", "b200q_op_attach_build", "b200q_op_shuffle_chunk_count", "b200q_op_shuffle_chunk", "b200q_lz4_frame_compress",
            "b200q_exchange_unique_id", "b200q_exchange_create", "b200q_exchange_shuffle", "b200q_exchange_kernel_launches",
            "b200q_exchange_destroy"]
 
@@ -105,6 +105,9 @@ def _load():
     lib.b200q_op_destroy.argtypes = [C.c_void_p]
     lib.b200q_op_destroy.restype = None
     lib.b200q_murmur3_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.b200q_set_file_reader.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200q_parquet_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.b200q_snappy_uncompress.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.b200q_op_attach_build.argtypes = [C.c_void_p, C.c_void_p]
     lib.b200q_op_shuffle_chunk_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.b200q_op_shuffle_chunk.argtypes = [C.c_void_p, C.c_int64, C.POINTER(ShuffleChunk)]
@@ -120,6 +123,22 @@ def _load():
 
 
 lib = _load()
+
+
+def parquet_explain(footer: bytes) -> str:
+    """host-only: the library's view of a parquet FileMetaData footer"""
+    need = C.c_size_t(0)
+    check(lib.b200q_parquet_explain(footer, len(footer), None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    check(lib.b200q_parquet_explain(footer, len(footer), buf, need.value, C.byref(need)))
+    return buf.value.decode()
+
+
+def snappy_uncompress(data: bytes, capacity: int) -> bytes:
+    out = C.create_string_buffer(max(1, capacity))
+    n = C.c_size_t(0)
+    check(lib.b200q_snappy_uncompress(data, len(data), out, capacity, C.byref(n)))
+    return out.raw[: n.value]
 
 
 def lz4_frame_compress(data: bytes) -> bytes:

@@ -187,6 +187,25 @@ class AggExec(ExecutionPlan):
         return P.agg_node(self.input.node(), self.exec_mode, self.groupings, self.aggs, self.supports_partial_skipping)
 
 
+class ParquetScanExec(ExecutionPlan):
+    """ParquetExec::new(base_conf, fs_resource_id, predicate) (datafusion-ext-plans/src/parquet_exec.rs:77-110): a LEAF that is its own
+    source — files = [(path, size, (range_start, range_end) | None)], projection = indices into file_schema."""
+
+    def __init__(self, file_schema: Schema, files, projection=None, pruning_predicates=(), limit=None):
+        import os
+        self.file_schema, self.projection = file_schema, list(projection) if projection is not None else list(range(len(file_schema)))
+        self.files = [(p, s if s else os.path.getsize(p), r) for p, s, r in files]
+        self.pruning, self.limit = list(pruning_predicates), limit
+        self.batches = []
+        self._validate()
+
+    def schema(self):
+        return Schema([self.file_schema[i] for i in self.projection])
+
+    def node(self):
+        return P.parquet_scan_node(self.file_schema, self.files, self.projection, self.pruning, self.limit)
+
+
 class SortExec(ExecutionPlan):
     """SortExec::new(input, exprs, fetch) (sort_exec.rs:97-112); exprs = [(expr, descending, nulls_first)] like arrow's
     PhysicalSortExpr{expr, SortOptions{descending, nulls_first}} (SortOptions::default() = ascending, NULLs first)."""

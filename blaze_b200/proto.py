@@ -136,6 +136,14 @@ def _build_pool():
     _msg(fd, "BroadcastJoinBuildHashMapExecNode", [("input", 1, "PhysicalPlanNode"), ("keys", 2, "PhysicalExprNode", R)])
     _msg(fd, "BroadcastJoinExecNode", [("schema", 1, "Schema"), ("left", 2, "PhysicalPlanNode"), ("right", 3, "PhysicalPlanNode"), ("on", 4, "JoinOn", R),
                                        ("join_type", 5, "enum:JoinType"), ("broadcast_side", 6, "enum:JoinSide"), ("cached_build_hash_map_id", 7, _F.TYPE_STRING)])
+    _msg(fd, "FileRange", [("start", 1, _F.TYPE_INT64), ("end", 2, _F.TYPE_INT64)])
+    _msg(fd, "PartitionedFile", [("path", 1, _F.TYPE_STRING), ("size", 2, _F.TYPE_UINT64), ("last_modified_ns", 3, _F.TYPE_UINT64),
+                                 ("partition_values", 4, "ScalarValue", R), ("range", 5, "FileRange")])
+    _msg(fd, "FileGroup", [("files", 1, "PartitionedFile", R)])
+    _msg(fd, "ScanLimit", [("limit", 1, _F.TYPE_UINT32)])
+    _msg(fd, "FileScanExecConf", [("num_partitions", 1, _F.TYPE_INT64), ("partition_index", 2, _F.TYPE_INT64), ("file_group", 3, "FileGroup"), ("schema", 4, "Schema"),
+                                  ("projection", 6, _F.TYPE_UINT32, R), ("limit", 7, "ScanLimit"), ("partition_schema", 9, "Schema")])
+    _msg(fd, "ParquetScanExecNode", [("base_conf", 1, "FileScanExecConf"), ("pruning_predicates", 2, "PhysicalExprNode", R), ("fsResourceId", 3, _F.TYPE_STRING)])
     _msg(fd, "FetchLimit", [("limit", 1, _F.TYPE_UINT64)])
     _msg(fd, "SortExecNode", [("input", 1, "PhysicalPlanNode"), ("expr", 2, "PhysicalExprNode", R), ("fetch_limit", 3, "FetchLimit")])
     _msg(fd, "PhysicalSingleRepartition", [("partition_count", 1, _F.TYPE_UINT64)])
@@ -148,7 +156,7 @@ def _build_pool():
     _msg(fd, "ShuffleWriterExecNode", [("input", 1, "PhysicalPlanNode"), ("output_partitioning", 2, "PhysicalRepartition"),
                                        ("output_data_file", 3, _F.TYPE_STRING), ("output_index_file", 4, _F.TYPE_STRING)])
     _msg(fd, "PhysicalPlanNode", [
-        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("projection", 6, "ProjectionExecNode", O), ("sort", 7, "SortExecNode", O),
+        ("shuffle_writer", 2, "ShuffleWriterExecNode", O), ("parquet_scan", 5, "ParquetScanExecNode", O), ("projection", 6, "ProjectionExecNode", O), ("sort", 7, "SortExecNode", O),
         ("hash_join", 11, "HashJoinExecNode", O), ("broadcast_join_build_hash_map", 12, "BroadcastJoinBuildHashMapExecNode", O),
         ("broadcast_join", 13, "BroadcastJoinExecNode", O), ("filter", 8, "FilterExecNode", O),
         ("empty_partitions", 15, "EmptyPartitionsExecNode", O), ("agg", 16, "AggExecNode", O),
@@ -348,6 +356,27 @@ def agg_node(input_node, exec_mode, groupings, aggs, supports_partial_skipping=F
         a.mode.append(ag.mode)
     a.initial_input_buffer_offset = initial_input_buffer_offset
     a.supports_partial_skipping = supports_partial_skipping
+    return n
+
+
+def parquet_scan_node(file_schema: Schema, files, projection=None, pruning_predicates=(), limit=None, fs_resource_id=""):
+    """files: [(path, size, (range_start, range_end) | None)] (FileScanExecConf, auron.proto:404-413)"""
+    n = PhysicalPlanNode()
+    c = n.parquet_scan.base_conf
+    c.num_partitions, c.partition_index = 1, 0
+    for path, size, rng in files:
+        f = c.file_group.files.add()
+        f.path, f.size = path, size
+        if rng is not None:
+            f.range.start, f.range.end = rng
+    c.schema.CopyFrom(schema_msg(file_schema))
+    for i in (projection if projection is not None else range(len(file_schema))):
+        c.projection.append(i)
+    if limit is not None:
+        c.limit.limit = limit
+    for p in pruning_predicates:
+        n.parquet_scan.pruning_predicates.add().CopyFrom(expr_msg(p))
+    n.parquet_scan.fsResourceId = fs_resource_id
     return n
 
 

@@ -36,6 +36,7 @@
  *                           BufferedData::write               datafusion-ext-plans/src/shuffle/buffered_data.rs:123-158
  *                           write_batch (byte planes)         datafusion-ext-commons/src/io/batch_serde.rs:66-77,264-306
  *                           IpcCompressionWriter              datafusion-ext-plans/src/common/ipc_compression.rs:34-112
+ *   ParquetScanExecNode leaf ParquetExec::execute (decode + row-group pruning)      datafusion-ext-plans/src/parquet_exec.rs:150-203,316-396
  *   SortExecNode plans      SortExec::new + ExternalSorter::insert_batch / output   datafusion-ext-plans/src/sort_exec.rs:97-112,626-752
  *   b200q_op_attach_build   collect_join_hash_map + execute_join_with_map   datafusion-ext-plans/src/broadcast_join_exec.rs:317-385,562-639
  *   b200q_op_shuffle_chunk  the per-partition encoded bytes before compression — what BufferedData::write_rss
@@ -236,6 +237,20 @@ void b200q_op_destroy(b200q_op* op);
  * cached_build_hash_map_id (broadcast_join_exec.rs:640-677); the build op must outlive them only until they are destroyed
  * (the table is reference counted).  Inner / Left / Right / Full / LeftSemi / LeftAnti / Existence, either side as the map. */
 b200q_status b200q_op_attach_build(b200q_op* probe_op, b200q_op* build_op);
+
+/* ---- ParquetScanExec as the source of an op (plans whose leaf is a ParquetScanExecNode) -----------------------------------
+ * Reference: ParquetExec::execute (datafusion-ext-plans/src/parquet_exec.rs:150-203) + the FsProvider byte-range reads
+ * (:316-396).  Such an op takes no b200q_op_push: b200q_op_finish reads the split's row groups (FileScanExecConf.file_group,
+ * projection, limit; row-group pruning from pruning_predicates), decodes them on the GPU and drives the stages above the scan;
+ * pull the result as usual.  Files are opened from the local file system unless a reader is registered — the hook for the host's
+ * Hadoop FileSystem bridge (JniBridge.getResource(fsResourceId) in the reference): it must fill dst with bytes
+ * [offset, offset + length) of `path` and return 0. */
+typedef int32_t (*b200q_file_reader_fn)(void* ctx, const char* path, int64_t offset, int64_t length, uint8_t* dst);
+b200q_status b200q_set_file_reader(b200q_file_reader_fn fn, void* ctx);   /* process-wide; fn = NULL restores local files */
+/* Host-only helpers of the scan (no GPU needed; debugging and the CPU test-suite): render a Thrift-encoded FileMetaData footer
+ * (columns with their Arrow mapping, row groups, codecs, statistics) as text; raw Snappy decompression of one page body. */
+b200q_status b200q_parquet_explain(const uint8_t* footer, size_t n, char* buf, size_t cap, size_t* needed);
+b200q_status b200q_snappy_uncompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len);
 
 /* ---- ShuffleWriterExec result (plans rooted at ShuffleWriterExecNode) ----------------------------------------
  * Every pushed batch becomes one CHUNK: the rows of the batch grouped by output partition
