@@ -319,38 +319,70 @@ __global__ void __launch_bounds__(JB) join_probe_fused_kernel(const uint32_t* __
       if (lane == 0 && total) s_base = atomicAdd(cursor, (unsigned long long)total);
     }
     __syncthreads();
+    // output positions of this thread's rows (row order inside the tile)
+    unsigned long long o[JP_ROWS];
 #pragma unroll
-    for (int r = 0; r < JP_ROWS; r++) {
-      if (h[r] == 0xFFFFFFFEu) continue;
-      const long long i = t0 + r * JB + threadIdx.x;
-      const unsigned long long o = s_base + s_cnt[r * (JB / 32) + warp] + __popc(bal[r] & lt);
-      for (int c = 0; c < pc.ncols; c++) {
-        const GatherCol col = pc.col[c];
-        uint8_t ok = 1;
-        if (col.vbits) { const unsigned long long bi = (unsigned long long)i + col.bit_offset; ok = (col.vbits[bi >> 3] >> (bi & 7)) & 1; }
-        switch (col.width) {
-          case 1: ((uint8_t*)col.out)[o] = ((const uint8_t*)col.src)[i]; break;
-          case 2: ((uint16_t*)col.out)[o] = ((const uint16_t*)col.src)[i]; break;
-          case 4: ((uint32_t*)col.out)[o] = ((const uint32_t*)col.src)[i]; break;
-          case 8: ((unsigned long long*)col.out)[o] = ((const unsigned long long*)col.src)[i]; break;
-          default: ((u128*)col.out)[o] = ((const u128*)col.src)[i]; break;
+    for (int r = 0; r < JP_ROWS; r++) o[r] = s_base + s_cnt[r * (JB / 32) + warp] + __popc(bal[r] & lt);
+    // column by column: the eight loads of a column are issued back to back, then its eight stores
+    for (int c = 0; c < pc.ncols; c++) {
+      const GatherCol col = pc.col[c];
+      if (col.width == 8) {
+        unsigned long long v[JP_ROWS];
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) if (h[r] != 0xFFFFFFFEu) v[r] = ((const unsigned long long*)col.src)[t0 + r * JB + threadIdx.x];
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) if (h[r] != 0xFFFFFFFEu) ((unsigned long long*)col.out)[o[r]] = v[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) {
+          if (h[r] == 0xFFFFFFFEu) continue;
+          const long long i = t0 + r * JB + threadIdx.x;
+          switch (col.width) {
+            case 1: ((uint8_t*)col.out)[o[r]] = ((const uint8_t*)col.src)[i]; break;
+            case 2: ((uint16_t*)col.out)[o[r]] = ((const uint16_t*)col.src)[i]; break;
+            case 4: ((uint32_t*)col.out)[o[r]] = ((const uint32_t*)col.src)[i]; break;
+            default: ((u128*)col.out)[o[r]] = ((const u128*)col.src)[i]; break;
+          }
         }
-        if (col.out_valid) col.out_valid[o] = ok;
       }
-      const uint32_t b = h[r];
-      if (b != JOIN_NIL && mark) mark[b] = 1;
-      for (int c = 0; c < bc.ncols; c++) {
-        const GatherCol col = bc.col[c];
-        uint8_t ok = b != JOIN_NIL;
-        if (ok && col.vbytes) ok = col.vbytes[b];
-        switch (col.width) {
-          case 1: ((uint8_t*)col.out)[o] = ok ? ((const uint8_t*)col.src)[b] : 0; break;
-          case 2: ((uint16_t*)col.out)[o] = ok ? ((const uint16_t*)col.src)[b] : 0; break;
-          case 4: ((uint32_t*)col.out)[o] = ok ? ((const uint32_t*)col.src)[b] : 0; break;
-          case 8: ((unsigned long long*)col.out)[o] = ok ? ((const unsigned long long*)col.src)[b] : 0; break;
-          default: { u128 v{0, 0}; if (ok) v = ((const u128*)col.src)[b]; ((u128*)col.out)[o] = v; break; }
+      if (col.out_valid) {
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) {
+          if (h[r] == 0xFFFFFFFEu) continue;
+          uint8_t ok = 1;
+          if (col.vbits) { const unsigned long long bi = (unsigned long long)(t0 + r * JB + threadIdx.x) + col.bit_offset; ok = (col.vbits[bi >> 3] >> (bi & 7)) & 1; }
+          col.out_valid[o[r]] = ok;
         }
-        if (col.out_valid) col.out_valid[o] = ok;
+      }
+    }
+    if (mark) {
+#pragma unroll
+      for (int r = 0; r < JP_ROWS; r++) if (h[r] < 0xFFFFFFFEu) mark[h[r]] = 1;
+    }
+    for (int c = 0; c < bc.ncols; c++) {
+      const GatherCol col = bc.col[c];
+      if (col.width == 8 && !col.vbytes) {
+        unsigned long long v[JP_ROWS];
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) v[r] = h[r] < 0xFFFFFFFEu ? ((const unsigned long long*)col.src)[h[r]] : 0;
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) if (h[r] != 0xFFFFFFFEu) { ((unsigned long long*)col.out)[o[r]] = v[r]; if (col.out_valid) col.out_valid[o[r]] = h[r] != JOIN_NIL; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < JP_ROWS; r++) {
+          if (h[r] == 0xFFFFFFFEu) continue;
+          const uint32_t b = h[r];
+          uint8_t ok = b != JOIN_NIL;
+          if (ok && col.vbytes) ok = col.vbytes[b];
+          switch (col.width) {
+            case 1: ((uint8_t*)col.out)[o[r]] = ok ? ((const uint8_t*)col.src)[b] : 0; break;
+            case 2: ((uint16_t*)col.out)[o[r]] = ok ? ((const uint16_t*)col.src)[b] : 0; break;
+            case 4: ((uint32_t*)col.out)[o[r]] = ok ? ((const uint32_t*)col.src)[b] : 0; break;
+            case 8: ((unsigned long long*)col.out)[o[r]] = ok ? ((const unsigned long long*)col.src)[b] : 0; break;
+            default: { u128 v{0, 0}; if (ok) v = ((const u128*)col.src)[b]; ((u128*)col.out)[o[r]] = v; break; }
+          }
+          if (col.out_valid) col.out_valid[o[r]] = ok;
+        }
       }
     }
     __syncthreads();

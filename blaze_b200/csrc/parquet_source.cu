@@ -9,8 +9,13 @@
 // stages above the scan (FilterExec / AggExec / ...).  A row group is skipped when a pruning predicate `col cmp literal`
 // cannot hold for its [min, max] statistics — an optimisation only: Spark keeps the FilterExec above the scan, so the
 // rows that leave the pipeline are the same.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "kernels_join.cuh"
 #include "kernels_parquet.cuh"
@@ -27,21 +32,26 @@ namespace {
 
 inline size_t bitmap_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4; }
 
-struct FileIo {
-  std::string path; FILE* f = nullptr; int64_t size = -1;
+struct FileIo {                                   // positional reads: the column chunks of a row group are read by concurrent host threads
+  std::string path; int fd = -1; int64_t size = -1; std::mutex mu;
   explicit FileIo(const std::string& p, uint64_t declared_size) : path(p) {
     if (g_reader) { size = (int64_t)declared_size; return; }
     std::string local = p;
     if (local.rfind("file://", 0) == 0) local = local.substr(7); else if (local.rfind("file:", 0) == 0) local = local.substr(5);
-    f = fopen(local.c_str(), "rb");
-    if (!f) throw ExecError(B200Q_ERR_EXECUTION, "parquet: cannot open " + p + " (register a reader with b200q_set_file_reader for non-local file systems)");
-    fseek(f, 0, SEEK_END); size = ftell(f);
+    fd = open(local.c_str(), O_RDONLY);
+    if (fd < 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: cannot open " + p + " (register a reader with b200q_set_file_reader for non-local file systems)");
+    size = (int64_t)lseek(fd, 0, SEEK_END);
   }
-  ~FileIo() { if (f) fclose(f); }
+  ~FileIo() { if (fd >= 0) close(fd); }
   void read(int64_t off, size_t len, uint8_t* dst) {
     if (off < 0 || (int64_t)(off + (int64_t)len) > size) throw ExecError(B200Q_ERR_EXECUTION, "parquet: read past the end of " + path);
-    if (g_reader) { if (g_reader(g_reader_ctx, path.c_str(), off, (int64_t)len, dst) != 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: the file reader callback failed for " + path); return; }
-    if (fseek(f, (long)off, SEEK_SET) != 0 || fread(dst, 1, len, f) != len) throw ExecError(B200Q_ERR_EXECUTION, "parquet: short read from " + path);
+    if (g_reader) {                                  // the host's callback is not assumed to be re-entrant
+      std::lock_guard<std::mutex> l(mu);
+      if (g_reader(g_reader_ctx, path.c_str(), off, (int64_t)len, dst) != 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: the file reader callback failed for " + path);
+      return;
+    }
+    size_t got = 0;
+    while (got < len) { const ssize_t r = pread(fd, dst + got, len - got, (off_t)(off + (int64_t)got)); if (r <= 0) throw ExecError(B200Q_ERR_EXECUTION, "parquet: short read from " + path); got += (size_t)r; }
   }
 };
 
@@ -83,39 +93,51 @@ DevMemP upload(OpContext& cx, const void* p, size_t n, size_t pad = 16) {
   return d;
 }
 
-// one column chunk -> one device column of `rows` rows
-DevColumn decode_chunk(OpContext& cx, FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, DevMemP d_err) {
+// host half of one column chunk (runs on a worker thread): read, frame + decompress the pages, flatten them into one byte buffer and
+// two run tables (levels by row, values by stored-value ordinal)
+struct PreparedChunk {
+  std::vector<uint8_t> bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
+  int32_t dict_count = 0; bool has_dict = false, any_null = false;
+  std::string error; int error_code = 0;
+};
+
+void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, PreparedChunk& pc) {
   if (cs.arrow.id == T_NULL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " has a physical / logical type outside the GPU path");
   if (cs.arrow != want) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " is " + cs.arrow.str() + " in the file, the plan expects " + want.str() + " (schema adaption stays on the host)");
   std::vector<uint8_t> raw((size_t)cc.total_compressed_size);
   io.read(cc.start(), raw.size(), raw.data());
   std::vector<PqPage> pages = parquet_read_pages(raw.data(), raw.size(), cc, cs);
-  // flatten: page bodies back to back, level runs by row, value runs by stored-value ordinal
-  std::vector<uint8_t> bytes; std::vector<PqDevRun> lruns, vruns; const PqPage* dict = nullptr;
-  int64_t row = 0, ord = 0; bool any_null = false;
-  for (auto& pg : pages) if (pg.type != PQ_DICTIONARY_PAGE && !pg.def_runs.empty()) any_null = true;
+  int64_t row = 0, ord = 0;
+  size_t total = 0;
+  for (auto& pg : pages) { if (pg.type != PQ_DICTIONARY_PAGE) { total += pg.bytes.size(); if (!pg.def_runs.empty()) pc.any_null = true; } }
+  pc.bytes.reserve(total + 16);
   for (auto& pg : pages) {
-    if (pg.type == PQ_DICTIONARY_PAGE) { dict = &pg; continue; }
-    const uint64_t base = bytes.size();
-    bytes.insert(bytes.end(), pg.bytes.begin(), pg.bytes.end());
-    if (any_null) {
-      if (pg.def_runs.empty()) lruns.push_back(PqDevRun{(uint32_t)row, (uint32_t)pg.num_values, PQR_RLE, 1, {}, 1});
+    if (pg.type == PQ_DICTIONARY_PAGE) { pc.has_dict = true; pc.dict_count = pg.num_values; pc.dict_bytes.swap(pg.bytes); continue; }
+    const uint64_t base = pc.bytes.size();
+    pc.bytes.insert(pc.bytes.end(), pg.bytes.begin(), pg.bytes.end());
+    if (pc.any_null) {
+      if (pg.def_runs.empty()) pc.lruns.push_back(PqDevRun{(uint32_t)row, (uint32_t)pg.num_values, PQR_RLE, 1, {}, 1});
       uint32_t at = (uint32_t)row;
-      for (auto& r : pg.def_runs) { lruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), 1, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
+      for (auto& r : pg.def_runs) { pc.lruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), 1, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
     }
     if (pg.non_null > 0) {
       if (!pg.idx_runs.empty()) {
         uint32_t at = (uint32_t)ord;
-        for (auto& r : pg.idx_runs) { vruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), (uint8_t)pg.dict_bit_width, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
-      } else vruns.push_back(PqDevRun{(uint32_t)ord, (uint32_t)pg.non_null, PQR_PLAIN, 0, {}, base + pg.values_offset});
+        for (auto& r : pg.idx_runs) { pc.vruns.push_back(PqDevRun{at, r.count, (uint8_t)(r.is_rle ? PQR_RLE : PQR_BITPACKED), (uint8_t)pg.dict_bit_width, {}, r.is_rle ? r.value_or_bit_offset : base * 8 + r.value_or_bit_offset}); at += r.count; }
+      } else pc.vruns.push_back(PqDevRun{(uint32_t)ord, (uint32_t)pg.non_null, PQR_PLAIN, 0, {}, base + pg.values_offset});
     }
     row += pg.num_values; ord += pg.non_null;
   }
   if (row != rows) throw ExecError(B200Q_ERR_EXECUTION, "parquet: column " + cs.name + " holds " + std::to_string(row) + " values, its row group " + std::to_string(rows) + " rows");
+}
+
+// device half: upload + expand -> one device column of `rows` rows
+DevColumn decode_chunk(OpContext& cx, const PreparedChunk& pc, const PqColumnSchema& cs, const DType& want, int64_t rows, DevMemP d_err) {
+  const bool any_null = pc.any_null;
   PqDecodeSpec sp{};
-  DevMemP d_bytes = upload(cx, bytes.data(), bytes.size()), d_vruns = upload(cx, vruns.data(), vruns.size() * sizeof(PqDevRun)), d_dict, d_lruns;
-  sp.bytes = (const uint8_t*)d_bytes->ptr; sp.value_runs = (const PqDevRun*)d_vruns->ptr; sp.n_value_runs = (int)vruns.size();
-  if (dict) { d_dict = upload(cx, dict->bytes.data(), dict->bytes.size()); sp.dict = (const uint8_t*)d_dict->ptr; sp.dict_count = dict->num_values; }
+  DevMemP d_bytes = upload(cx, pc.bytes.data(), pc.bytes.size()), d_vruns = upload(cx, pc.vruns.data(), pc.vruns.size() * sizeof(PqDevRun)), d_dict, d_lruns;
+  sp.bytes = (const uint8_t*)d_bytes->ptr; sp.value_runs = (const PqDevRun*)d_vruns->ptr; sp.n_value_runs = (int)pc.vruns.size();
+  if (pc.has_dict) { d_dict = upload(cx, pc.dict_bytes.data(), pc.dict_bytes.size()); sp.dict = (const uint8_t*)d_dict->ptr; sp.dict_count = pc.dict_count; }
   int out_w = want.byte_width();
   switch (cs.type) {
     case PQ_BOOLEAN: sp.src_width = 0; sp.out_kind = PQO_BOOL_BYTES; out_w = 1; break;
@@ -125,13 +147,13 @@ DevColumn decode_chunk(OpContext& cx, FileIo& io, const PqColumnChunk& cc, const
     case PQ_DOUBLE: sp.src_width = 8; sp.out_kind = PQO_I64; break;
     default: sp.src_width = cs.type_length; sp.out_kind = PQO_DEC_FROM_FLBA; break;
   }
-  if (dict && sp.src_width > 0 && (int64_t)dict->bytes.size() < (int64_t)dict->num_values * sp.src_width) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary page shorter than its entry count");
+  if (pc.has_dict && sp.src_width > 0 && (int64_t)pc.dict_bytes.size() < (int64_t)pc.dict_count * sp.src_width) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary page shorter than its entry count");
   DevColumn col; col.type = want;
   DevMemP d_valid, d_ord;
   if (any_null) {
-    d_lruns = upload(cx, lruns.data(), lruns.size() * sizeof(PqDevRun));
+    d_lruns = upload(cx, pc.lruns.data(), pc.lruns.size() * sizeof(PqDevRun));
     d_valid = DevMem::alloc((size_t)rows + 16, cx.stream);
-    cx.m.launches += launch_pq_levels((const uint8_t*)d_bytes->ptr, (const PqDevRun*)d_lruns->ptr, (int)lruns.size(), rows, (uint8_t*)d_valid->ptr, cx.stream);
+    cx.m.launches += launch_pq_levels((const uint8_t*)d_bytes->ptr, (const PqDevRun*)d_lruns->ptr, (int)pc.lruns.size(), rows, (uint8_t*)d_valid->ptr, cx.stream);
     DevMemP fl = DevMem::alloc((size_t)rows * 4 + 16, cx.stream), sums = DevMem::alloc((size_t)scan_num_blocks(rows) * 4 + 16, cx.stream);
     d_ord = DevMem::alloc((size_t)(rows + 1) * 4, cx.stream);
     cx.m.launches += launch_bytes_to_flags((const uint8_t*)d_valid->ptr, rows, 0, (int32_t*)fl->ptr, cx.stream);
@@ -181,7 +203,24 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       if (rg.num_rows > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: row group above 2^31-1 rows");
       DevBatch b; b.num_rows = rg.num_rows;
       B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-      for (int pi : leaf.scan_projection) {
+      // host half of every projected chunk on its own thread (file read, Thrift, Snappy, run tables); the device half follows in column order
+      std::vector<PreparedChunk> prep(leaf.scan_projection.size());
+      {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
+          const int pi = leaf.scan_projection[k], fc = file_col_of[(size_t)pi];
+          if (fc < 0) continue;
+          th.emplace_back([&, k, pi, fc] {
+            try { prepare_chunk(io, rg.columns[(size_t)fc], meta.columns[(size_t)fc], leaf.scan_file_schema.fields[(size_t)pi].type, rg.num_rows, prep[k]); }
+            catch (const PlanError& e) { prep[k].error = e.what(); prep[k].error_code = e.code; }
+            catch (const ExecError& e) { prep[k].error = e.what(); prep[k].error_code = e.code; }
+            catch (const std::exception& e) { prep[k].error = e.what(); prep[k].error_code = B200Q_ERR_EXECUTION; }
+          });
+        }
+        for (auto& t : th) t.join();
+      }
+      for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
+        const int pi = leaf.scan_projection[k];
         const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
         const int fc = file_col_of[(size_t)pi];
         if (fc < 0) {                                                       // column missing in this file (schema evolution): all NULL
@@ -189,7 +228,10 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
           c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
           c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
           b.cols.push_back(c);
-        } else b.cols.push_back(decode_chunk(cx, io, rg.columns[(size_t)fc], meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
+          continue;
+        }
+        if (prep[k].error_code) throw ExecError(prep[k].error_code, prep[k].error);
+        b.cols.push_back(decode_chunk(cx, prep[k], meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
       }
       B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
       int err = 0;
