@@ -214,7 +214,9 @@ PqFileMeta parquet_parse_footer(const uint8_t* footer, size_t n) {
 size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
   size_t ip = 0; uint64_t ulen = 0; int shift = 0;
   while (true) { if (ip >= n) bad("snappy: truncated preamble"); const uint8_t b = src[ip++]; ulen |= (uint64_t)(b & 0x7F) << shift; if (!(b & 0x80)) break; shift += 7; if (shift > 35) bad("snappy: bad preamble"); }
-  out.resize((size_t)ulen);
+  const size_t start = out.size();
+  out.resize(start + (size_t)ulen);
+  uint8_t* const dst = out.data() + start;
   size_t op = 0;
   while (ip < n) {
     const uint8_t tag = src[ip++];
@@ -223,19 +225,20 @@ size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out
       case 0: {
         len = (size_t)(tag >> 2) + 1;
         if (len > 60) { const size_t nb = len - 60; if (ip + nb > n) bad("snappy: truncated literal length"); len = 0; for (size_t i = 0; i < nb; i++) len |= (size_t)src[ip + i] << (8 * i); len += 1; ip += nb; }
-        if (ip + len > n || op + len > out.size()) bad("snappy: literal overruns the buffer");
-        memcpy(out.data() + op, src + ip, len); ip += len; op += len;
+        if (ip + len > n || op + len > (size_t)ulen) bad("snappy: literal overruns the buffer");
+        memcpy(dst + op, src + ip, len); ip += len; op += len;
         continue;
       }
       case 1: if (ip + 1 > n) bad("snappy: truncated copy"); len = (size_t)((tag >> 2) & 7) + 4; offset = ((size_t)(tag >> 5) << 8) | src[ip]; ip += 1; break;
       case 2: if (ip + 2 > n) bad("snappy: truncated copy"); len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip] | ((size_t)src[ip + 1] << 8); ip += 2; break;
       default: if (ip + 4 > n) bad("snappy: truncated copy"); len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24); ip += 4; break;
     }
-    if (offset == 0 || offset > op || op + len > out.size()) bad("snappy: copy outside the buffer");
-    for (size_t i = 0; i < len; i++) out[op + i] = out[op - offset + i];             // byte-wise: copies may overlap their own output
+    if (offset == 0 || offset > op || op + len > (size_t)ulen) bad("snappy: copy outside the buffer");
+    if (offset >= len) memcpy(dst + op, dst + op - offset, len);
+    else for (size_t i = 0; i < len; i++) dst[op + i] = dst[op - offset + i];        // overlapping copy: byte-wise (run-length patterns)
     op += len;
   }
-  if (op != out.size()) bad("snappy: decompressed size mismatch");
+  if (op != (size_t)ulen) bad("snappy: decompressed size mismatch");
   return op;
 }
 
@@ -300,7 +303,8 @@ int64_t hybrid_runs(const uint8_t* data, size_t n, int bit_width, int64_t max_va
 
 }  // namespace
 
-std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs) {
+std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, std::vector<uint8_t>& out, std::vector<uint8_t>& dict_out) {
+  out.clear(); dict_out.clear();
   if (cc.codec != PQ_UNCOMPRESSED && cc.codec != PQ_SNAPPY) unsupported("compression codec " + std::to_string(cc.codec) + " (only UNCOMPRESSED and SNAPPY are decoded)");
   std::vector<PqPage> pages;
   size_t pos = 0; int64_t seen = 0;
@@ -312,22 +316,26 @@ std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqC
     pos += blen;
     if (h.type == PQ_INDEX_PAGE) continue;
     PqPage pg; pg.type = h.type; pg.num_values = h.num_values; pg.encoding = h.encoding;
+    std::vector<uint8_t>& dst = h.type == PQ_DICTIONARY_PAGE ? dict_out : out;
+    pg.base = dst.size();
     size_t levels = 0;
     if (h.type == PQ_DATA_PAGE_V2) {                               // levels are stored uncompressed in front of the (optionally compressed) values
       levels = (size_t)h.v2_rep_len + (size_t)h.v2_def_len;
       if (levels > blen) bad("v2 level bytes overrun the page");
       if (h.v2_rep_len) unsupported("repetition levels (nested columns)");
-      pg.bytes.assign(body, body + levels);
-      if (cc.codec == PQ_SNAPPY && h.v2_compressed && blen > levels) { std::vector<uint8_t> vals; snappy_uncompress(body + levels, blen - levels, vals); pg.bytes.insert(pg.bytes.end(), vals.begin(), vals.end()); }
-      else pg.bytes.insert(pg.bytes.end(), body + levels, body + blen);
-    } else if (cc.codec == PQ_SNAPPY) snappy_uncompress(body, blen, pg.bytes);
-    else pg.bytes.assign(body, body + blen);
+      dst.insert(dst.end(), body, body + levels);
+      if (cc.codec == PQ_SNAPPY && h.v2_compressed && blen > levels) snappy_uncompress(body + levels, blen - levels, dst);
+      else dst.insert(dst.end(), body + levels, body + blen);
+    } else if (cc.codec == PQ_SNAPPY) snappy_uncompress(body, blen, dst);
+    else dst.insert(dst.end(), body, body + blen);
+    pg.size = dst.size() - pg.base;
     if (h.type == PQ_DICTIONARY_PAGE) {
       if (h.encoding != PQ_PLAIN && h.encoding != PQ_PLAIN_DICTIONARY) unsupported("dictionary page encoding " + std::to_string(h.encoding));
       pg.values_offset = 0; pg.non_null = h.num_values;
       pages.push_back(std::move(pg));
       continue;
     }
+    const uint8_t* pb = dst.data() + pg.base;                        // valid until the next append (offsets are kept, not pointers)
     if (h.type != PQ_DATA_PAGE && h.type != PQ_DATA_PAGE_V2) unsupported("page type " + std::to_string(h.type));
     seen += h.num_values;
     size_t at = 0;
@@ -336,14 +344,14 @@ std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqC
       int64_t ones = 0;
       if (h.type == PQ_DATA_PAGE) {
         if (h.def_encoding != PQ_RLE) unsupported("definition level encoding " + std::to_string(h.def_encoding));
-        if (pg.bytes.size() < 4) bad("page without definition levels");
-        uint32_t len; memcpy(&len, pg.bytes.data(), 4);
-        if (4 + (size_t)len > pg.bytes.size()) bad("definition levels overrun the page");
-        hybrid_runs(pg.bytes.data() + 4, len, 1, h.num_values, pg.def_runs, &ones);
+        if (pg.size < 4) bad("page without definition levels");
+        uint32_t len; memcpy(&len, pb, 4);
+        if (4 + (size_t)len > pg.size) bad("definition levels overrun the page");
+        hybrid_runs(pb + 4, len, 1, h.num_values, pg.def_runs, &ones);
         for (auto& r : pg.def_runs) if (!r.is_rle) r.value_or_bit_offset += 32;          // bit offsets relative to bytes[0]
         at = 4 + len;
       } else {
-        hybrid_runs(pg.bytes.data(), (size_t)h.v2_def_len, 1, h.num_values, pg.def_runs, &ones);
+        hybrid_runs(pb, (size_t)h.v2_def_len, 1, h.num_values, pg.def_runs, &ones);
         at = levels;
       }
       pg.non_null = ones;
@@ -352,18 +360,18 @@ std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqC
     pg.values_offset = at;
     if (h.encoding == PQ_PLAIN_DICTIONARY || h.encoding == PQ_RLE_DICTIONARY) {
       if (pg.non_null > 0) {
-        if (at >= pg.bytes.size()) bad("dictionary-encoded page without a bit width");
-        pg.dict_bit_width = pg.bytes[at];
+        if (at >= pg.size) bad("dictionary-encoded page without a bit width");
+        pg.dict_bit_width = pb[at];
         if (pg.dict_bit_width > 32) bad("dictionary index width " + std::to_string(pg.dict_bit_width));
-        hybrid_runs(pg.bytes.data() + at + 1, pg.bytes.size() - at - 1, pg.dict_bit_width, pg.non_null, pg.idx_runs, nullptr);
+        hybrid_runs(pb + at + 1, pg.size - at - 1, pg.dict_bit_width, pg.non_null, pg.idx_runs, nullptr);
         for (auto& r : pg.idx_runs) if (!r.is_rle) r.value_or_bit_offset += (uint64_t)(at + 1) * 8;
       }
     } else if (h.encoding == PQ_PLAIN) {
     } else if (h.encoding == PQ_RLE && cs.type == PQ_BOOLEAN) {     // v2 Boolean values: u32 length + RLE hybrid of width 1
-      if (at + 4 > pg.bytes.size()) bad("RLE Boolean page without a length");
-      uint32_t len; memcpy(&len, pg.bytes.data() + at, 4);
+      if (at + 4 > pg.size) bad("RLE Boolean page without a length");
+      uint32_t len; memcpy(&len, pb + at, 4);
       pg.dict_bit_width = 1;
-      hybrid_runs(pg.bytes.data() + at + 4, len, 1, pg.non_null, pg.idx_runs, nullptr);
+      hybrid_runs(pb + at + 4, len, 1, pg.non_null, pg.idx_runs, nullptr);
       for (auto& r : pg.idx_runs) if (!r.is_rle) r.value_or_bit_offset += (uint64_t)(at + 4) * 8;
     } else unsupported("value encoding " + std::to_string(h.encoding) + " (PLAIN and RLE_DICTIONARY are decoded)");
     pages.push_back(std::move(pg));

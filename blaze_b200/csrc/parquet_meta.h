@@ -53,8 +53,8 @@ struct PqPage {
   int type = 0;                         // PQ_DATA_PAGE / PQ_DATA_PAGE_V2 / PQ_DICTIONARY_PAGE
   int32_t num_values = 0;               // entries incl. NULLs (data pages); dictionary entries
   int encoding = 0;
-  std::vector<uint8_t> bytes;           // decompressed page body
-  size_t values_offset = 0;             // where the value bytes start inside `bytes`
+  size_t base = 0, size = 0;            // the decompressed page body = out[base, base + size) of the buffer handed to parquet_read_pages
+  size_t values_offset = 0;             // where the value bytes start inside the body
   std::vector<PqRun> def_runs;          // definition levels (max level 1) as runs; empty: every value is present
   int dict_bit_width = 0;
   std::vector<PqRun> idx_runs;          // dictionary indices as runs (offsets relative to values_offset + 1)
@@ -63,8 +63,10 @@ struct PqPage {
 
 // walks the pages of one column chunk (`chunk` = its bytes [start, start + total_compressed_size)); throws PlanError(UNSUPPORTED) for
 // codecs / encodings outside the GPU path
-std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs);
+// data page bodies are appended to `out` (one contiguous buffer per chunk: what the device reads), the dictionary page's to `dict_out`;
+// both keep their capacity across calls so that a scan does not re-fault its buffers for every row group
+std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, std::vector<uint8_t>& out, std::vector<uint8_t>& dict_out);
 
-size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out);     // raw Snappy block format
+size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out);     // raw Snappy block format; appends to `out`, returns the decompressed size
 
 }  // namespace b200q

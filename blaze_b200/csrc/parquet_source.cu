@@ -12,7 +12,9 @@
 #include <fcntl.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -95,8 +97,8 @@ DevMemP upload(OpContext& cx, const void* p, size_t n, size_t pad = 16) {
 
 // host half of one column chunk (runs on a worker thread): read, frame + decompress the pages, flatten them into one byte buffer and
 // two run tables (levels by row, values by stored-value ordinal)
-struct PreparedChunk {
-  std::vector<uint8_t> bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
+struct PreparedChunk {                            // lives across the row groups of a scan: its buffers keep their capacity (no page faults per row group)
+  std::vector<uint8_t> raw, bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
   int32_t dict_count = 0; bool has_dict = false, any_null = false;
   std::string error; int error_code = 0;
 };
@@ -104,17 +106,15 @@ struct PreparedChunk {
 void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, PreparedChunk& pc) {
   if (cs.arrow.id == T_NULL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " has a physical / logical type outside the GPU path");
   if (cs.arrow != want) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " is " + cs.arrow.str() + " in the file, the plan expects " + want.str() + " (schema adaption stays on the host)");
-  std::vector<uint8_t> raw((size_t)cc.total_compressed_size);
-  io.read(cc.start(), raw.size(), raw.data());
-  std::vector<PqPage> pages = parquet_read_pages(raw.data(), raw.size(), cc, cs);
+  pc.lruns.clear(); pc.vruns.clear(); pc.has_dict = pc.any_null = false; pc.dict_count = 0; pc.error.clear(); pc.error_code = 0;
+  pc.raw.resize((size_t)cc.total_compressed_size);
+  io.read(cc.start(), pc.raw.size(), pc.raw.data());
+  std::vector<PqPage> pages = parquet_read_pages(pc.raw.data(), pc.raw.size(), cc, cs, pc.bytes, pc.dict_bytes);
   int64_t row = 0, ord = 0;
-  size_t total = 0;
-  for (auto& pg : pages) { if (pg.type != PQ_DICTIONARY_PAGE) { total += pg.bytes.size(); if (!pg.def_runs.empty()) pc.any_null = true; } }
-  pc.bytes.reserve(total + 16);
+  for (auto& pg : pages) if (pg.type != PQ_DICTIONARY_PAGE && !pg.def_runs.empty()) pc.any_null = true;
   for (auto& pg : pages) {
-    if (pg.type == PQ_DICTIONARY_PAGE) { pc.has_dict = true; pc.dict_count = pg.num_values; pc.dict_bytes.swap(pg.bytes); continue; }
-    const uint64_t base = pc.bytes.size();
-    pc.bytes.insert(pc.bytes.end(), pg.bytes.begin(), pg.bytes.end());
+    if (pg.type == PQ_DICTIONARY_PAGE) { pc.has_dict = true; pc.dict_count = pg.num_values; continue; }
+    const uint64_t base = pg.base;
     if (pc.any_null) {
       if (pg.def_runs.empty()) pc.lruns.push_back(PqDevRun{(uint32_t)row, (uint32_t)pg.num_values, PQR_RLE, 1, {}, 1});
       uint32_t at = (uint32_t)row;
@@ -171,8 +171,12 @@ DevColumn decode_chunk(OpContext& cx, const PreparedChunk& pc, const PqColumnSch
 }  // namespace
 
 void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<void(DevBatch&)>& emit) {
+  static const bool timing = getenv("B200Q_PARQUET_TIMING") != nullptr;       // where a scan's wall time goes (stderr)
+  double t_prep = 0, t_dev = 0, t_sync = 0, t_emit = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   int64_t remaining = leaf.scan_has_limit ? (int64_t)leaf.scan_limit : -1;
   DevMemP d_err = DevMem::alloc(16, cx.stream, true);
+  std::vector<PreparedChunk> prep;
   for (auto& sf : leaf.scan_files) {
     if (remaining == 0) break;
     FileIo io(sf.path, sf.size);
@@ -204,7 +208,8 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       DevBatch b; b.num_rows = rg.num_rows;
       B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
       // host half of every projected chunk on its own thread (file read, Thrift, Snappy, run tables); the device half follows in column order
-      std::vector<PreparedChunk> prep(leaf.scan_projection.size());
+      prep.resize(leaf.scan_projection.size());
+      const double t0 = now();
       {
         std::vector<std::thread> th;
         for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
@@ -219,6 +224,7 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
         }
         for (auto& t : th) t.join();
       }
+      const double t1 = now(); t_prep += t1 - t0;
       for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
         const int pi = leaf.scan_projection[k];
         const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
@@ -234,17 +240,22 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
         b.cols.push_back(decode_chunk(cx, prep[k], meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
       }
       B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+      const double t2 = now(); t_dev += t2 - t1;
       int err = 0;
       B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
       B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      const double t3 = now(); t_sync += t3 - t2;
       if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
       { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
       if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
       if (remaining >= 0) remaining -= b.num_rows;
       cx.m.input_rows += b.num_rows; cx.m.input_batches++;
+      const double t4 = now();
       emit(b);
+      t_emit += now() - t4;
     }
   }
+  if (timing) fprintf(stderr, "parquet scan: host prepare %.1f ms, upload + launch %.1f ms, wait for the device %.1f ms, stages above %.1f ms\n", t_prep, t_dev, t_sync, t_emit);
 }
 
 }  // namespace b200q
