@@ -196,8 +196,9 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       for (size_t j = 0; j < meta.columns.size() && file_col_of[i] < 0; j++)
         if (meta.columns[j].name.size() == want.size()) { bool eq = true; for (size_t k = 0; k < want.size(); k++) eq = eq && tolower((unsigned char)want[k]) == tolower((unsigned char)meta.columns[j].name[k]); if (eq) file_col_of[i] = (int)j; }
     }
+    // the row groups of this split that survive pruning
+    std::vector<const PqRowGroup*> todo;
     for (auto& rg : meta.row_groups) {
-      if (remaining == 0) break;
       if (rg.num_rows == 0 || rg.columns.empty()) continue;
       const int64_t rg_start = rg.columns[0].start();                     // a row group belongs to the split that holds its first byte
       if (sf.has_range && (rg_start < sf.range_start || rg_start >= sf.range_end)) continue;
@@ -205,54 +206,70 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       for (auto& p : leaf.scan_pruning) keep = keep && may_match(p, file_col_of, meta, rg);
       if (!keep) { cx.m.fast_launches++; continue; }                        // pruned row groups show up in fast_path_launches
       if (rg.num_rows > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: row group above 2^31-1 rows");
-      DevBatch b; b.num_rows = rg.num_rows;
-      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-      // host half of every projected chunk on its own thread (file read, Thrift, Snappy, run tables); the device half follows in column order
-      prep.resize(leaf.scan_projection.size());
+      todo.push_back(&rg);
+    }
+    // host half (file read, Thrift, Snappy, run tables): one thread per (row group, projected chunk), a window of row groups at a time so that
+    // the host cores are busy; device half (upload, expand, stages above) in row-group order
+    const size_t ncol = leaf.scan_projection.size();
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t window = std::max<size_t>(1, std::min<size_t>(8, hw / std::max<size_t>(1, ncol)));
+    prep.resize(window * ncol);
+    for (size_t w0 = 0; w0 < todo.size() && remaining != 0; w0 += window) {
+      const size_t wn = std::min(window, todo.size() - w0);
       const double t0 = now();
       {
         std::vector<std::thread> th;
-        for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
-          const int pi = leaf.scan_projection[k], fc = file_col_of[(size_t)pi];
-          if (fc < 0) continue;
-          th.emplace_back([&, k, pi, fc] {
-            try { prepare_chunk(io, rg.columns[(size_t)fc], meta.columns[(size_t)fc], leaf.scan_file_schema.fields[(size_t)pi].type, rg.num_rows, prep[k]); }
-            catch (const PlanError& e) { prep[k].error = e.what(); prep[k].error_code = e.code; }
-            catch (const ExecError& e) { prep[k].error = e.what(); prep[k].error_code = e.code; }
-            catch (const std::exception& e) { prep[k].error = e.what(); prep[k].error_code = B200Q_ERR_EXECUTION; }
-          });
-        }
+        for (size_t w = 0; w < wn; w++)
+          for (size_t k = 0; k < ncol; k++) {
+            const int pi = leaf.scan_projection[k], fc = file_col_of[(size_t)pi];
+            if (fc < 0) continue;
+            const PqRowGroup* rg = todo[w0 + w];
+            PreparedChunk* pc = &prep[w * ncol + k];
+            th.emplace_back([&, rg, pc, pi, fc] {
+              try { prepare_chunk(io, rg->columns[(size_t)fc], meta.columns[(size_t)fc], leaf.scan_file_schema.fields[(size_t)pi].type, rg->num_rows, *pc); }
+              catch (const PlanError& e) { pc->error = e.what(); pc->error_code = e.code; }
+              catch (const ExecError& e) { pc->error = e.what(); pc->error_code = e.code; }
+              catch (const std::exception& e) { pc->error = e.what(); pc->error_code = B200Q_ERR_EXECUTION; }
+            });
+          }
         for (auto& t : th) t.join();
       }
-      const double t1 = now(); t_prep += t1 - t0;
-      for (size_t k = 0; k < leaf.scan_projection.size(); k++) {
-        const int pi = leaf.scan_projection[k];
-        const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
-        const int fc = file_col_of[(size_t)pi];
-        if (fc < 0) {                                                       // column missing in this file (schema evolution): all NULL
-          DevColumn c; c.type = f.type;
-          c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
-          c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
-          b.cols.push_back(c);
-          continue;
+      t_prep += now() - t0;
+      for (size_t w = 0; w < wn && remaining != 0; w++) {
+        const PqRowGroup& rg = *todo[w0 + w];
+        const double t1 = now();
+        DevBatch b; b.num_rows = rg.num_rows;
+        B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+        for (size_t k = 0; k < ncol; k++) {
+          const int pi = leaf.scan_projection[k];
+          const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
+          const int fc = file_col_of[(size_t)pi];
+          if (fc < 0) {                                                     // column missing in this file (schema evolution): all NULL
+            DevColumn c; c.type = f.type;
+            c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
+            c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
+            b.cols.push_back(c);
+            continue;
+          }
+          const PreparedChunk& pc = prep[w * ncol + k];
+          if (pc.error_code) throw ExecError(pc.error_code, pc.error);
+          b.cols.push_back(decode_chunk(cx, pc, meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
         }
-        if (prep[k].error_code) throw ExecError(prep[k].error_code, prep[k].error);
-        b.cols.push_back(decode_chunk(cx, prep[k], meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
+        B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+        const double t2 = now(); t_dev += t2 - t1;
+        int err = 0;
+        B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
+        B200Q_CUDA(cudaStreamSynchronize(cx.stream));                      // the pageable uploads of this row group have left the prepared buffers
+        const double t3 = now(); t_sync += t3 - t2;
+        if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
+        { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
+        if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
+        if (remaining >= 0) remaining -= b.num_rows;
+        cx.m.input_rows += b.num_rows; cx.m.input_batches++;
+        const double t4 = now();
+        emit(b);
+        t_emit += now() - t4;
       }
-      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
-      const double t2 = now(); t_dev += t2 - t1;
-      int err = 0;
-      B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-      const double t3 = now(); t_sync += t3 - t2;
-      if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
-      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
-      if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
-      if (remaining >= 0) remaining -= b.num_rows;
-      cx.m.input_rows += b.num_rows; cx.m.input_batches++;
-      const double t4 = now();
-      emit(b);
-      t_emit += now() - t4;
     }
   }
   if (timing) fprintf(stderr, "parquet scan: host prepare %.1f ms, upload + launch %.1f ms, wait for the device %.1f ms, stages above %.1f ms\n", t_prep, t_dev, t_sync, t_emit);

@@ -17,7 +17,9 @@ sys.path.insert(0, ROOT)
 
 def main(argv):
     out = os.environ.get("B200Q_EMU_DIR") or os.path.join(os.environ.get("TMPDIR", "/tmp"), "b200q_emu")
-    lib = subprocess.run([os.path.join(HERE, "build_lib.sh"), out], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    lib = os.path.join(out, "libblaze_b200_emu.so")
+    if not (os.environ.get("B200Q_EMU_REUSE") and os.path.exists(lib)):               # B200Q_EMU_REUSE=1: several runs share one build (tests/test_pipeline_emulated.py)
+        lib = subprocess.run([os.path.join(HERE, "build_lib.sh"), out], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     from blaze_b200 import native
     native.LIB_PATH = lib
     native.lib = native._load()
