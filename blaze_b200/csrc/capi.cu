@@ -747,10 +747,10 @@ b200q_status b200q_parquet_explain(const uint8_t* footer, size_t n, char* buf, s
 b200q_status b200q_snappy_uncompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len) {
   if ((!src && n) || !out_len) return fail(B200Q_ERR_INVALID_ARG, "null argument");
   return guarded(nullptr, [&] {
-    std::vector<uint8_t> v; snappy_uncompress(src, n, v);
+    ByteBuf v; snappy_uncompress(src, n, v);
     *out_len = v.size();
     if (!dst || cap < v.size()) throw ExecError(B200Q_ERR_INVALID_ARG, "snappy output needs " + std::to_string(v.size()) + " bytes");
-    if (!v.empty()) memcpy(dst, v.data(), v.size());
+    if (v.size()) memcpy(dst, v.data(), v.size());
   });
 }
 b200q_status b200q_set_file_reader(b200q_file_reader_fn fn, void* ctx) { set_file_reader(fn, ctx); return B200Q_OK; }

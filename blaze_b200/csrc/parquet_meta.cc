@@ -10,6 +10,7 @@
 // SURVEY.md §8(f)-3 prescribes: the reference holds no native golden for this path ("parity unpinned").
 #include "parquet_meta.h"
 
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/blaze_b200.h"
@@ -211,12 +212,21 @@ PqFileMeta parquet_parse_footer(const uint8_t* footer, size_t n) {
 }
 
 // ---- Snappy raw format ------------------------------------------------------------------------------------------------
-size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+void ByteBuf::reserve(size_t want) {
+  if (want <= cap) return;
+  size_t nc = (size_t)1 << 16; while (nc < want) nc <<= 1;                       // power-of-two capacities: blocks are interchangeable in the scan's pinned pool
+  uint8_t* np = (uint8_t*)(alloc_fn ? alloc_fn(nc) : malloc(nc));
+  if (!np) throw PlanError(B200Q_ERR_EXECUTION, "parquet: out of host memory for " + std::to_string(nc) + " bytes of page data");
+  if (n) memcpy(np, p, n);
+  if (p) { if (free_fn) free_fn(p); else free(p); }
+  p = np; cap = nc;
+}
+
+size_t snappy_uncompress(const uint8_t* src, size_t n, ByteBuf& out) {
   size_t ip = 0; uint64_t ulen = 0; int shift = 0;
   while (true) { if (ip >= n) bad("snappy: truncated preamble"); const uint8_t b = src[ip++]; ulen |= (uint64_t)(b & 0x7F) << shift; if (!(b & 0x80)) break; shift += 7; if (shift > 35) bad("snappy: bad preamble"); }
-  const size_t start = out.size();
-  out.resize(start + (size_t)ulen);
-  uint8_t* const dst = out.data() + start;
+  if (ulen > (uint64_t)1 << 31) bad("snappy: block above 2 GiB");
+  uint8_t* const dst = out.grow((size_t)ulen);
   size_t op = 0;
   while (ip < n) {
     const uint8_t tag = src[ip++];
@@ -303,7 +313,7 @@ int64_t hybrid_runs(const uint8_t* data, size_t n, int bit_width, int64_t max_va
 
 }  // namespace
 
-std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, std::vector<uint8_t>& out, std::vector<uint8_t>& dict_out) {
+std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, ByteBuf& out, ByteBuf& dict_out) {
   out.clear(); dict_out.clear();
   if (cc.codec != PQ_UNCOMPRESSED && cc.codec != PQ_SNAPPY) unsupported("compression codec " + std::to_string(cc.codec) + " (only UNCOMPRESSED and SNAPPY are decoded)");
   std::vector<PqPage> pages;
@@ -316,18 +326,18 @@ std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqC
     pos += blen;
     if (h.type == PQ_INDEX_PAGE) continue;
     PqPage pg; pg.type = h.type; pg.num_values = h.num_values; pg.encoding = h.encoding;
-    std::vector<uint8_t>& dst = h.type == PQ_DICTIONARY_PAGE ? dict_out : out;
+    ByteBuf& dst = h.type == PQ_DICTIONARY_PAGE ? dict_out : out;
     pg.base = dst.size();
     size_t levels = 0;
     if (h.type == PQ_DATA_PAGE_V2) {                               // levels are stored uncompressed in front of the (optionally compressed) values
       levels = (size_t)h.v2_rep_len + (size_t)h.v2_def_len;
       if (levels > blen) bad("v2 level bytes overrun the page");
       if (h.v2_rep_len) unsupported("repetition levels (nested columns)");
-      dst.insert(dst.end(), body, body + levels);
+      dst.append(body, levels);
       if (cc.codec == PQ_SNAPPY && h.v2_compressed && blen > levels) snappy_uncompress(body + levels, blen - levels, dst);
-      else dst.insert(dst.end(), body + levels, body + blen);
+      else dst.append(body + levels, blen - levels);
     } else if (cc.codec == PQ_SNAPPY) snappy_uncompress(body, blen, dst);
-    else dst.insert(dst.end(), body, body + blen);
+    else dst.append(body, blen);
     pg.size = dst.size() - pg.base;
     if (h.type == PQ_DICTIONARY_PAGE) {
       if (h.encoding != PQ_PLAIN && h.encoding != PQ_PLAIN_DICTIONARY) unsupported("dictionary page encoding " + std::to_string(h.encoding));

@@ -2,6 +2,8 @@
 // PageHeader, page decompression (Snappy, uncompressed), RLE / bit-packed hybrid run tables.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -48,6 +50,23 @@ PqFileMeta parquet_parse_footer(const uint8_t* footer, size_t n);
 
 struct PqRun { uint32_t count; uint32_t is_rle; uint64_t value_or_bit_offset; };      // RLE run: the value; bit-packed run: bit offset of its first value inside the page's value bytes
 
+// growable byte buffer for decompressed page bodies.  Plain heap by default; the scan backs it with pinned host memory (alloc_fn / free_fn) so that
+// the upload of a column chunk is a DMA straight out of the buffer the pages were decompressed into.  Bytes appended are not initialised.
+struct ByteBuf {
+  uint8_t* p = nullptr; size_t n = 0, cap = 0;
+  void* (*alloc_fn)(size_t) = nullptr; void (*free_fn)(void*) = nullptr;
+  ByteBuf() = default;
+  ByteBuf(const ByteBuf&) = delete; ByteBuf& operator=(const ByteBuf&) = delete;
+  ~ByteBuf() { release(); }
+  void release() { if (p) { if (free_fn) free_fn(p); else free(p); } p = nullptr; n = cap = 0; }
+  void reserve(size_t want);
+  uint8_t* grow(size_t add) { reserve(n + add); uint8_t* r = p + n; n += add; return r; }
+  void append(const uint8_t* s, size_t len) { if (len) memcpy(grow(len), s, len); }
+  void clear() { n = 0; }
+  const uint8_t* data() const { return p; }
+  size_t size() const { return n; }
+};
+
 // one decoded (decompressed) page, described for the device
 struct PqPage {
   int type = 0;                         // PQ_DATA_PAGE / PQ_DATA_PAGE_V2 / PQ_DICTIONARY_PAGE
@@ -65,8 +84,8 @@ struct PqPage {
 // codecs / encodings outside the GPU path
 // data page bodies are appended to `out` (one contiguous buffer per chunk: what the device reads), the dictionary page's to `dict_out`;
 // both keep their capacity across calls so that a scan does not re-fault its buffers for every row group
-std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, std::vector<uint8_t>& out, std::vector<uint8_t>& dict_out);
+std::vector<PqPage> parquet_read_pages(const uint8_t* chunk, size_t n, const PqColumnChunk& cc, const PqColumnSchema& cs, ByteBuf& out, ByteBuf& dict_out);
 
-size_t snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out);     // raw Snappy block format; appends to `out`, returns the decompressed size
+size_t snappy_uncompress(const uint8_t* src, size_t n, ByteBuf& out);     // raw Snappy block format; appends to `out`, returns the decompressed size
 
 }  // namespace b200q

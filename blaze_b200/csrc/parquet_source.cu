@@ -16,8 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "kernels_join.cuh"
 #include "kernels_parquet.cuh"
@@ -97,18 +100,43 @@ DevMemP upload(OpContext& cx, const void* p, size_t n, size_t pad = 16) {
 
 // host half of one column chunk (runs on a worker thread): read, frame + decompress the pages, flatten them into one byte buffer and
 // two run tables (levels by row, values by stored-value ordinal)
-struct PreparedChunk {                            // lives across the row groups of a scan: its buffers keep their capacity (no page faults per row group)
-  std::vector<uint8_t> raw, bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
+// Pinned host blocks outlive a scan: pinning pages costs ~1 ms per MB and a long-lived executor runs scan after scan.  Process-wide pool of
+// power-of-two blocks, bounded in bytes (B200Q_SCAN_HOST_CACHE_MB, default 2048); blocks above the bound go back to the driver.
+struct PinnedPool {
+  std::mutex mu; std::unordered_map<void*, size_t> size_of; std::unordered_map<size_t, std::vector<void*>> free_blocks; size_t cached = 0;
+  static size_t budget() { static const size_t b = [] { const char* e = getenv("B200Q_SCAN_HOST_CACHE_MB"); return (size_t)(e ? atoll(e) : 2048) << 20; }(); return b; }
+  static size_t size_class(size_t n) { size_t c = (size_t)1 << 18; while (c < n) c <<= 1; return c; }
+  void* get(size_t n) {
+    const size_t c = size_class(n);
+    { std::lock_guard<std::mutex> l(mu); auto it = free_blocks.find(c); if (it != free_blocks.end() && !it->second.empty()) { void* p = it->second.back(); it->second.pop_back(); cached -= c; return p; } }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, c) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> l(mu); size_of[p] = c; return p;
+  }
+  void put(void* p) {
+    { std::lock_guard<std::mutex> l(mu); const size_t c = size_of[p]; if (cached + c <= budget()) { cached += c; free_blocks[c].push_back(p); return; } size_of.erase(p); }
+    cudaFreeHost(p);
+  }
+};
+PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }            // leaked on purpose: no pinned frees after the driver is gone
+void* pinned_alloc(size_t n) { return pinned_pool().get(n); }
+void pinned_free(void* p) { pinned_pool().put(p); }
+
+// host half of one column chunk: the file bytes, the decompressed page bodies (what the device reads) and the run tables
+struct PreparedChunk {
+  ByteBuf raw, bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
   int32_t dict_count = 0; bool has_dict = false, any_null = false;
   std::string error; int error_code = 0;
+  PreparedChunk() { for (ByteBuf* b : {&raw, &bytes, &dict_bytes}) { b->alloc_fn = pinned_alloc; b->free_fn = pinned_free; } }
 };
 
 void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, PreparedChunk& pc) {
   if (cs.arrow.id == T_NULL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " has a physical / logical type outside the GPU path");
   if (cs.arrow != want) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: column " + cs.name + " is " + cs.arrow.str() + " in the file, the plan expects " + want.str() + " (schema adaption stays on the host)");
   pc.lruns.clear(); pc.vruns.clear(); pc.has_dict = pc.any_null = false; pc.dict_count = 0; pc.error.clear(); pc.error_code = 0;
-  pc.raw.resize((size_t)cc.total_compressed_size);
-  io.read(cc.start(), pc.raw.size(), pc.raw.data());
+  pc.raw.clear();
+  io.read(cc.start(), (size_t)cc.total_compressed_size, pc.raw.grow((size_t)cc.total_compressed_size));
+  pc.bytes.reserve((size_t)std::max<int64_t>(cc.total_uncompressed_size, cc.total_compressed_size) + 64);   // page bodies <= the chunk's uncompressed size: no regrowth of the pinned buffer
   std::vector<PqPage> pages = parquet_read_pages(pc.raw.data(), pc.raw.size(), cc, cs, pc.bytes, pc.dict_bytes);
   int64_t row = 0, ord = 0;
   for (auto& pg : pages) if (pg.type != PQ_DICTIONARY_PAGE && !pg.def_runs.empty()) pc.any_null = true;
@@ -174,9 +202,10 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
   static const bool timing = getenv("B200Q_PARQUET_TIMING") != nullptr;       // where a scan's wall time goes (stderr)
   double t_prep = 0, t_dev = 0, t_sync = 0, t_emit = 0;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   int64_t remaining = leaf.scan_has_limit ? (int64_t)leaf.scan_limit : -1;
   DevMemP d_err = DevMem::alloc(16, cx.stream, true);
-  std::vector<PreparedChunk> prep;
+  std::vector<std::unique_ptr<PreparedChunk>> prep;   // the ring of prepared chunks of this scan (their buffers return to the pinned pool with them)
   for (auto& sf : leaf.scan_files) {
     if (remaining == 0) break;
     FileIo io(sf.path, sf.size);
@@ -208,71 +237,87 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       if (rg.num_rows > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "parquet: row group above 2^31-1 rows");
       todo.push_back(&rg);
     }
-    // host half (file read, Thrift, Snappy, run tables): one thread per (row group, projected chunk), a window of row groups at a time so that
-    // the host cores are busy; device half (upload, expand, stages above) in row-group order
+    // host half (file read, Thrift, Snappy, run tables): a pool of worker threads takes the (row group, projected chunk) tasks in order and
+    // fills a ring of row-group slots; device half (upload, expand, stages above) on this thread, in row-group order, while the workers
+    // are already preparing the row groups behind it
     const size_t ncol = leaf.scan_projection.size();
+    const size_t ntasks = todo.size() * ncol;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t window = std::max<size_t>(1, std::min<size_t>(8, hw / std::max<size_t>(1, ncol)));
-    prep.resize(window * ncol);
-    for (size_t w0 = 0; w0 < todo.size() && remaining != 0; w0 += window) {
-      const size_t wn = std::min(window, todo.size() - w0);
-      const double t0 = now();
-      {
-        std::vector<std::thread> th;
-        for (size_t w = 0; w < wn; w++)
-          for (size_t k = 0; k < ncol; k++) {
-            const int pi = leaf.scan_projection[k], fc = file_col_of[(size_t)pi];
-            if (fc < 0) continue;
-            const PqRowGroup* rg = todo[w0 + w];
-            PreparedChunk* pc = &prep[w * ncol + k];
-            th.emplace_back([&, rg, pc, pi, fc] {
-              try { prepare_chunk(io, rg->columns[(size_t)fc], meta.columns[(size_t)fc], leaf.scan_file_schema.fields[(size_t)pi].type, rg->num_rows, *pc); }
-              catch (const PlanError& e) { pc->error = e.what(); pc->error_code = e.code; }
-              catch (const ExecError& e) { pc->error = e.what(); pc->error_code = e.code; }
-              catch (const std::exception& e) { pc->error = e.what(); pc->error_code = B200Q_ERR_EXECUTION; }
-            });
-          }
-        for (auto& t : th) t.join();
-      }
-      t_prep += now() - t0;
-      for (size_t w = 0; w < wn && remaining != 0; w++) {
-        const PqRowGroup& rg = *todo[w0 + w];
-        const double t1 = now();
-        DevBatch b; b.num_rows = rg.num_rows;
-        B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-        for (size_t k = 0; k < ncol; k++) {
-          const int pi = leaf.scan_projection[k];
-          const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
-          const int fc = file_col_of[(size_t)pi];
-          if (fc < 0) {                                                     // column missing in this file (schema evolution): all NULL
-            DevColumn c; c.type = f.type;
-            c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
-            c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
-            b.cols.push_back(c);
-            continue;
-          }
-          const PreparedChunk& pc = prep[w * ncol + k];
-          if (pc.error_code) throw ExecError(pc.error_code, pc.error);
-          b.cols.push_back(decode_chunk(cx, pc, meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t)hw, (size_t)32, ntasks}));
+    const size_t ring = std::min(todo.size(), (nthreads + ncol - 1) / std::max<size_t>(1, ncol) + 3);
+    while (prep.size() < ring * ncol) prep.push_back(std::make_unique<PreparedChunk>());
+    struct Shared {
+      std::mutex mu; std::condition_variable cv_done, cv_free;
+      std::vector<int> done; size_t consumed = 0, next = 0; bool stop = false;
+    } sh;
+    sh.done.assign(todo.size(), 0);
+    auto worker = [&] {
+      while (true) {
+        size_t t;
+        { std::unique_lock<std::mutex> l(sh.mu); t = sh.next++; if (t >= ntasks) return;
+          sh.cv_free.wait(l, [&] { return sh.stop || t / ncol < sh.consumed + ring; });
+          if (sh.stop) return; }
+        const size_t rgi = t / ncol, k = t % ncol;
+        const int pi = leaf.scan_projection[k], fc = file_col_of[(size_t)pi];
+        if (fc >= 0) {
+          PreparedChunk* pc = prep[(rgi % ring) * ncol + k].get();
+          const PqRowGroup* rg = todo[rgi];
+          try { prepare_chunk(io, rg->columns[(size_t)fc], meta.columns[(size_t)fc], leaf.scan_file_schema.fields[(size_t)pi].type, rg->num_rows, *pc); }
+          catch (const PlanError& e) { pc->error = e.what(); pc->error_code = e.code; }
+          catch (const ExecError& e) { pc->error = e.what(); pc->error_code = e.code; }
+          catch (const std::exception& e) { pc->error = e.what(); pc->error_code = B200Q_ERR_EXECUTION; }
         }
-        B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
-        const double t2 = now(); t_dev += t2 - t1;
-        int err = 0;
-        B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
-        B200Q_CUDA(cudaStreamSynchronize(cx.stream));                      // the pageable uploads of this row group have left the prepared buffers
-        const double t3 = now(); t_sync += t3 - t2;
-        if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
-        { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
-        if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
-        if (remaining >= 0) remaining -= b.num_rows;
-        cx.m.input_rows += b.num_rows; cx.m.input_batches++;
-        const double t4 = now();
-        emit(b);
-        t_emit += now() - t4;
+        { std::lock_guard<std::mutex> l(sh.mu); sh.done[rgi]++; }
+        sh.cv_done.notify_all();
       }
+    };
+    struct Pool {                                   // joins on every exit path (an error in the device half must not leave workers behind)
+      Shared& sh; std::vector<std::thread> th;
+      ~Pool() { { std::lock_guard<std::mutex> l(sh.mu); sh.stop = true; } sh.cv_free.notify_all(); for (auto& t : th) t.join(); }
+    } pool{sh, {}};
+    for (size_t i = 0; i < nthreads && ntasks; i++) pool.th.emplace_back(worker);
+    for (size_t rgi = 0; rgi < todo.size() && remaining != 0; rgi++) {
+      const PqRowGroup& rg = *todo[rgi];
+      const double t0 = now();
+      { std::unique_lock<std::mutex> l(sh.mu); sh.cv_done.wait(l, [&] { return sh.done[rgi] == (int)ncol; }); }
+      const double t1 = now(); t_prep += t1 - t0;
+      DevBatch b; b.num_rows = rg.num_rows;
+      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+      for (size_t k = 0; k < ncol; k++) {
+        const int pi = leaf.scan_projection[k];
+        const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
+        const int fc = file_col_of[(size_t)pi];
+        if (fc < 0) {                                                     // column missing in this file (schema evolution): all NULL
+          DevColumn c; c.type = f.type;
+          c.values = DevMem::alloc(f.type.id == T_BOOL ? bitmap_bytes(rg.num_rows) : (size_t)rg.num_rows * f.type.byte_width() + 16, cx.stream, true);
+          c.validity = DevMem::alloc(bitmap_bytes(rg.num_rows), cx.stream, true);
+          b.cols.push_back(c);
+          continue;
+        }
+        const PreparedChunk& pc = *prep[(rgi % ring) * ncol + k];
+        if (pc.error_code) throw ExecError(pc.error_code, pc.error);
+        b.cols.push_back(decode_chunk(cx, pc, meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
+      }
+      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+      const double t2 = now(); t_dev += t2 - t1;
+      int err = 0;
+      B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaStreamSynchronize(cx.stream));                      // the uploads of this row group have left the prepared buffers: its ring slot is free
+      { std::lock_guard<std::mutex> l(sh.mu); sh.consumed = rgi + 1; }
+      sh.cv_free.notify_all();
+      const double t3 = now(); t_sync += t3 - t2;
+      if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
+      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
+      if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
+      if (remaining >= 0) remaining -= b.num_rows;
+      cx.m.input_rows += b.num_rows; cx.m.input_batches++;
+      const double t4 = now();
+      emit(b);
+      t_emit += now() - t4;
     }
   }
-  if (timing) fprintf(stderr, "parquet scan: host prepare %.1f ms, upload + launch %.1f ms, wait for the device %.1f ms, stages above %.1f ms\n", t_prep, t_dev, t_sync, t_emit);
+  if (timing) fprintf(stderr, "parquet scan: %.1f ms = waiting for the host workers %.1f ms + upload + launch %.1f ms + wait for the device %.1f ms + stages above %.1f ms + footer / setup\n",
+                      now() - t_begin, t_prep, t_dev, t_sync, t_emit);
 }
 
 }  // namespace b200q
