@@ -92,7 +92,7 @@ bool may_match(const ExprP& e, const std::vector<int>& file_col_of, const PqFile
 }
 
 DevMemP upload(OpContext& cx, const void* p, size_t n, size_t pad = 16) {
-  DevMemP d = DevMem::alloc(n + pad, cx.stream, true);
+  DevMemP d = DevMem::alloc(n + pad, cx.stream);       // the pad is only ever over-read by the funnel-shift loads and masked out: no memset
   if (n) B200Q_CUDA(cudaMemcpyAsync(d->ptr, p, n, cudaMemcpyHostToDevice, cx.stream));
   cx.m.h2d_bytes += (int64_t)n;
   return d;
@@ -125,9 +125,11 @@ void pinned_free(void* p) { pinned_pool().put(p); }
 // host half of one column chunk: the file bytes, the decompressed page bodies (what the device reads) and the run tables
 struct PreparedChunk {
   ByteBuf raw, bytes, dict_bytes; std::vector<PqDevRun> lruns, vruns;
+  size_t dict_off = 0, dict_len = 0, runs_off = 0;          // bytes = page bodies ‖ dictionary ‖ level runs ‖ value runs: ONE pinned buffer, one DMA per chunk
+                                                            // (every extra stream operation costs ~10 us of engine hand-over, more than a MB of transfer)
   int32_t dict_count = 0; bool has_dict = false, any_null = false;
   std::string error; int error_code = 0;
-  PreparedChunk() { for (ByteBuf* b : {&raw, &bytes, &dict_bytes}) { b->alloc_fn = pinned_alloc; b->free_fn = pinned_free; } }
+  PreparedChunk() { for (ByteBuf* b : {&raw, &bytes}) { b->alloc_fn = pinned_alloc; b->free_fn = pinned_free; } }
 };
 
 void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs, const DType& want, int64_t rows, PreparedChunk& pc) {
@@ -136,7 +138,7 @@ void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs
   pc.lruns.clear(); pc.vruns.clear(); pc.has_dict = pc.any_null = false; pc.dict_count = 0; pc.error.clear(); pc.error_code = 0;
   pc.raw.clear();
   io.read(cc.start(), (size_t)cc.total_compressed_size, pc.raw.grow((size_t)cc.total_compressed_size));
-  pc.bytes.reserve((size_t)std::max<int64_t>(cc.total_uncompressed_size, cc.total_compressed_size) + 64);   // page bodies <= the chunk's uncompressed size: no regrowth of the pinned buffer
+  pc.bytes.reserve((size_t)std::max<int64_t>(cc.total_uncompressed_size, cc.total_compressed_size) + (256u << 10));   // page bodies <= the chunk's uncompressed size: no regrowth of the pinned buffer
   std::vector<PqPage> pages = parquet_read_pages(pc.raw.data(), pc.raw.size(), cc, cs, pc.bytes, pc.dict_bytes);
   int64_t row = 0, ord = 0;
   for (auto& pg : pages) if (pg.type != PQ_DICTIONARY_PAGE && !pg.def_runs.empty()) pc.any_null = true;
@@ -156,16 +158,27 @@ void prepare_chunk(FileIo& io, const PqColumnChunk& cc, const PqColumnSchema& cs
     }
     row += pg.num_values; ord += pg.non_null;
   }
+  auto align16 = [&] { static const uint8_t z[16] = {0}; pc.bytes.append(z, (16 - pc.bytes.size() % 16) % 16); };
+  align16(); pc.dict_off = pc.bytes.size(); pc.dict_len = pc.dict_bytes.size(); pc.bytes.append(pc.dict_bytes.data(), pc.dict_bytes.size());
+  align16(); pc.runs_off = pc.bytes.size();
+  pc.bytes.append((const uint8_t*)pc.lruns.data(), pc.lruns.size() * sizeof(PqDevRun));
+  pc.bytes.append((const uint8_t*)pc.vruns.data(), pc.vruns.size() * sizeof(PqDevRun));
   if (row != rows) throw ExecError(B200Q_ERR_EXECUTION, "parquet: column " + cs.name + " holds " + std::to_string(row) + " values, its row group " + std::to_string(rows) + " rows");
 }
 
 // device half: upload + expand -> one device column of `rows` rows
+double g_dbg_copy_ms = 0, g_dbg_kernel_ms = 0;     // B200Q_PARQUET_TIMING=2: serialised split of the device half (copies / kernels)
 DevColumn decode_chunk(OpContext& cx, const PreparedChunk& pc, const PqColumnSchema& cs, const DType& want, int64_t rows, DevMemP d_err) {
+  static const bool dbg = getenv("B200Q_PARQUET_TIMING") && atoi(getenv("B200Q_PARQUET_TIMING")) >= 2;
+  auto hnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double td0 = 0; if (dbg) { cudaStreamSynchronize(cx.stream); td0 = hnow(); }
   const bool any_null = pc.any_null;
   PqDecodeSpec sp{};
-  DevMemP d_bytes = upload(cx, pc.bytes.data(), pc.bytes.size()), d_vruns = upload(cx, pc.vruns.data(), pc.vruns.size() * sizeof(PqDevRun)), d_dict, d_lruns;
-  sp.bytes = (const uint8_t*)d_bytes->ptr; sp.value_runs = (const PqDevRun*)d_vruns->ptr; sp.n_value_runs = (int)pc.vruns.size();
-  if (pc.has_dict) { d_dict = upload(cx, pc.dict_bytes.data(), pc.dict_bytes.size()); sp.dict = (const uint8_t*)d_dict->ptr; sp.dict_count = pc.dict_count; }
+  DevMemP d_bytes = upload(cx, pc.bytes.data(), pc.bytes.size());
+  const PqDevRun* d_lruns = (const PqDevRun*)((const uint8_t*)d_bytes->ptr + pc.runs_off); const PqDevRun* d_vruns = d_lruns + pc.lruns.size();
+  sp.bytes = (const uint8_t*)d_bytes->ptr; sp.value_runs = d_vruns; sp.n_value_runs = (int)pc.vruns.size();
+  if (pc.has_dict) { sp.dict = (const uint8_t*)d_bytes->ptr + pc.dict_off; sp.dict_count = pc.dict_count; }
+  double td1 = 0; if (dbg) { cudaStreamSynchronize(cx.stream); td1 = hnow(); g_dbg_copy_ms += td1 - td0; }
   int out_w = want.byte_width();
   switch (cs.type) {
     case PQ_BOOLEAN: sp.src_width = 0; sp.out_kind = PQO_BOOL_BYTES; out_w = 1; break;
@@ -175,13 +188,12 @@ DevColumn decode_chunk(OpContext& cx, const PreparedChunk& pc, const PqColumnSch
     case PQ_DOUBLE: sp.src_width = 8; sp.out_kind = PQO_I64; break;
     default: sp.src_width = cs.type_length; sp.out_kind = PQO_DEC_FROM_FLBA; break;
   }
-  if (pc.has_dict && sp.src_width > 0 && (int64_t)pc.dict_bytes.size() < (int64_t)pc.dict_count * sp.src_width) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary page shorter than its entry count");
+  if (pc.has_dict && sp.src_width > 0 && (int64_t)pc.dict_len < (int64_t)pc.dict_count * sp.src_width) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary page shorter than its entry count");
   DevColumn col; col.type = want;
   DevMemP d_valid, d_ord;
   if (any_null) {
-    d_lruns = upload(cx, pc.lruns.data(), pc.lruns.size() * sizeof(PqDevRun));
     d_valid = DevMem::alloc((size_t)rows + 16, cx.stream);
-    cx.m.launches += launch_pq_levels((const uint8_t*)d_bytes->ptr, (const PqDevRun*)d_lruns->ptr, (int)pc.lruns.size(), rows, (uint8_t*)d_valid->ptr, cx.stream);
+    cx.m.launches += launch_pq_levels((const uint8_t*)d_bytes->ptr, d_lruns, (int)pc.lruns.size(), rows, (uint8_t*)d_valid->ptr, cx.stream);
     DevMemP fl = DevMem::alloc((size_t)rows * 4 + 16, cx.stream), sums = DevMem::alloc((size_t)scan_num_blocks(rows) * 4 + 16, cx.stream);
     d_ord = DevMem::alloc((size_t)(rows + 1) * 4, cx.stream);
     cx.m.launches += launch_bytes_to_flags((const uint8_t*)d_valid->ptr, rows, 0, (int32_t*)fl->ptr, cx.stream);
@@ -193,6 +205,7 @@ DevColumn decode_chunk(OpContext& cx, const PreparedChunk& pc, const PqColumnSch
   cx.m.launches += launch_pq_decode(sp, any_null ? (const uint8_t*)d_valid->ptr : nullptr, any_null ? (const int32_t*)d_ord->ptr : nullptr, rows, out->ptr, (int*)d_err->ptr, cx.stream);
   if (cs.type == PQ_BOOLEAN) { col.values = DevMem::alloc(bitmap_bytes(rows), cx.stream, true); cx.m.launches += launch_pack_valid((const uint8_t*)out->ptr, (uint32_t*)col.values->ptr, rows, cx.stream); }
   else col.values = out;
+  if (dbg) { cudaStreamSynchronize(cx.stream); g_dbg_kernel_ms += hnow() - td1; }
   return col;
 }
 
@@ -276,13 +289,27 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
       ~Pool() { { std::lock_guard<std::mutex> l(sh.mu); sh.stop = true; } sh.cv_free.notify_all(); for (auto& t : th) t.join(); }
     } pool{sh, {}};
     for (size_t i = 0; i < nthreads && ntasks; i++) pool.th.emplace_back(worker);
+    struct Events {                                 // one pair per ring slot: the row group's device work is awaited one row group later
+      std::vector<cudaEvent_t> a, b;
+      explicit Events(size_t n) : a(n), b(n) { for (size_t i = 0; i < n; i++) { B200Q_CUDA(cudaEventCreate(&a[i])); B200Q_CUDA(cudaEventCreate(&b[i])); } }
+      ~Events() { for (auto e : a) cudaEventDestroy(e); for (auto e : b) cudaEventDestroy(e); }
+    } ev(ring);
+    auto retire = [&](size_t rgi) {                 // row group rgi's uploads and kernels are done: its ring slot goes back to the workers
+      const double t = now();
+      B200Q_CUDA(cudaEventSynchronize(ev.b[rgi % ring]));
+      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, ev.a[rgi % ring], ev.b[rgi % ring])); cx.m.gpu_ms += ms; }
+      { std::lock_guard<std::mutex> l(sh.mu); sh.consumed = rgi + 1; }
+      sh.cv_free.notify_all();
+      t_sync += now() - t;
+    };
+    size_t in_flight = 0, next_retire = 0;
     for (size_t rgi = 0; rgi < todo.size() && remaining != 0; rgi++) {
       const PqRowGroup& rg = *todo[rgi];
       const double t0 = now();
       { std::unique_lock<std::mutex> l(sh.mu); sh.cv_done.wait(l, [&] { return sh.done[rgi] == (int)ncol; }); }
       const double t1 = now(); t_prep += t1 - t0;
       DevBatch b; b.num_rows = rg.num_rows;
-      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+      B200Q_CUDA(cudaEventRecord(ev.a[rgi % ring], cx.stream));
       for (size_t k = 0; k < ncol; k++) {
         const int pi = leaf.scan_projection[k];
         const FieldDef& f = leaf.scan_file_schema.fields[(size_t)pi];
@@ -298,26 +325,26 @@ void run_parquet_scan(OpContext& cx, const PlanNode& leaf, const std::function<v
         if (pc.error_code) throw ExecError(pc.error_code, pc.error);
         b.cols.push_back(decode_chunk(cx, pc, meta.columns[(size_t)fc], f.type, rg.num_rows, d_err));
       }
-      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
-      const double t2 = now(); t_dev += t2 - t1;
-      int err = 0;
-      B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));                      // the uploads of this row group have left the prepared buffers: its ring slot is free
-      { std::lock_guard<std::mutex> l(sh.mu); sh.consumed = rgi + 1; }
-      sh.cv_free.notify_all();
-      const double t3 = now(); t_sync += t3 - t2;
-      if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
-      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; }
+      B200Q_CUDA(cudaEventRecord(ev.b[rgi % ring], cx.stream));
+      in_flight = rgi + 1;
+      t_dev += now() - t1;
       if (remaining >= 0 && b.num_rows > remaining) b.num_rows = remaining;  // ScanLimit: a prefix of the row group (columns keep their buffers)
       if (remaining >= 0) remaining -= b.num_rows;
       cx.m.input_rows += b.num_rows; cx.m.input_batches++;
       const double t4 = now();
       emit(b);
       t_emit += now() - t4;
+      while (next_retire + 1 < in_flight) retire(next_retire++);          // the previous row group: its device work overlapped this one's host side
     }
+    while (next_retire < in_flight) retire(next_retire++);
+    int err = 0;
+    B200Q_CUDA(cudaMemcpyAsync(&err, d_err->ptr, 4, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    if (err) throw ExecError(B200Q_ERR_EXECUTION, "parquet: dictionary index out of range in " + sf.path);
   }
   if (timing) fprintf(stderr, "parquet scan: %.1f ms = waiting for the host workers %.1f ms + upload + launch %.1f ms + wait for the device %.1f ms + stages above %.1f ms + footer / setup\n",
                       now() - t_begin, t_prep, t_dev, t_sync, t_emit);
+  if (timing && g_dbg_copy_ms > 0) { fprintf(stderr, "  device half, serialised: uploads %.1f ms, allocations + kernels %.1f ms\n", g_dbg_copy_ms, g_dbg_kernel_ms); g_dbg_copy_ms = g_dbg_kernel_ms = 0; }
 }
 
 }  // namespace b200q

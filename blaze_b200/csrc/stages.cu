@@ -84,6 +84,7 @@ class FilterProjectStage : public Stage {
   CompiledProgram cp_;
   DevMemP d_prog_;
   bool has_filters_;
+  bool identity_ = false;            // no filter, output i = input column i: batches are forwarded as they are (no copy, no launch)
   bool lean_possible_ = false;
   LeanFpSpec lean_{};
 
@@ -124,6 +125,8 @@ class FilterProjectStage : public Stage {
   FilterProjectStage(OpContext& cx, const SchemaDef& in, const std::vector<ExprP>& filters, const std::vector<ExprP>& outs, const SchemaDef& out) {
     in_schema = in; out_schema = out;
     has_filters_ = !filters.empty();
+    identity_ = !has_filters_ && outs.size() == in.fields.size();
+    for (size_t i = 0; identity_ && i < outs.size(); i++) identity_ = outs[i]->kind == E_COLUMN && outs[i]->col_index == (int)i && outs[i]->type == in.fields[i].type;
     cp_ = compile_program(filters, outs, has_filters_);
     used_input_cols = cp_.used_cols;
     if (!cx.conf.force_generic_kernels) detect_lean(filters, outs);
@@ -136,6 +139,12 @@ class FilterProjectStage : public Stage {
     const int64_t n = in.num_rows;
     if (n == 0) return;
     if (n > 0x7FFFFFFFLL) throw ExecError(B200Q_ERR_UNSUPPORTED, "batches above 2^31-1 rows must be split by the caller");
+    if (identity_) {
+      bool plain = true;
+      auto ours = [](const DevMemP& m) { return !m || m->owned || m->owner; };          // borrowed caller memory (push_device) is only valid until the batch is released
+      for (auto& c : in.cols) plain = plain && c.offset == 0 && ours(c.values) && ours(c.validity) && ours(c.offsets);
+      if (plain) { outs.push_back(in); return; }
+    }
     ColTable ct{};
     for (size_t i = 0; i < cp_.used_cols.size(); i++) ct.col[i] = dev_col_of(in.cols[cp_.used_cols[i]]);
     OutTable ot{};
