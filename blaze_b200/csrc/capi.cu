@@ -137,6 +137,22 @@ static bool is_identity(const std::vector<ExprP>& cols, const SchemaDef& s) {
   return true;
 }
 
+static bool fusable_partial_final(const PlanNode& p, const PlanNode& f) {
+  static const bool off = getenv("B200Q_NO_AGG_FUSION") != nullptr;             // keeps the two-stage form reachable for tests
+  if (off || p.kind != N_AGG || f.kind != N_AGG) return false;
+  if (p.need_partial_merge || p.need_final_merge || !f.need_final_merge) return false;
+  if (p.aggs.size() != f.aggs.size() || p.group_exprs.size() != f.group_exprs.size()) return false;
+  for (size_t k = 0; k < f.group_exprs.size(); k++) {                            // the Final groups by the Partial's key columns, in order
+    const ExprP& g = f.group_exprs[k];
+    if (g->kind != E_COLUMN || g->col_index != (int)k || !(g->type == p.group_exprs[k]->type)) return false;
+  }
+  for (size_t a = 0; a < f.aggs.size(); a++) {
+    if (p.aggs[a].mode != MODE_PARTIAL || f.aggs[a].mode != MODE_FINAL) return false;
+    if (p.aggs[a].fn != f.aggs[a].fn || !(p.aggs[a].data_type == f.aggs[a].data_type)) return false;
+  }
+  return true;
+}
+
 static void build_pipeline(b200q_op* op) {
   std::vector<PlanNode*> chain;
   for (PlanNode* n = op->plan.get(); n; n = n->input.get()) chain.push_back(n);
@@ -157,7 +173,16 @@ static void build_pipeline(b200q_op* op) {
       std::vector<ExprP> gex; for (auto& g : n->group_exprs) gex.push_back(substitute(g, cur_cols));
       std::vector<std::vector<ExprP>> aargs;
       for (auto& a : n->aggs) { std::vector<ExprP> v; if (a.mode == MODE_PARTIAL) for (auto& e : a.args) v.push_back(substitute(e, cur_cols)); aargs.push_back(v); }
-      op->stages.push_back(make_agg_stage(op->cx, stage_in, filters, *n, gex, aargs));
+      // AggExec(Final) directly above AggExec(Partial) in the same op (Spark plans this when the child is already partitioned on the grouping keys):
+      // the Partial stage's table holds one entry per group, so a Final stage would only re-insert unique keys into a second table.  One stage
+      // accumulates from the raw inputs and emits the Final columns (AVG division, result types) straight from its table.
+      PlanNode fused;
+      const PlanNode* agg_node = n;
+      if (i + 1 < chain.size() && fusable_partial_final(*n, *chain[i + 1])) {
+        fused = *n; fused.need_final_merge = true; fused.schema = chain[i + 1]->schema;
+        agg_node = &fused; last = chain[i + 1]; i++;
+      }
+      op->stages.push_back(make_agg_stage(op->cx, stage_in, filters, *agg_node, gex, aargs));
       stage_in = op->stages.back()->out_schema;
       cur_cols = identity_cols(stage_in); filters.clear(); pending_tail = false;
     } else if (n->kind == N_SORT) {

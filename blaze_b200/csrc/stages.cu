@@ -477,7 +477,7 @@ class AggStage : public Stage {
     // capacity: any size (slot = mulhi(hash, capacity)); sized for a load of ~0.6 at the hinted group count so that
     // key area + accumulator area stay L2-resident; floor 2^20 keeps the slack above the load limit (0.3 * capacity)
     // larger than the concurrent-insert overshoot bound (resident threads ~ 303K)
-    capacity_ = std::max<uint64_t>(1ULL << 20, (uint64_t)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * 3);   // load <= 1/3 for the expected groups
+    capacity_ = std::max<uint64_t>(1ULL << 20, (uint64_t)((double)std::max<int64_t>(cx.conf.agg_initial_groups, 1) * cap_factor()));
     if (capacity_ >= (1ULL << 32)) throw PlanError(B200Q_ERR_UNSUPPORTED, "agg_initial_groups too large");
     alloc_table(cx, capacity_, keys_, accs_, counters_);
     if (lay_.nkeys == 0) seed_global_group(cx);
@@ -900,7 +900,13 @@ class AggStage : public Stage {
 
   // probe chains cost one dependent L2 round trip per extra slot: the table is kept at most half full (measured on
   // M1-hash: load 0.3 -> 6.7e10 rows/s, load 0.6 -> 5.6e10; only the sectors holding occupied slots are L2-resident)
-  static uint64_t load_limit(uint64_t cap) { return cap / 2; }
+  // experiment knobs (percent): slots per expected group, load limit
+  static double cap_factor() { static const double f = getenv("B200Q_AGG_CAP_PCT") ? atof(getenv("B200Q_AGG_CAP_PCT")) / 100.0 : 3.0; return f; }
+  static uint64_t load_limit(uint64_t cap) {
+    static const double l = getenv("B200Q_AGG_LOAD_PCT") ? atof(getenv("B200Q_AGG_LOAD_PCT")) / 100.0 : 0.5;
+    const uint64_t lim = (uint64_t)((double)cap * l);
+    return cap > (1ULL << 19) ? std::min<uint64_t>(lim, cap - (1ULL << 19)) : lim;      // slack above the limit > the concurrent-insert overshoot bound (resident threads)
+  }
 
   AggTable table_view(int deferred_idx) const {
     AggTable t{};
