@@ -1,5 +1,6 @@
 // Stage implementations: FilterProjectStage and AggStage (see runtime.h).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -256,6 +257,24 @@ static ExprP strip_noop_casts(ExprP e) {
   }
   return e;
 }
+
+// Small pinned host slots (counter snapshots).  cudaMallocHost / cudaFreeHost cost milliseconds once tens of GB are mapped in the process, so
+// ops never call them on their own: one pinned page per process, 32-byte slots, recycled.
+class PinnedSlots {
+  std::mutex mu_; std::vector<unsigned long long*> free_; 
+ public:
+  unsigned long long* get() {
+    std::lock_guard<std::mutex> l(mu_);
+    if (free_.empty()) {
+      unsigned long long* page = nullptr;
+      B200Q_CUDA(cudaMallocHost((void**)&page, 4096));
+      for (int i = 0; i < 4096 / 32; i++) free_.push_back(page + i * 4);
+    }
+    unsigned long long* p = free_.back(); free_.pop_back(); return p;
+  }
+  void put(unsigned long long* p) { std::lock_guard<std::mutex> l(mu_); free_.push_back(p); }
+};
+static PinnedSlots& pinned_slots() { static PinnedSlots* p = new PinnedSlots(); return *p; }
 
 class AggStage : public Stage {
   PlanNode node_;                       // copy of the Agg node (exprs already rewritten over the stage input)
@@ -794,14 +813,25 @@ class AggStage : public Stage {
     const int64_t sample = std::min<int64_t>(n, 1 << 22);
     // padded value range of every key column: [min - margin, max + margin] of the sample
     long long base[2] = {0, 0}; uint64_t span[2] = {1, 1}; long long nonnull = 0;
+    // ONE host round trip for the whole decision: the range kernels of every key and the skew probe are enqueued back to back, their results
+    // come back together
+    DevMemP d = DevMem::alloc(64, cx.stream);
+    { const long long init[8] = {INT64_MAX, INT64_MIN, 0, INT64_MAX, INT64_MIN, 0, 0, 0};
+      B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 64, cudaMemcpyHostToDevice, cx.stream)); }
+    for (int k = 0; k < fs_.nkeys; k++) cx.m.launches += launch_key_range(ct.col[fs_.key_col[k]], fs_.key_phys[k], sample, (long long*)d->ptr + 3 * k, cx.stream);
+    DevMemP hist;
+    const bool probe_skew = cx.conf.agg_hot_key_cache != 0;
+    if (probe_skew) {
+      hist = DevMem::alloc((65536 + 1) * 4, cx.stream, true);
+      DevCol kc[2] = {ct.col[fs_.key_col[0]], ct.col[fs_.key_col[fs_.nkeys == 2 ? 1 : 0]]};
+      cx.m.launches += launch_key_skew_probe(kc, fs_.key_phys, fs_.nkeys, sample, (unsigned*)hist->ptr, cx.stream);
+    }
+    long long hr[8] = {0}; unsigned mx = 0;
+    B200Q_CUDA(cudaMemcpyAsync(hr, d->ptr, 48, cudaMemcpyDeviceToHost, cx.stream));
+    if (probe_skew) B200Q_CUDA(cudaMemcpyAsync(&mx, (unsigned*)hist->ptr + 65536, 4, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
     for (int k = 0; k < fs_.nkeys; k++) {
-      DevMemP d = DevMem::alloc(24, cx.stream);
-      const long long init[3] = {INT64_MAX, INT64_MIN, 0};
-      B200Q_CUDA(cudaMemcpyAsync(d->ptr, init, 24, cudaMemcpyHostToDevice, cx.stream));
-      cx.m.launches += launch_key_range(ct.col[fs_.key_col[k]], fs_.key_phys[k], sample, (long long*)d->ptr, cx.stream);
-      long long h[3];
-      B200Q_CUDA(cudaMemcpyAsync(h, d->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+      const long long* h = hr + 3 * k;
       if (h[2] <= 0 || h[1] < h[0]) return;
       const unsigned __int128 range = (unsigned __int128)((__int128)h[1] - (__int128)h[0]) + 1;
       if (range > ((uint64_t)1 << 26)) return;
@@ -821,15 +851,8 @@ class AggStage : public Stage {
     dense_tab_ = DevMem::alloc((size_t)fs_.dense_cap * fs_.dense_stride * 8, cx.stream, true);
     fs_.dense_tab = (unsigned long long*)dense_tab_->ptr;
     fs_.dense = 1;
-    if (cx.conf.agg_hot_key_cache && fs_.dense_cap * fs_.dense_stride > 4096) {     // EXPERIMENTAL: do a few keys dominate the sample?
-      DevMemP hist = DevMem::alloc((65536 + 1) * 4, cx.stream, true);
-      DevCol kc[2] = {ct.col[fs_.key_col[0]], ct.col[fs_.key_col[fs_.nkeys == 2 ? 1 : 0]]};
-      cx.m.launches += launch_key_skew_probe(kc, fs_.key_phys, fs_.nkeys, sample, (unsigned*)hist->ptr, cx.stream);
-      unsigned mx = 0;
-      B200Q_CUDA(cudaMemcpyAsync(&mx, (unsigned*)hist->ptr + 65536, 4, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-      fs_.hot_cache = (uint64_t)mx * 256 > (uint64_t)sample ? 1 : 0;          // one hash bucket holds > 0.4 % of the rows
-    }
+    if (probe_skew && fs_.dense_cap * fs_.dense_stride > 4096)                 // do a few keys dominate the sample?  one hash bucket holds > 0.4 % of the rows
+      fs_.hot_cache = (uint64_t)mx * 256 > (uint64_t)sample ? 1 : 0;
   }
 
   // LEAN kernels: every referenced column is a non-null, 32-byte aligned int64 column
@@ -938,36 +961,97 @@ class AggStage : public Stage {
     cx.m.num_groups = ngroups_;
   }
 
-  void update_rows(OpContext& cx, const ColTable& ct, int64_t n) {
-    const int64_t chunk = std::max<int64_t>(1 << 16, std::min<int64_t>(cx.conf.max_launch_rows, 0x7FFFFFFFLL));
-    for (int64_t begin = 0; begin < n; begin += chunk) {
-      const int64_t m = std::min(chunk, n - begin);
-      if (deferred_cap_ < m) {
-        deferred_cap_ = m;
-        deferred_[0] = DevMem::alloc((size_t)m * 4, cx.stream);
-        deferred_[1] = DevMem::alloc((size_t)m * 4, cx.stream);
-      }
-      B200Q_CUDA(cudaEventRecord(cx.ev0, cx.stream));
-      cx.m.launches += launch_update(cx, ct, table_view(0), begin, m, nullptr);
-      B200Q_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+  // The counters of a chunk (groups, deferred rows, error flags) are copied into a pinned snapshot right behind its kernel and read
+  // while the NEXT chunk's kernel already runs: no host round trip between the launches of a batch.
+  struct Snap { unsigned long long* h = nullptr; cudaEvent_t ready = nullptr, k0 = nullptr, k1 = nullptr; };
+  Snap snap_[2];
+ public:
+  ~AggStage() override { for (auto& s : snap_) { if (s.h) pinned_slots().put(s.h); if (s.ready) cudaEventDestroy(s.ready); if (s.k0) cudaEventDestroy(s.k0); if (s.k1) cudaEventDestroy(s.k1); } }
+  void ensure_snaps() {
+    if (snap_[0].h) return;
+    for (auto& s : snap_) {
+      s.h = pinned_slots().get();
+      B200Q_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming)); B200Q_CUDA(cudaEventCreate(&s.k0)); B200Q_CUDA(cudaEventCreate(&s.k1));
+    }
+  }
+  void account(OpContext& cx, const Snap& s, int64_t rows) {
+    float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, s.k0, s.k1));
+    cx.m.gpu_ms += ms; if (cx.cur_stage == 0) { cx.m.hot_ms += ms; cx.m.hot_rows += rows; cx.m.hot_launches++; }
+  }
+  // rows of [begin, ...) that could not be inserted (the table was at its load limit): grow, then replay only those rows
+  void replay(OpContext& cx, const ColTable& ct, int64_t begin, const uint32_t* list, uint64_t ndef, bool grow_first) {
+    int wr = list == (const uint32_t*)deferred_[0]->ptr ? 1 : 0;          // new deferrals go to the buffer the list does not live in
+    while (ndef > 0) {
+      if (grow_first) grow(cx, (uint64_t)ngroups_ + ndef);
+      grow_first = true;
+      B200Q_CUDA(cudaMemsetAsync((uint8_t*)counters_->ptr + 8, 0, 8, cx.stream));
+      cx.m.launches += launch_update(cx, ct, table_view(wr), begin, (int64_t)ndef, list);
       B200Q_CUDA(cudaGetLastError());
       unsigned long long h[3];
       read_counters(cx, h);
-      { float ms = 0; B200Q_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1)); cx.m.gpu_ms += ms; if (cx.cur_stage == 0) { cx.m.hot_ms += ms; cx.m.hot_rows += m; cx.m.hot_launches++; } }
-      int cur = 0;
-      while (h[1] > 0) {
-        // the table hit its load limit: grow it, then replay only the rows that could not be inserted
-        const uint64_t ndef = h[1];
-        grow(cx, (uint64_t)ngroups_ + ndef);
-        B200Q_CUDA(cudaMemsetAsync((uint8_t*)counters_->ptr + 8, 0, 8, cx.stream));
-        // counters_ is new after grow(): ngroups was recounted by the rehash, deferred/err start at 0
-        AggTable t = table_view(cur ^ 1);
-        cx.m.launches += launch_update(cx, ct, t, begin, (int64_t)ndef, (const uint32_t*)deferred_[cur]->ptr);
-        B200Q_CUDA(cudaGetLastError());
-        cur ^= 1;
-        read_counters(cx, h);
-      }
+      ndef = h[1]; list = (const uint32_t*)deferred_[wr]->ptr; wr ^= 1;
     }
+  }
+
+  void update_rows(OpContext& cx, const ColTable& ct, int64_t n) {
+    const int64_t chunk = std::max<int64_t>(1 << 16, std::min<int64_t>(cx.conf.max_launch_rows, 0x7FFFFFFFLL));
+    static const bool dbg = getenv("B200Q_AGG_TIMING") != nullptr;
+    auto hnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tA = hnow();
+    ensure_snaps();
+    const double tB = hnow();
+    const int64_t m_max = std::min(chunk, n);
+    if (deferred_cap_ < 2 * m_max) {                                      // two chunks' worth: a chunk is launched before the counters of the one before it are back
+      deferred_cap_ = 2 * m_max;
+      deferred_[0] = DevMem::alloc((size_t)deferred_cap_ * 4, cx.stream);
+      deferred_[1] = DevMem::alloc((size_t)deferred_cap_ * 4, cx.stream);
+    }
+    const double tC = hnow(); double t_launch = 0, t_settle = 0;
+    int64_t prev_begin = 0, prev_m = 0; bool have_prev = false;
+    int idx = 0;
+    // settles the chunk whose snapshot is snap_[pi]; `cur` (when >= 0): the chunk launched behind it, whose snapshot is snap_[pi ^ 1]
+    auto settle = [&](int pi, int64_t pb, int64_t pm, bool cur_in_flight, int64_t cb, int64_t cm) -> bool {
+      Snap& sp = snap_[pi];
+      B200Q_CUDA(cudaEventSynchronize(sp.ready));
+      account(cx, sp, pm);
+      check_device_error_flags((int)sp.h[2]);
+      ngroups_ = (int64_t)sp.h[0]; cx.m.num_groups = ngroups_;
+      const uint64_t d_prev = sp.h[1];
+      if (d_prev == 0) return false;
+      // slow path: the table hit its load limit.  The chunk behind (if any) appended its own deferred rows after ours.
+      uint64_t d_cur = 0; DevMemP list_cur;
+      if (cur_in_flight) {
+        Snap& sc = snap_[pi ^ 1];
+        B200Q_CUDA(cudaEventSynchronize(sc.ready));
+        account(cx, sc, cm);
+        check_device_error_flags((int)sc.h[2]);
+        ngroups_ = (int64_t)sc.h[0]; cx.m.num_groups = ngroups_;
+        d_cur = sc.h[1] - d_prev;
+        if (d_cur) { list_cur = DevMem::alloc((size_t)d_cur * 4, cx.stream); B200Q_CUDA(cudaMemcpyAsync(list_cur->ptr, (const uint32_t*)deferred_[0]->ptr + d_prev, (size_t)d_cur * 4, cudaMemcpyDeviceToDevice, cx.stream)); }
+      }
+      replay(cx, ct, pb, (const uint32_t*)deferred_[0]->ptr, d_prev, true);
+      if (d_cur) replay(cx, ct, cb, (const uint32_t*)list_cur->ptr, d_cur, false);
+      return true;
+    };
+    for (int64_t begin = 0; begin < n; begin += chunk, idx++) {
+      const int64_t m = std::min(chunk, n - begin);
+      Snap& s = snap_[idx & 1];
+      const double tl = hnow();
+      B200Q_CUDA(cudaEventRecord(s.k0, cx.stream));
+      cx.m.launches += launch_update(cx, ct, table_view(0), begin, m, nullptr);
+      B200Q_CUDA(cudaEventRecord(s.k1, cx.stream));
+      B200Q_CUDA(cudaGetLastError());
+      B200Q_CUDA(cudaMemcpyAsync(s.h, counters_->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+      B200Q_CUDA(cudaEventRecord(s.ready, cx.stream));
+      const double ts = hnow(); t_launch += ts - tl;
+      const bool slow = have_prev && settle((idx & 1) ^ 1, prev_begin, prev_m, true, begin, m);
+      t_settle += hnow() - ts;
+      if (slow) { have_prev = false; continue; }                          // the slow path settled this chunk too
+      prev_begin = begin; prev_m = m; have_prev = true;
+    }
+    const double tD = hnow();
+    if (have_prev) settle((idx & 1) ^ 1, prev_begin, prev_m, false, 0, 0);
+    if (dbg) fprintf(stderr, "update_rows: snaps %.3f ms, deferred buffers %.3f ms, launches %.3f ms, settles %.3f ms, last settle %.3f ms (%d chunks)\n", tB - tA, tC - tB, t_launch, t_settle, hnow() - tD, idx);
   }
 
   void push(OpContext& cx, DevBatch& in, std::vector<DevBatch>&) override {

@@ -87,6 +87,17 @@ def test_table_growth_many_groups():
     assert plan.last_metrics["table_grow_count"] >= 0
 
 
+@pytest.mark.parametrize("n,launch_rows", [(1_500_000, 1 << 16), (700_000, 200_000)])
+def test_table_growth_while_the_next_launch_is_in_flight(n, launch_rows):
+    # a batch is cut into launches that are enqueued back to back; the counters of launch i are read while launch i + 1 runs, so when the
+    # table hits its load limit TWO launches hold deferred rows: both are replayed (stages.cu update_rows / settle)
+    rb = m1_batch(n, 2**40, 47)
+    specs = [("s", E.AGG_SUM, [E.Column("v")], T.int64), ("c", E.AGG_COUNT, [E.Column("v")], T.int64)]
+    conf = native.default_conf(agg_initial_groups=1024, staging_rows=0, max_launch_rows=launch_rows)
+    got, plan = run_partial_final(rb, ["k"], specs, batch_rows=n, conf=conf)
+    assert plan.last_metrics["table_grow_count"] >= 1
+
+
 def test_two_keys_filter_fused_q1_shape():
     n = 250_000
     rng = np.random.default_rng(46)
