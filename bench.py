@@ -215,6 +215,19 @@ class Runner:
                 self.last = self._pull_all_device(op)
                 self._acc(op.metrics())
             return
+        if os.environ.get("B200Q_BENCH_PHASES"):                                               # N > 1: partial op / exchange / final op (host clock, synchronised)
+            t = [time.perf_counter()]
+            def lap(): self.torch.cuda.synchronize(); t.append(time.perf_counter())
+            part = self._partial_device(); lap()
+            out, schema = part
+            recv = self.ex.shuffle(schema, out, self.plans["nkeys"]); lap()
+            with native.NativeOp(self.plans["final_col"], self.conf_col, self.local) as op:
+                lap(); op.push_device_array(recv); lap(); op.finish(); lap(); res = op.pull_device(); self._acc(op.metrics(), hot=False); lap()
+            lap()
+            names = ["partial op (create..destroy)", "exchange", "final create", "final push", "final finish", "final pull", "final destroy"]
+            if self.rank == 0: sys.stderr.write("phases[%s N=%d] " % (self.w, self.world) + ", ".join(f"{n}={1e3 * (b - a):.3f}ms" for n, a, b in zip(names, t, t[1:])) + "\n")
+            self.last = [res]
+            return
         self.last = [self._exchange_and_final(self._partial_device())]
 
     def _partial_device(self):
