@@ -430,7 +430,7 @@ def extra_shuffle_and_join(torch, dist, native, world, local, dev, rows, steps, 
     out.append({"workload": WORKLOADS["M4"], "value": rows * world / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "rows_per_gpu": rows, "verified": ok4,
                 "verification": "output rows == probe rows (every key matches a unique map key) and SUM(d_year) over the output == SUM(1900 + sk // 366) over the probe side",
                 "gpu_launches": st["all"], "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                                                        "kernel": "join_probe_pairs_kernel + join_gather_kernel x 7 (per 2^24-row probe chunk)", "launches": st["launches"],
+                                                        "kernel": "join_probe_count_kernel + join_probe_fused_kernel (per 2^26-row probe chunk)", "launches": st["launches"],
                                                         "avg_launch_ms": st["ns"] / max(1, st["launches"]) / 1e6, "alg_bytes_per_row": ALG_BYTES_PER_ROW["M4"]}})
     return out, ok3, ok4
 

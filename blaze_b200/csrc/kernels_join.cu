@@ -23,6 +23,9 @@ namespace b200q {
 namespace {
 
 constexpr int JB = 256;
+#ifndef JOIN_MIN_CTAS
+#define JOIN_MIN_CTAS 4       // the probe kernels are latency-bound (ncu: 34 % warps active at 70-80 registers): cap the registers for 4 CTAs per SM
+#endif
 
 int jgrid(int64_t n, int per_block = JB * 4) {
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(JB) join_pack_kernel(const JoinTable t) {
   }
 }
 
-__global__ void __launch_bounds__(JB) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count,
+__global__ void __launch_bounds__(JB, JOIN_MIN_CTAS) join_probe_count_kernel(const JoinKeys k, long long n, const JoinTable t, int probe_outer, uint32_t* __restrict__ head, int32_t* __restrict__ count,
                                                               unsigned long long* total) {
   // 8 rows per thread and step: the eight key loads, then the eight table probes, are independent of each other — with one row per
   // thread the kernel is latency-bound (16 KB of key loads in flight per SM, measured 4.4e10 rows/s)
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(JB) join_gather_multi_kernel(const GatherSpec 
 // ROW order, one atomic per 2048-row tile reserves the tile's output rows, and the probe-side columns are copied (coalesced in,
 // coalesced out) and the map-side columns gathered (L2-resident dimension table) straight into the output columns — no index
 // vectors at all.  `total` rows were counted by a first pass (join_probe_pairs_kernel without outputs), so the outputs are exact.
-__global__ void __launch_bounds__(JB) join_probe_fused_kernel(const uint32_t* __restrict__ head, long long n, int probe_outer, unsigned long long* cursor,
+__global__ void __launch_bounds__(JB, JOIN_MIN_CTAS) join_probe_fused_kernel(const uint32_t* __restrict__ head, long long n, int probe_outer, unsigned long long* cursor,
                                                               const GatherSpec pc, const GatherSpec bc, uint8_t* mark) {
   __shared__ unsigned s_cnt[JP_ROWS * (JB / 32) + 1];
   __shared__ unsigned long long s_base;
