@@ -980,7 +980,10 @@ class AggStage : public Stage {
   }
   // rows of [begin, ...) that could not be inserted (the table was at its load limit): grow, then replay only those rows
   void replay(OpContext& cx, const ColTable& ct, int64_t begin, const uint32_t* list, uint64_t ndef, bool grow_first) {
-    int wr = list == (const uint32_t*)deferred_[0]->ptr ? 1 : 0;          // new deferrals go to the buffer the list does not live in
+    // new deferrals go to the buffer the list does not live in; the second buffer only exists once a replay needs it (the slow path is rare, and
+    // a buffer is 8 bytes per row of a launch)
+    if (!deferred_[1] || deferred_[1]->bytes < (size_t)deferred_cap_ * 4) deferred_[1] = DevMem::alloc((size_t)deferred_cap_ * 4, cx.stream);
+    int wr = list == (const uint32_t*)deferred_[0]->ptr ? 1 : 0;
     while (ndef > 0) {
       if (grow_first) grow(cx, (uint64_t)ngroups_ + ndef);
       grow_first = true;
@@ -1004,7 +1007,7 @@ class AggStage : public Stage {
     if (deferred_cap_ < 2 * m_max) {                                      // two chunks' worth: a chunk is launched before the counters of the one before it are back
       deferred_cap_ = 2 * m_max;
       deferred_[0] = DevMem::alloc((size_t)deferred_cap_ * 4, cx.stream);
-      deferred_[1] = DevMem::alloc((size_t)deferred_cap_ * 4, cx.stream);
+      deferred_[1] = nullptr;
     }
     const double tC = hnow(); double t_launch = 0, t_settle = 0;
     int64_t prev_begin = 0, prev_m = 0; bool have_prev = false;
