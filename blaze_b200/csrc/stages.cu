@@ -1096,29 +1096,23 @@ class AggStage : public Stage {
   }
 
   void finish(OpContext& cx, std::vector<DevBatch>& outs) override {
-    unsigned long long h[3];
-    read_counters(cx, h);
-    int64_t g = ngroups_;
-    if (fs_.dense) {
-      DevMemP dc = DevMem::alloc(8, cx.stream, true);
-      cx.m.launches += launch_dense_count(fs_, (unsigned long long*)dc->ptr, cx.stream);
-      unsigned long long hc = 0;
-      B200Q_CUDA(cudaMemcpyAsync(&hc, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-      g += (int64_t)hc;
-      cx.m.num_groups = g;
-    }
+    // ONE host round trip for the group counts: the hash table's counters and the occupied entries of the dense / wide table land in one pinned slot
     const bool wide = wide_possible_ && ws_.dense_tab;
-    if (wide) {
-      cx.m.launches += launch_tile_wide_normalise(ws_, cx.stream);
-      DevMemP dc = DevMem::alloc(8, cx.stream, true);
-      cx.m.launches += launch_tile_wide_count(ws_, (unsigned long long*)dc->ptr, cx.stream);
-      unsigned long long hc = 0;
-      B200Q_CUDA(cudaMemcpyAsync(&hc, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
-      B200Q_CUDA(cudaStreamSynchronize(cx.stream));
-      g += (int64_t)hc;
-      cx.m.num_groups = g;
-    }
+    ensure_snaps();
+    unsigned long long* hs = snap_[0].h;
+    DevMemP dc;
+    if (fs_.dense || wide) {
+      dc = DevMem::alloc(8, cx.stream, true);
+      if (wide) cx.m.launches += launch_tile_wide_normalise(ws_, cx.stream);
+      cx.m.launches += fs_.dense ? launch_dense_count(fs_, (unsigned long long*)dc->ptr, cx.stream) : launch_tile_wide_count(ws_, (unsigned long long*)dc->ptr, cx.stream);
+      B200Q_CUDA(cudaMemcpyAsync(hs + 3, dc->ptr, 8, cudaMemcpyDeviceToHost, cx.stream));
+    } else hs[3] = 0;
+    B200Q_CUDA(cudaMemcpyAsync(hs, counters_->ptr, 24, cudaMemcpyDeviceToHost, cx.stream));
+    B200Q_CUDA(cudaStreamSynchronize(cx.stream));
+    check_device_error_flags((int)hs[2]);
+    ngroups_ = (int64_t)hs[0];
+    const int64_t g = ngroups_ + (int64_t)hs[3];
+    cx.m.num_groups = g;
     if (g == 0) return;                                             // no records (agg_table.rs:154-156)
     EmitTable et{}; et.ncols = (int)emit_.size();
     if (et.ncols > EMIT_MAX_COLS) throw ExecError(B200Q_ERR_UNSUPPORTED, "too many output columns");
