@@ -227,28 +227,54 @@ size_t snappy_uncompress(const uint8_t* src, size_t n, ByteBuf& out) {
   while (true) { if (ip >= n) bad("snappy: truncated preamble"); const uint8_t b = src[ip++]; ulen |= (uint64_t)(b & 0x7F) << shift; if (!(b & 0x80)) break; shift += 7; if (shift > 35) bad("snappy: bad preamble"); }
   if (ulen > (uint64_t)1 << 31) bad("snappy: block above 2 GiB");
   uint8_t* const dst = out.grow((size_t)ulen);
+  const size_t olen = (size_t)ulen;
   size_t op = 0;
-  while (ip < n) {
+  // one element with every bound checked (the tail of the block, long literals, overlapping copies)
+  auto careful = [&]() {
     const uint8_t tag = src[ip++];
     size_t len, offset;
     switch (tag & 3) {
       case 0: {
         len = (size_t)(tag >> 2) + 1;
         if (len > 60) { const size_t nb = len - 60; if (ip + nb > n) bad("snappy: truncated literal length"); len = 0; for (size_t i = 0; i < nb; i++) len |= (size_t)src[ip + i] << (8 * i); len += 1; ip += nb; }
-        if (ip + len > n || op + len > (size_t)ulen) bad("snappy: literal overruns the buffer");
+        if (ip + len > n || op + len > olen) bad("snappy: literal overruns the buffer");
         memcpy(dst + op, src + ip, len); ip += len; op += len;
-        continue;
+        return;
       }
       case 1: if (ip + 1 > n) bad("snappy: truncated copy"); len = (size_t)((tag >> 2) & 7) + 4; offset = ((size_t)(tag >> 5) << 8) | src[ip]; ip += 1; break;
       case 2: if (ip + 2 > n) bad("snappy: truncated copy"); len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip] | ((size_t)src[ip + 1] << 8); ip += 2; break;
       default: if (ip + 4 > n) bad("snappy: truncated copy"); len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24); ip += 4; break;
     }
-    if (offset == 0 || offset > op || op + len > (size_t)ulen) bad("snappy: copy outside the buffer");
-    if (offset >= len) memcpy(dst + op, dst + op - offset, len);
-    else for (size_t i = 0; i < len; i++) dst[op + i] = dst[op - offset + i];        // overlapping copy: byte-wise (run-length patterns)
+    if (offset == 0 || offset > op || op + len > olen) bad("snappy: copy outside the buffer");
+    uint8_t* d = dst + op; const uint8_t* s = d - offset;
+    if (offset >= len) memcpy(d, s, len);
+    else for (size_t i = 0; i < len; i++) d[i] = s[i];              // overlapping copy: byte-wise (run-length patterns)
     op += len;
+  };
+  // Fast loop (the usual Snappy decoder tricks): while at least 21 input bytes and 80 output bytes remain, short literals move one 16-byte block
+  // and copies with offset >= 8 move 8-byte blocks (they never read what they are about to write).  The blocks may write up to 15 bytes past
+  // the element: that slop lies inside this block's output and is overwritten by the elements that follow.
+  while (ip + 21 <= n && op + 80 <= olen) {
+    const uint8_t tag = src[ip];
+    const unsigned kind = tag & 3;
+    if (kind == 0) {
+      const size_t len = (size_t)(tag >> 2) + 1;
+      if (len > 16) { careful(); continue; }
+      memcpy(dst + op, src + ip + 1, 16); ip += 1 + len; op += len;
+      continue;
+    }
+    size_t len, offset, adv;
+    if (kind == 1) { len = (size_t)((tag >> 2) & 7) + 4; offset = ((size_t)(tag >> 5) << 8) | src[ip + 1]; adv = 2; }
+    else if (kind == 2) { len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip + 1] | ((size_t)src[ip + 2] << 8); adv = 3; }
+    else { len = (size_t)(tag >> 2) + 1; offset = (size_t)src[ip + 1] | ((size_t)src[ip + 2] << 8) | ((size_t)src[ip + 3] << 16) | ((size_t)src[ip + 4] << 24); adv = 5; }
+    if (offset < 8 || offset > op) { careful(); continue; }         // overlapping pattern or a bad offset: the checked path decides
+    uint8_t* d = dst + op; const uint8_t* s = d - offset;           // len <= 64, op + 80 <= olen: the 8-byte blocks stay inside the output
+    memcpy(d, s, 8); memcpy(d + 8, s + 8, 8);
+    for (size_t i = 16; i < len; i += 8) memcpy(d + i, s + i, 8);
+    ip += adv; op += len;
   }
-  if (op != (size_t)ulen) bad("snappy: decompressed size mismatch");
+  while (ip < n) careful();
+  if (op != olen) bad("snappy: decompressed size mismatch");
   return op;
 }
 

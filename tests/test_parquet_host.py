@@ -50,6 +50,35 @@ def test_snappy_decoder_reads_what_a_conforming_encoder_writes(kind):
     assert native.snappy_uncompress(comp, len(data)) == data
 
 
+def test_snappy_decoder_fuzz_against_the_conforming_codec():
+    # the decoder's fast loop moves 16 / 8-byte blocks with slop: many shapes (short periods = overlapping copies, long literals, column-like
+    # integers, sizes around the fast-loop margins) against pyarrow's codec; truncated and bit-flipped streams must fail or decode, never crash
+    rng = np.random.default_rng(12)
+    shapes = []
+    for n in [0, 1, 5, 15, 16, 17, 20, 21, 22, 63, 64, 65, 79, 80, 81, 100, 1000, 4097, 70_001]:
+        shapes.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        shapes.append(bytes(rng.integers(0, 4, n, dtype=np.uint8)))
+        for period in (1, 2, 3, 7, 8, 9, 15, 16, 17):
+            shapes.append((bytes(rng.integers(0, 256, period, dtype=np.uint8)) * (n // period + 1))[:n])
+    for bits, dt in ((21, np.int64), (11, np.int32), (40, np.int64), (7, np.int16)):
+        shapes.append(rng.integers(0, 1 << bits, 50_000).astype(dt).tobytes())
+        shapes.append(np.sort(rng.integers(0, 1 << bits, 50_000)).astype(dt).tobytes())
+    for data in shapes:
+        comp = pa.compress(data, codec="snappy", asbytes=True)
+        assert native.snappy_uncompress(comp, len(data)) == data
+    data = rng.integers(0, 1 << 21, 4000).astype(np.int64).tobytes()
+    comp = bytearray(pa.compress(data, codec="snappy", asbytes=True))
+    for cut in range(1, len(comp), 37):                                          # truncations: an error, never a crash
+        with pytest.raises(native.NativeError):
+            native.snappy_uncompress(bytes(comp[:cut]), len(data))
+    for _ in range(300):                                                         # bit flips: either an error or SOME output of the declared size
+        c = bytearray(comp); i = int(rng.integers(1, len(c))); c[i] ^= 1 << int(rng.integers(0, 8))
+        try:
+            native.snappy_uncompress(bytes(c), len(data) + 64)
+        except native.NativeError:
+            pass
+
+
 def test_corrupt_inputs_fail_cleanly():
     with pytest.raises(native.NativeError):
         native.snappy_uncompress(b"\xff\xff\xff\xff\x0f\x00", 16)               # claims 4 GiB, then a literal that overruns
